@@ -1,0 +1,172 @@
+/*
+ * fitoct_b200.h — C ABI of the B200-native batched NUTS engine for the FitOCT decay models.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / R / C++ types.  Every entry point
+ * cites the reference interface it replaces (paths are relative to the upstream rbocheux/FitOCT tree).
+ * The mathematics is frozen in MODEL_SPEC.md; the reference-side binding (R `.Call` shim) is shown in
+ * INTEGRATION.md and r-pkg/.
+ *
+ * Conventions
+ *   - all floating point data is IEEE fp64, row-major, caller-owned; the library allocates nothing the
+ *     caller must free except opaque `foct_plan` handles (freed with foct_plan_destroy);
+ *   - every function returns 0 on success, a negative FOCT_E* code on failure; the message is available
+ *     from foct_last_error() (thread-local);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with FOCT_ENODEV.
+ */
+#ifndef FITOCT_B200_H
+#define FITOCT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FOCT_ABI_VERSION 1
+
+#define FOCT_MAX_D 32        /* unconstrained dimensions live one-per-lane in a warp */
+#define FOCT_MAX_NN 27       /* => D = Nn + 5 <= 32 (reference UI range is 5..20, ShinyInterface/ui.R:200-207) */
+#define FOCT_MAX_CHAINS 8
+#define FOCT_N_SAMPLER_PARAMS 6 /* accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__ */
+#define FOCT_N_SUMMARY_COLS 11  /* mean, se_mean, sd, 2.5%, 25%, 50%, 75%, 97.5%, n_eff, Rhat (rstan::summary), Bulk_ESS */
+
+/* error codes */
+#define FOCT_OK 0
+#define FOCT_EINVAL (-1)  /* bad argument */
+#define FOCT_ENODEV (-2)  /* no CUDA device / driver: the product has no CPU path */
+#define FOCT_ECUDA (-3)   /* CUDA runtime error */
+#define FOCT_ENOMEM (-4)
+
+/* model kinds */
+#define FOCT_EXPGP 0   /* replaces FitOCTLib::fitExpGP   (FitOCT.R:110-124, priPost.R:2-16, server.R:408-426) */
+#define FOCT_MONOEXP 1 /* replaces FitOCTLib::fitMonoExp (FitOCT.R:95, server.R:341-343) */
+
+/* gridType (ShinyInterface/ui.R:211-218, server.R:626-635) */
+#define FOCT_GRID_INTERNAL 0
+#define FOCT_GRID_EXTREMAL 1
+
+/* MODEL_SPEC.md §8 switch table.  Defaults from foct_model_spec_default(). */
+typedef struct foct_model_spec {
+  int modulation;    /* 0 = length (synthData.R:22), 1 = amplitude */
+  int kernel;        /* 0 = stan_exp_quad exp(-d^2/(2 rho^2)), 1 = rmgauss exp(-d^2/rho^2) (server.R:648) */
+  double jitter;     /* added to diag(Kgg); default 1e-9 */
+  int ygp_prior;     /* 0 = normal(0, lambda), 1 = laplace(0, lambda) (Tests/lassoPrior.stan) */
+  int lambda_prior;  /* 0 = gamma(2, lambda_rate), 1 = exponential(lambda_rate) (Tests/testGamma.R:27) */
+  double sigma_mean; /* prior on the noise factor sigma: normal(sigma_mean, sigma_sd); sigma_sd <= 0 => flat */
+  double sigma_sd;
+  int theta_prior;   /* 0 = multi_normal(theta0, Sigma0), 1 = flat */
+  int br_ndf;        /* 0 = N - n_params_of_mean, 1 = N */
+} foct_model_spec;
+
+/* One depth profile + the knobs the reference passes to fitExpGP (FitOCT.R:110-124). */
+typedef struct foct_problem {
+  int N;            /* points in this profile (ragged batches allowed) */
+  const double* x;  /* depth                         (FitOCT.R:84-86) */
+  const double* y;  /* signal */
+  const double* uy; /* signal uncertainty from estimateNoise (FitOCT.R:89-90) */
+  int dataType;     /* 1 amplitude / 2 intensity     (FitOCT.R:39,112) */
+  int Nn;           /* control points; must be uniform over a batch; ignored for FOCT_MONOEXP */
+  int gridType;     /* FOCT_GRID_*                   (FitOCT.R:114) */
+  double rho;       /* GP length scale, already resolved by the caller (0 => 1/Nn done in R, FitOCT.R:119) */
+  double lambda_rate;
+  double theta0[3]; /* prior mean                    (FitOCT.R:116) */
+  double Sigma0[9]; /* prior covariance, row-major   (FitOCT.R:117) */
+  int prior_PD;     /* 1 => likelihood switched off  (FitOCT.R:122, priPost.R:14) */
+  long long id;     /* RNG stream id of this profile: results do not depend on batch order or GPU count */
+} foct_problem;
+
+/* Sampler controls.  The reference exposes only nb_warmup / nb_iter (FitOCT.R:120-121); the rest are the
+ * rstan `sampling(control=...)` knobs FitOCTLib hard-codes (unknown, SURVEY a-7) — rstan defaults here. */
+typedef struct foct_sampler_cfg {
+  int chains;              /* default 4 (server.R:469) */
+  int n_warmup;            /* nb_warmup */
+  int n_iter;              /* nb_iter = nb_warmup + nb_sample, as FitOCT.R:121 passes it */
+  double adapt_delta;      /* 0.8 */
+  int max_treedepth;       /* 10 */
+  double stepsize0;        /* 1.0 */
+  unsigned long long seed; /* FitOCT.R:15 seeds R; rstan then draws its seed from R's RNG */
+  int init_mode;           /* MODEL_SPEC §7: 0 prior-centred, 1 U(-2,2), 2 caller-supplied */
+  const double* init;      /* [n_problems][chains][D] unconstrained, only for init_mode == 2 */
+  int save_warmup;         /* 1 => draws include warm-up (plotExpGP.R:46 traceplot(inc_warmup=TRUE)) */
+  /* adaptation constants (0 => Stan defaults 0.05 / 0.75 / 10 / 75 / 50 / 25) */
+  double gamma, kappa, t0;
+  int init_buffer, term_buffer, window;
+  /* devices to shard profiles over (independent shards, no collective); n_devices == 0 => current device */
+  int n_devices;
+  const int* devices;
+} foct_sampler_cfg;
+
+/* Caller-allocated outputs; any pointer may be NULL to skip that output.
+ * n_saved = save_warmup ? n_iter : n_iter - n_warmup. */
+typedef struct foct_result {
+  double* draws;          /* [n_problems][n_saved][chains][P_out]  constrained, MODEL_SPEC §6 column order */
+  double* sampler_params; /* [n_problems][n_saved][chains][6] */
+  double* summary;        /* [n_problems][P_out][FOCT_N_SUMMARY_COLS] over post-warm-up draws, all chains */
+  double* stepsize;       /* [n_problems][chains] adapted step size */
+  double* inv_metric;     /* [n_problems][chains][D] adapted diagonal inverse metric */
+  double* n_leapfrog;     /* [n_problems][chains][2] total leapfrog steps: {warm-up, sampling} */
+  double* n_divergent;    /* [n_problems][chains] post-warm-up divergences */
+} foct_result;
+
+int foct_version(void);
+int foct_device_count(void);
+const char* foct_last_error(void);
+
+void foct_model_spec_default(foct_model_spec* spec, int kind);
+void foct_sampler_cfg_default(foct_sampler_cfg* cfg);
+/* D (unconstrained) and P_out (output columns) for a model kind. */
+int foct_dims(int kind, int Nn, int* D, int* P_out);
+
+/* Control-point grid `xGP` (returned as fitOut$xGP, plotExpGP.R:31; definition server.R:626-635).
+ * Pure host arithmetic, no device needed. */
+int foct_expgp_grid(int Nn, int gridType, double* xGP /*[Nn]*/);
+
+/* GP conditional-mean basis B = K(xp,xGP) K(xGP,xGP)^-1, built on the device (MODEL_SPEC §1).
+ * B_out is [Nn][N] (control-point major, the layout the kernels stage in shared memory). */
+int foct_expgp_basis(const foct_problem* P, const foct_model_spec* spec, double* B_out);
+
+/* Parity hook: log density and analytic gradient on the unconstrained space (MODEL_SPEC §4-5) for
+ * n_q points per problem.  q, grad: [n_problems][n_q][D]; lp, chi2: [n_problems][n_q]
+ * (chi2 = sum((y-m)/uy)^2, the numerator of br; may be NULL).  Replaces the generated Stan model class'
+ * log_prob + reverse-mode gradient (SURVEY a-4, a-5). */
+int foct_logp_grad(int kind, const foct_problem* P, int n_problems, const foct_model_spec* spec,
+                   const double* q, int n_q, double* lp, double* grad, double* chi2);
+
+/* One-shot batched NUTS: upload, sample on device, (optionally) summarise on device, download.
+ * Replaces FitOCTLib::fitExpGP(method='sample') -> rstan::sampling (FitOCT.R:110-124) for a whole batch. */
+int foct_sample(int kind, const foct_problem* P, int n_problems, const foct_model_spec* spec,
+                const foct_sampler_cfg* cfg, foct_result* R);
+/* Named as SURVEY §8(b) lists them. */
+int foct_expgp_sample(const foct_problem* P, int n_problems, const foct_model_spec* spec,
+                      const foct_sampler_cfg* cfg, foct_result* R);
+int foct_monoexp_sample(const foct_problem* P, int n_problems, const foct_model_spec* spec,
+                        const foct_sampler_cfg* cfg, foct_result* R);
+
+/* MAP fit of the mono-exponential (the reference's only use of fitMonoExp: FitOCT.R:94-97,
+ * plotMonoExp.R:14-16).  theta: [n][3]; hessian: [n][9] of lp at the optimum (negative definite, as rstan::optimizing(hessian=TRUE)); br: [n];
+ * status: [n] (0 converged).  init may be NULL (then a log-linear start is used). */
+int foct_monoexp_map(const foct_problem* P, int n_problems, const foct_model_spec* spec,
+                     const double* init /*[n][3] or NULL*/, double* theta, double* hessian, double* br,
+                     int* status);
+
+/* Generated quantities for selected draws (SURVEY a-6): m, resid, dL at every depth.
+ * draws: [n_draws][P_out] constrained rows of one problem; outputs [n_draws][N] (any may be NULL). */
+int foct_predict(int kind, const foct_problem* P, const foct_model_spec* spec, const double* draws,
+                 int n_draws, double* m, double* resid, double* dL);
+
+/* Plan API: the same path with device-resident inputs, for repeated runs and for timing the
+ * sampling step without host<->device copies (bench.py `value`; `e2e` uses foct_sample). */
+typedef struct foct_plan foct_plan;
+int foct_plan_create(int kind, const foct_problem* P, int n_problems, const foct_model_spec* spec,
+                     const foct_sampler_cfg* cfg, int want_draws, int want_summary, foct_plan** plan);
+int foct_plan_run(foct_plan* plan, unsigned long long seed); /* async on the plan's stream */
+int foct_plan_sync(foct_plan* plan, float* kernel_ms /* CUDA-event time of the sampling kernel, may be NULL */);
+int foct_plan_fetch(foct_plan* plan, foct_result* R);
+void foct_plan_destroy(foct_plan* plan);
+
+/* Measured fp64 FMA throughput of the device (DFMA-chain microbenchmark), the roofline denominator for
+ * the sampling kernel (MEASURED_PEAKS.json has no fp64 figure). */
+int foct_fp64_peak(int device, double* tflops, double* sm_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FITOCT_B200_H */
