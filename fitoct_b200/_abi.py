@@ -11,7 +11,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 FOCT_MAX_D = 32
-FOCT_MAX_NN = 27
+FOCT_MAX_NN = 25
 FOCT_MAX_CHAINS = 8
 FOCT_N_SAMPLER_PARAMS = 6
 FOCT_N_SUMMARY_COLS = 11

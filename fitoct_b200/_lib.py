@@ -1,0 +1,205 @@
+"""ctypes binding of libfitoct_b200.so (the CUDA product library behind include/fitoct_b200.h).
+
+The library must be built in-tree (`make -C fitoct_b200/csrc`, or `__graft_entry__.build()`); there is no
+CPU fallback — a missing library or a missing CUDA device is a hard error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfitoct_b200.so")
+
+# every symbol include/fitoct_b200.h declares (tests/test_abi.py checks the header against this list)
+EXPORTS = (
+    "foct_version", "foct_device_count", "foct_last_error", "foct_model_spec_default", "foct_sampler_cfg_default",
+    "foct_dims", "foct_expgp_grid", "foct_expgp_basis", "foct_logp_grad", "foct_sample", "foct_expgp_sample",
+    "foct_monoexp_sample", "foct_monoexp_map", "foct_predict", "foct_plan_create", "foct_plan_run",
+    "foct_plan_sync", "foct_plan_fetch", "foct_plan_destroy", "foct_fp64_peak",
+)
+
+_LIB = None
+
+
+class FitOCTError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"fitoct_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build the CUDA extension with `make -C fitoct_b200/csrc -j` "
+                "(fitoct_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        dp, ip = abi.c_double_p, C.POINTER(C.c_int)
+        PP, MS, SC, RS = (C.POINTER(abi.Problem), C.POINTER(abi.ModelSpec), C.POINTER(abi.SamplerCfg),
+                          C.POINTER(abi.Result))
+        L.foct_last_error.restype = C.c_char_p
+        L.foct_model_spec_default.argtypes = [MS, C.c_int]
+        L.foct_model_spec_default.restype = None
+        L.foct_sampler_cfg_default.argtypes = [SC]
+        L.foct_sampler_cfg_default.restype = None
+        L.foct_dims.argtypes = [C.c_int, C.c_int, ip, ip]
+        L.foct_expgp_grid.argtypes = [C.c_int, C.c_int, dp]
+        L.foct_expgp_basis.argtypes = [PP, MS, dp]
+        L.foct_logp_grad.argtypes = [C.c_int, PP, C.c_int, MS, dp, C.c_int, dp, dp, dp]
+        for name in ("foct_sample",):
+            getattr(L, name).argtypes = [C.c_int, PP, C.c_int, MS, SC, RS]
+        for name in ("foct_expgp_sample", "foct_monoexp_sample"):
+            getattr(L, name).argtypes = [PP, C.c_int, MS, SC, RS]
+        L.foct_monoexp_map.argtypes = [PP, C.c_int, MS, dp, dp, dp, dp, ip]
+        L.foct_predict.argtypes = [C.c_int, PP, MS, dp, C.c_int, dp, dp, dp]
+        L.foct_plan_create.argtypes = [C.c_int, PP, C.c_int, MS, SC, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.foct_plan_run.argtypes = [C.c_void_p, C.c_ulonglong]
+        L.foct_plan_sync.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.foct_plan_fetch.argtypes = [C.c_void_p, RS]
+        L.foct_plan_destroy.argtypes = [C.c_void_p]
+        L.foct_plan_destroy.restype = None
+        L.foct_fp64_peak.argtypes = [C.c_int, dp, dp]
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int):
+    if rc != 0:
+        raise FitOCTError(rc, lib().foct_last_error().decode())
+
+
+def device_count() -> int:
+    return lib().foct_device_count()
+
+
+def grid(Nn: int, gridType: int) -> np.ndarray:
+    out = np.empty(Nn)
+    check(lib().foct_expgp_grid(Nn, gridType, abi.as_ptr(out)))
+    return out
+
+
+def basis(batch: abi.ProblemBatch, j: int, spec: abi.ModelSpec) -> np.ndarray:
+    p = batch.array[j]
+    B = np.empty((p.Nn, p.N))
+    check(lib().foct_expgp_basis(C.byref(p), C.byref(spec), abi.as_ptr(B)))
+    return B
+
+
+def logp_grad(kind: int, batch: abi.ProblemBatch, n_problems: int, spec: abi.ModelSpec, q: np.ndarray):
+    """q: [n_problems, n_q, D] -> lp [n_problems, n_q], grad [n_problems, n_q, D], chi2 [n_problems, n_q]."""
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    n, n_q, D = q.shape
+    assert n == n_problems
+    lp = np.empty((n, n_q))
+    g = np.empty((n, n_q, D))
+    chi2 = np.empty((n, n_q))
+    check(lib().foct_logp_grad(kind, batch.array, n, C.byref(spec), abi.as_ptr(q), n_q, abi.as_ptr(lp), abi.as_ptr(g),
+                               abi.as_ptr(chi2)))
+    return lp, g, chi2
+
+
+def alloc_result(kind, n_problems, Nn, cfg: abi.SamplerCfg, draws=True, summary=True):
+    D, P_out = abi.dims(kind, Nn)
+    n_saved = cfg.n_iter if cfg.save_warmup else cfg.n_iter - cfg.n_warmup
+    Cn = cfg.chains
+    out = dict(
+        draws=np.full((n_problems, n_saved, Cn, P_out), np.nan) if draws else None,
+        sampler_params=np.full((n_problems, n_saved, Cn, 6), np.nan) if draws else None,
+        summary=np.full((n_problems, P_out, abi.FOCT_N_SUMMARY_COLS), np.nan) if summary else None,
+        stepsize=np.full((n_problems, Cn), np.nan),
+        inv_metric=np.full((n_problems, Cn, D), np.nan),
+        n_leapfrog=np.zeros((n_problems, Cn, 2)),
+        n_divergent=np.zeros((n_problems, Cn)),
+    )
+    R = abi.Result()
+    for k, v in out.items():
+        setattr(R, k, abi.as_ptr(v))
+    return out, R
+
+
+def sample(kind: int, batch: abi.ProblemBatch, n_problems: int, spec: abi.ModelSpec, cfg: abi.SamplerCfg, draws=True,
+           summary=True, devices=None):
+    """One-shot batched NUTS through the C ABI with host buffers (the `e2e` path)."""
+    Nn = batch.array[0].Nn if kind == abi.FOCT_EXPGP else 0
+    out, R = alloc_result(kind, n_problems, Nn, cfg, draws, summary)
+    keep = None
+    if devices is not None:
+        keep = (C.c_int * len(devices))(*devices)
+        cfg.n_devices = len(devices)
+        cfg.devices = C.cast(keep, C.POINTER(C.c_int))
+    try:
+        check(lib().foct_sample(kind, batch.array, n_problems, C.byref(spec), C.byref(cfg), C.byref(R)))
+    finally:
+        if devices is not None:
+            cfg.n_devices = 0
+            cfg.devices = C.POINTER(C.c_int)()
+    return out
+
+
+class Plan:
+    """Device-resident batch (foct_plan_*): upload once, run/time the sampling kernel repeatedly."""
+
+    def __init__(self, kind, batch, n_problems, spec, cfg, want_draws=False, want_summary=True):
+        self.kind, self.n, self.cfg = kind, n_problems, cfg
+        self.Nn = batch.array[0].Nn if kind == abi.FOCT_EXPGP else 0
+        self.want_draws, self.want_summary = want_draws, want_summary
+        self._h = C.c_void_p()
+        check(lib().foct_plan_create(kind, batch.array, n_problems, C.byref(spec), C.byref(cfg), int(want_draws),
+                                     int(want_summary), C.byref(self._h)))
+
+    def run(self, seed=None):
+        check(lib().foct_plan_run(self._h, int(self.cfg.seed if seed is None else seed)))
+
+    def sync(self) -> float:
+        ms = C.c_float()
+        check(lib().foct_plan_sync(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def fetch(self):
+        out, R = alloc_result(self.kind, self.n, self.Nn, self.cfg, self.want_draws, self.want_summary)
+        check(lib().foct_plan_fetch(self._h, C.byref(R)))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().foct_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def monoexp_map(batch: abi.ProblemBatch, n_problems: int, spec: abi.ModelSpec, init=None):
+    theta = np.empty((n_problems, 3))
+    H = np.empty((n_problems, 3, 3))
+    br = np.empty(n_problems)
+    st = np.empty(n_problems, dtype=np.int32)
+    ip = abi.as_ptr(np.ascontiguousarray(init, dtype=np.float64)) if init is not None else abi.c_double_p()
+    check(lib().foct_monoexp_map(batch.array, n_problems, C.byref(spec), ip, abi.as_ptr(theta), abi.as_ptr(H),
+                                 abi.as_ptr(br), st.ctypes.data_as(C.POINTER(C.c_int))))
+    return theta, H, br, st
+
+
+def predict(kind, batch, j, spec, draws):
+    draws = np.ascontiguousarray(draws, dtype=np.float64)
+    n = draws.shape[0]
+    N = batch.array[j].N
+    m, r, dl = np.empty((n, N)), np.empty((n, N)), np.empty((n, N))
+    check(lib().foct_predict(kind, C.byref(batch.array[j]), C.byref(spec), abi.as_ptr(draws), n, abi.as_ptr(m),
+                             abi.as_ptr(r), abi.as_ptr(dl)))
+    return m, r, dl
+
+
+def fp64_peak(device: int = 0):
+    t, f = np.zeros(1), np.zeros(1)
+    check(lib().foct_fp64_peak(device, abi.as_ptr(t), abi.as_ptr(f)))
+    return float(t[0]), float(f[0])

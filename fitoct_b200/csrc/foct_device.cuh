@@ -1,0 +1,319 @@
+// foct_device.cuh — device-side building blocks: Philox, warp reductions, the fused fp64
+// log-density + analytic-gradient sweep (MODEL_SPEC §3-5, SURVEY a-4/a-5).
+//
+// Layout contract: one warp owns one chain; lane d (< D) owns component d of every
+// D-vector (q, p, grad, rho, ...); warp-uniform scalars are held redundantly by all lanes.  The profile
+// lives in shared memory as a "blob": cx[Npad] | y[Npad] | w[Npad] | B[NN][Npad] (control-point major),
+// padded points carry w = 0 so they contribute exactly nothing.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "../../include/fitoct_b200.h"
+
+#define FOCT_FULL 0xffffffffu
+#define FOCT_STACK_LEVELS 12  // subtree depth <= max_treedepth - 1 <= 12
+
+namespace foct {
+
+// Per-profile constants the kernels read from global memory (written by the setup kernel).
+struct DevProblem {
+  int N, npass, prior_PD, Nn;
+  double c;  // dataType
+  double theta0[3];
+  double Pinv[9];  // Sigma0^-1
+  double lambda_rate;
+  double sum_log_uy;
+  double br_ndf;
+  long long id;
+  double xmin, xscale;  // xp = (x - xmin) * xscale
+  double rho;
+  int gridType, pad_;
+};
+
+// Batch-global model switches (MODEL_SPEC §8), passed by value as kernel parameters.
+struct DevSpec {
+  int ygp_prior, lambda_prior, theta_prior;
+  double sigma_mean, sigma_sd;
+};
+
+// ---------------------------------------------------------------- RNG (MODEL_SPEC §7)
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+enum { SITE_MOM = 0, SITE_DIR = 1, SITE_MERGE = 2, SITE_INITEPS = 3, SITE_INIT = 4 };
+
+struct Rng {
+  uint32_t k0, k1;
+  __device__ void seed(unsigned long long s, long long id, int chain) {
+    unsigned long long stream = (unsigned long long)id * 64ull + (unsigned long long)chain;
+    k0 = (uint32_t)s ^ ((uint32_t)(s >> 32) * 0x85EBCA6Bu) ^ (uint32_t)(stream >> 32);
+    k1 = (uint32_t)stream;
+  }
+  __device__ __forceinline__ void block(uint32_t it, uint32_t kind, uint32_t a, uint32_t b, uint32_t lvl,
+                                        uint32_t (&r)[4]) const {
+    philox4x32_10(it, kind | (a << 8), b, lvl, k0, k1, r);
+  }
+};
+
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+  unsigned long long a = (((unsigned long long)hi << 32) | lo) >> 11;
+  return ((double)a + 0.5) * 0x1.0p-53;
+}
+__device__ __forceinline__ double normal_from(const uint32_t (&r)[4]) {
+  double u0 = u53(r[0], r[1]), u1 = u53(r[2], r[3]);
+  return sqrt(-2.0 * log(u0)) * cos(6.283185307179586476925286766559 * u1);
+}
+
+// ---------------------------------------------------------------- warp helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FOCT_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(FOCT_FULL, v, src); }
+
+// Transposed ("reduce-scatter") warp reduction of KP (= 8, 16 or 32) per-lane accumulators: KP-1 + (5-log2 KP)
+// 64-bit shuffles instead of 5*KP.  On return, the full sum of accumulator index a is returned to lane a
+// (a < KP); lanes >= KP get accumulator (lane mod KP).
+template <int KP>
+__device__ __forceinline__ double warp_reduce_scatter(double (&v)[KP], int lane) {
+  static_assert(KP == 8 || KP == 16 || KP == 32, "KP");
+  int width = KP;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (width > 1) {
+      const int half = width / 2;
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int j = 0; j < half; ++j) {
+        double keep = upper ? v[j + half] : v[j];
+        double send = upper ? v[j] : v[j + half];
+        v[j] = keep + __shfl_xor_sync(FOCT_FULL, send, off);
+      }
+      width = half;
+    } else {
+      v[0] += __shfl_xor_sync(FOCT_FULL, v[0], off);
+    }
+  }
+  // lane L now holds accumulator index: bits of L taken from the top (off=16 first) for log2(KP) levels
+  // i.e. idx = L >> (5 - log2 KP).  Route index a to lane a.
+  constexpr int SH = KP == 32 ? 0 : (KP == 16 ? 1 : 2);
+  if (SH == 0) return v[0];
+  return __shfl_sync(FOCT_FULL, v[0], (lane << SH) & 31);
+}
+
+// ---------------------------------------------------------------- model sweep
+// Result of one log-density/gradient evaluation, in the warp layout.
+struct Eval {
+  double g;     // lane d: d lp / d q_d   (0 for lanes >= D)
+  double lp;    // uniform
+  double chi2;  // uniform: sum ((y-m)/uy)^2  (NaN when prior_PD)
+};
+
+template <int NN>
+struct Dims {
+  static constexpr bool GP = NN > 0;
+  static constexpr int D = GP ? NN + 5 : 3;
+  static constexpr int P_OUT = GP ? NN + 7 : 5;
+  static constexpr int KP = D <= 8 ? 8 : (D <= 16 ? 16 : 32);
+};
+
+// Fused sweep over the staged profile.  qd = this lane's component of q.  Everything a lane needs from
+// the other lanes is fetched with shuffles up front; the per-point loop touches only shared memory.
+template <int NN, int MOD>
+__device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, int npad, const DevProblem& P,
+                                               const DevSpec& S, double qd, int lane) {
+  using DM = Dims<NN>;
+  constexpr int D = DM::D;
+  constexpr int KP = DM::KP;
+  const double th1 = bcast(qd, 0), th2 = bcast(qd, 1), th3 = bcast(qd, 2);
+  double yg[NN > 0 ? NN : 1];
+#pragma unroll
+  for (int k = 0; k < NN; ++k) yg[k] = bcast(qd, 3 + k);
+  const double qlam = DM::GP ? bcast(qd, 3 + NN) : 0.0;
+  const double qsig = DM::GP ? bcast(qd, 4 + NN) : 0.0;
+  const double lam = DM::GP ? exp(qlam) : 1.0;
+  const double sig = DM::GP ? exp(qsig) : 1.0;
+  const double isig = DM::GP ? exp(-qsig) : 1.0;
+
+  double acc[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) acc[k] = 0.0;
+  // acc[0..2] = d/d theta (unscaled), acc[3..3+NN) = d/d yGP (unscaled), acc[ZI] = sum z^2
+  constexpr int ZI = DM::GP ? 4 + NN : KP - 1;
+  Eval out;
+  double zz = 0.0;
+  if (!P.prior_PD) {
+    const double* s_cx = blob;
+    const double* s_y = blob + npad;
+    const double* s_w = blob + 2 * npad;
+    const double* s_B = blob + 3 * npad;
+    const double r3 = 1.0 / th3;
+#pragma unroll 1
+    for (int i = lane; i < P.npass * 32; i += 32) {
+      double b[NN > 0 ? NN : 1];
+      double dl = 0.0;
+#pragma unroll
+      for (int k = 0; k < NN; ++k) {
+        b[k] = s_B[k * npad + i];
+        dl = fma(b[k], yg[k], dl);
+      }
+      const double s = 1.0 + dl;
+      const double cx = s_cx[i], y = s_y[i], ws = s_w[i] * isig;
+      if (MOD == 0) {
+        const double r = DM::GP ? 1.0 / (th3 * s) : r3;
+        const double t = cx * r;
+        const double e = exp(-t);
+        const double m = fma(th2, e, th1);
+        const double z = (y - m) * ws;
+        const double gi = z * ws;
+        const double ge = gi * e;
+        const double qq = ge * t * r;  // x theta2 after the reduction
+        acc[ZI] = fma(z, z, acc[ZI]);
+        acc[0] += gi;
+        acc[1] += ge;
+        acc[2] = fma(qq, s, acc[2]);
+#pragma unroll
+        for (int k = 0; k < NN; ++k) acc[3 + k] = fma(qq, b[k], acc[3 + k]);
+      } else {
+        const double t = cx * r3;
+        const double e = exp(-t);
+        const double es = e * s;
+        const double m = fma(th2, es, th1);
+        const double z = (y - m) * ws;
+        const double gi = z * ws;
+        const double ge = gi * e;
+        const double ges = gi * es;
+        acc[ZI] = fma(z, z, acc[ZI]);
+        acc[0] += gi;
+        acc[1] += ges;
+        acc[2] = fma(ges, t, acc[2]);
+#pragma unroll
+        for (int k = 0; k < NN; ++k) acc[3 + k] = fma(ge, b[k], acc[3 + k]);
+      }
+    }
+    // sum z^2 travels in slot ZI: the log-sigma gradient slot for GP models, the last slot otherwise
+    const double red = warp_reduce_scatter<KP>(acc, lane);
+    zz = bcast(red, ZI);
+    // scale the raw sums into gradient components
+    double scale = 1.0;
+    if (MOD == 0) {
+      if (lane == 2) scale = th2;
+      if (lane >= 3 && lane < 3 + NN) scale = th2 * th3;
+    } else {
+      if (lane == 2) scale = th2 * r3;
+      if (lane >= 3 && lane < 3 + NN) scale = th2;
+    }
+    out.g = red * scale;
+    if (DM::GP && lane == 4 + NN) out.g = zz - (double)P.N;
+    if (lane >= D) out.g = 0.0;
+    out.lp = -0.5 * zz - (double)P.N * qsig - P.sum_log_uy;
+    out.chi2 = zz * sig * sig;
+  } else {
+    out.g = 0.0;
+    out.lp = 0.0;
+    out.chi2 = CUDART_NAN;
+  }
+
+  // priors + Jacobians (O(D), evaluated redundantly by every lane; each lane keeps its own component)
+  if (S.theta_prior == 0) {
+    const double d0 = th1 - P.theta0[0], d1 = th2 - P.theta0[1], d2 = th3 - P.theta0[2];
+    const double v0 = P.Pinv[0] * d0 + P.Pinv[1] * d1 + P.Pinv[2] * d2;
+    const double v1 = P.Pinv[3] * d0 + P.Pinv[4] * d1 + P.Pinv[5] * d2;
+    const double v2 = P.Pinv[6] * d0 + P.Pinv[7] * d1 + P.Pinv[8] * d2;
+    out.lp += -0.5 * (d0 * v0 + d1 * v1 + d2 * v2);
+    if (lane == 0) out.g -= v0;
+    if (lane == 1) out.g -= v1;
+    if (lane == 2) out.g -= v2;
+  }
+  if (DM::GP) {
+    double sy = 0.0;
+    if (S.ygp_prior == 0) {
+      const double il2 = 1.0 / (lam * lam);
+#pragma unroll
+      for (int k = 0; k < NN; ++k) sy = fma(yg[k], yg[k], sy);
+      out.lp += -(double)NN * qlam - 0.5 * sy * il2;
+      if (lane >= 3 && lane < 3 + NN) out.g -= qd * il2;
+      if (lane == 3 + NN) out.g += sy * il2 - (double)NN;
+    } else {
+      const double il = 1.0 / lam;
+#pragma unroll
+      for (int k = 0; k < NN; ++k) sy += fabs(yg[k]);
+      out.lp += -(double)NN * qlam - sy * il;
+      if (lane >= 3 && lane < 3 + NN) out.g -= (qd > 0.0 ? 1.0 : (qd < 0.0 ? -1.0 : 0.0)) * il;
+      if (lane == 3 + NN) out.g += sy * il - (double)NN;
+    }
+    const double rl = P.lambda_rate * lam;
+    if (S.lambda_prior == 0) {
+      out.lp += qlam - rl;
+      if (lane == 3 + NN) out.g += 1.0 - rl;
+    } else {
+      out.lp += -rl;
+      if (lane == 3 + NN) out.g += -rl;
+    }
+    if (S.sigma_sd > 0.0) {
+      const double u = (sig - S.sigma_mean) / S.sigma_sd;
+      out.lp += -0.5 * u * u;
+      if (lane == 4 + NN) out.g += -sig * u / S.sigma_sd;
+    }
+    out.lp += qlam + qsig;
+    if (lane == 3 + NN || lane == 4 + NN) out.g += 1.0;
+  }
+  return out;
+}
+
+// Stage one profile blob (contiguous in global memory) into shared memory with a TMA bulk copy
+// (cp.async.bulk, SASS UBLKCP) completed on an mbarrier.  Called by all threads of the CTA.
+__device__ __forceinline__ void stage_blob_tma(double* smem_dst, const double* gsrc, uint32_t bytes, uint64_t* mbar,
+                                               uint32_t& phase) {
+  const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
+  if (threadIdx.x == 0) {
+    const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(bytes) : "memory");
+    // chunks of <= 64 KB keep every copy well inside any per-instruction limit
+    uint32_t off = 0;
+    while (off < bytes) {
+      uint32_t n = bytes - off;
+      if (n > 65536u) n = 65536u;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s + off),
+          "l"((const char*)gsrc + off), "r"(n), "r"(mbar_s)
+          : "memory");
+      off += n;
+    }
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mbar_s), "r"(phase)
+        : "memory");
+  }
+  phase ^= 1u;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* mbar) {
+  if (threadIdx.x == 0) {
+    const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+}
+
+}  // namespace foct

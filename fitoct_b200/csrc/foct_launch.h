@@ -1,0 +1,33 @@
+// foct_launch.h — host-callable launchers, one translation unit per control-point count NN
+// (foct_inst.cu compiled with -DFOCT_INST_NN=<NN>); foct_lib.cu dispatches through foct_inst_table().
+#pragma once
+#include <cuda_runtime.h>
+
+#include "foct_nuts.cuh"
+
+namespace foct {
+
+struct LogpParams {
+  const double* blobs;
+  size_t blob_stride;
+  int npad;
+  const DevProblem* probs;
+  int n_problems;
+  DevSpec spec;
+  const double* q;  // [n_problems][n_q][D]
+  int n_q;
+  double* lp;    // [n_problems][n_q]
+  double* grad;  // [n_problems][n_q][D]
+  double* chi2;  // [n_problems][n_q] or nullptr
+};
+
+struct InstEntry {
+  int NN;  // 0 = mono-exponential
+  cudaError_t (*launch_nuts)(int mod, int grid, int block, size_t smem, cudaStream_t st, const SamplerParams& K);
+  cudaError_t (*launch_logp)(int mod, int grid, int block, size_t smem, cudaStream_t st, const LogpParams& K);
+  cudaError_t (*nuts_occupancy)(int mod, int block, size_t smem, int* blocks_per_sm, int* regs);
+};
+
+#define FOCT_DECL_INST(NN) const InstEntry* foct_inst_##NN();
+
+}  // namespace foct

@@ -1,0 +1,853 @@
+// foct_lib.cu — host side of the C ABI (include/fitoct_b200.h): argument checking, device-resident plans,
+// the setup kernel that builds the per-profile shared-memory blobs (incl. the GP basis, MODEL_SPEC §1),
+// multi-GPU sharding with one host thread per device (no collective: SURVEY §8e), and small helper kernels.
+//
+// There is no CPU compute path in this file: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "foct_launch.h"
+#include "foct_summary.cuh"
+
+namespace foct {
+FOCT_DECL_INST(0)
+FOCT_DECL_INST(1)  FOCT_DECL_INST(2)  FOCT_DECL_INST(3)  FOCT_DECL_INST(4)  FOCT_DECL_INST(5)
+FOCT_DECL_INST(6)  FOCT_DECL_INST(7)  FOCT_DECL_INST(8)  FOCT_DECL_INST(9)  FOCT_DECL_INST(10)
+FOCT_DECL_INST(11) FOCT_DECL_INST(12) FOCT_DECL_INST(13) FOCT_DECL_INST(14) FOCT_DECL_INST(15)
+FOCT_DECL_INST(16) FOCT_DECL_INST(17) FOCT_DECL_INST(18) FOCT_DECL_INST(19) FOCT_DECL_INST(20)
+FOCT_DECL_INST(21) FOCT_DECL_INST(22) FOCT_DECL_INST(23) FOCT_DECL_INST(24) FOCT_DECL_INST(25)
+
+static const InstEntry* inst_for(int NN) {
+  typedef const InstEntry* (*getter)();
+  static const getter table[FOCT_MAX_NN + 1] = {
+      foct_inst_0,  foct_inst_1,  foct_inst_2,  foct_inst_3,  foct_inst_4,  foct_inst_5,  foct_inst_6,
+      foct_inst_7,  foct_inst_8,  foct_inst_9,  foct_inst_10, foct_inst_11, foct_inst_12, foct_inst_13,
+      foct_inst_14, foct_inst_15, foct_inst_16, foct_inst_17, foct_inst_18, foct_inst_19, foct_inst_20,
+      foct_inst_21, foct_inst_22, foct_inst_23, foct_inst_24, foct_inst_25};
+  if (NN < 0 || NN > FOCT_MAX_NN) return nullptr;
+  return table[NN]();
+}
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(FOCT_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------ setup kernel
+// Host-side description of one profile inside the concatenated upload buffer.
+struct HostMeta {
+  size_t off;  // offset (doubles) of x in the upload buffer; y at off+N, uy at off+2N
+  int N, dataType, gridType, prior_PD;
+  double rho, lambda_rate, theta0[3], Pinv[9];
+  long long id;
+};
+
+__device__ __forceinline__ double gp_kern(double a, double b, double rho, int kernel) {
+  const double d = a - b;
+  const double den = kernel == 0 ? 2.0 * rho * rho : rho * rho;
+  return exp(-(d * d) / den);
+}
+
+// One CTA per profile: depth normalisation, Cholesky of Kgg (thread 0; Nn <= 25), per-point triangular
+// solves B_i = Kgg^-1 k(xp_i, xGP), and the blob cx | y | w | B[k][i] written straight into global memory
+// in the layout the sampling kernel bulk-copies into shared memory.
+__global__ void __launch_bounds__(128) setup_kernel(const double* __restrict__ up, const HostMeta* __restrict__ meta,
+                                                    int n_problems, int NN, int npad, size_t blob_stride,
+                                                    double* __restrict__ blobs, DevProblem* __restrict__ probs,
+                                                    int kernel, double jitter, int br_mode, int* __restrict__ status) {
+  __shared__ double sL[FOCT_MAX_NN * FOCT_MAX_NN];
+  __shared__ double sxg[FOCT_MAX_NN];
+  __shared__ double red[3][128];
+  __shared__ int s_bad;
+  for (int j = blockIdx.x; j < n_problems; j += gridDim.x) {
+    const HostMeta M = meta[j];
+    const int N = M.N;
+    const double* x = up + M.off;
+    const double* y = x + N;
+    const double* uy = y + N;
+    double mn = CUDART_INF, mx = -CUDART_INF, slu = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      mn = fmin(mn, x[i]);
+      mx = fmax(mx, x[i]);
+      slu += log(uy[i]);
+    }
+    red[0][threadIdx.x] = mn; red[1][threadIdx.x] = mx; red[2][threadIdx.x] = slu;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+      if (threadIdx.x < s) {
+        red[0][threadIdx.x] = fmin(red[0][threadIdx.x], red[0][threadIdx.x + s]);
+        red[1][threadIdx.x] = fmax(red[1][threadIdx.x], red[1][threadIdx.x + s]);
+        red[2][threadIdx.x] += red[2][threadIdx.x + s];
+      }
+      __syncthreads();
+    }
+    const double xmin = red[0][0], xmax = red[1][0];
+    if (threadIdx.x == 0) {
+      // control grid (server.R:626-635) and Cholesky of Kgg + jitter I
+      const double dx = 1.0 / (NN + 1);
+      const double lo = M.gridType == FOCT_GRID_INTERNAL ? 0.5 * dx : 0.0;
+      const double hi = M.gridType == FOCT_GRID_INTERNAL ? 1.0 - 0.5 * dx : 1.0;
+      for (int k = 0; k < NN; ++k) sxg[k] = NN == 1 ? lo : lo + (hi - lo) * (double)k / (double)(NN - 1);
+      for (int i = 0; i < NN; ++i)
+        for (int jj = 0; jj <= i; ++jj) {
+          double s = gp_kern(sxg[i], sxg[jj], M.rho, kernel) + (i == jj ? jitter : 0.0);
+          for (int k = 0; k < jj; ++k) s -= sL[i * NN + k] * sL[jj * NN + k];
+          if (i == jj) {
+            if (!(s > 0.0)) s_bad = 1;
+            sL[i * NN + i] = sqrt(s);
+          } else {
+            sL[i * NN + jj] = s / sL[jj * NN + jj];
+          }
+        }
+      DevProblem P;
+      P.N = N; P.npass = (N + 31) / 32; P.prior_PD = M.prior_PD; P.Nn = NN;
+      P.c = (double)M.dataType;
+      for (int k = 0; k < 3; ++k) P.theta0[k] = M.theta0[k];
+      for (int k = 0; k < 9; ++k) P.Pinv[k] = M.Pinv[k];
+      P.lambda_rate = M.lambda_rate;
+      P.sum_log_uy = red[2][0];
+      P.br_ndf = br_mode == 1 ? (double)N : (double)(N - 3 - NN);
+      P.id = M.id;
+      P.xmin = xmin; P.xscale = 1.0 / (xmax - xmin);
+      P.rho = M.rho; P.gridType = M.gridType; P.pad_ = 0;
+      probs[j] = P;
+      if (s_bad || !(xmax > xmin)) atomicExch(status, j + 1);
+    }
+    __syncthreads();
+    double* blob = blobs + (size_t)j * blob_stride;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+      const bool in = i < N;
+      blob[i] = in ? (double)M.dataType * x[i] : 0.0;
+      blob[npad + i] = in ? y[i] : 0.0;
+      blob[2 * npad + i] = in ? 1.0 / uy[i] : 0.0;
+      if (NN > 0) {
+        double v[FOCT_MAX_NN];
+        if (in) {
+          const double xp = (x[i] - xmin) / (xmax - xmin);
+          for (int k = 0; k < NN; ++k) v[k] = gp_kern(xp, sxg[k], M.rho, kernel);
+          for (int k = 0; k < NN; ++k) {
+            double s = v[k];
+            for (int jj = 0; jj < k; ++jj) s -= sL[k * NN + jj] * v[jj];
+            v[k] = s / sL[k * NN + k];
+          }
+          for (int k = NN - 1; k >= 0; --k) {
+            double s = v[k];
+            for (int jj = k + 1; jj < NN; ++jj) s -= sL[jj * NN + k] * v[jj];
+            v[k] = s / sL[k * NN + k];
+          }
+        }
+        for (int k = 0; k < NN; ++k) blob[(size_t)(3 + k) * npad + i] = in ? v[k] : 0.0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Generated quantities (SURVEY a-6) for selected draws of one profile.
+__global__ void predict_kernel(const double* __restrict__ blob, int npad, int N, int NN, int mod, int P_out,
+                               const double* __restrict__ draws, int n_draws, double* m_out, double* resid,
+                               double* dL) {
+  const size_t tot = (size_t)n_draws * N;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t / N), i = (int)(t % N);
+    const double* r = draws + (size_t)j * P_out;
+    double dl = 0.0;
+    for (int k = 0; k < NN; ++k) dl = fma(blob[(size_t)(3 + k) * npad + i], r[3 + k], dl);
+    const double cx = blob[i];
+    const double m = mod == 0 ? r[0] + r[1] * exp(-cx / (r[2] * (1.0 + dl))) : r[0] + r[1] * exp(-cx / r[2]) * (1.0 + dl);
+    if (m_out) m_out[t] = m;
+    if (resid) resid[t] = blob[npad + i] - m;
+    if (dL) dL[t] = dl;
+  }
+}
+
+// DFMA-chain microbenchmark: 8 independent chains per thread, the roofline denominator.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+    v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+}
+
+// ---------------------------------------------------------------- MonoExp MAP (SURVEY a-12)
+// One warp per profile: damped Newton (Levenberg-Marquardt on the exact Hessian) on -lp of the
+// mono-exponential with sigma == 1; the same iteration the oracle runs, lanes striding over the points.
+__device__ __forceinline__ bool dev_inv3(const double* S, double* Pi) {
+  const double a = S[0], b = S[1], c = S[2], d = S[3], e = S[4], f = S[5], g = S[6], h = S[7], i = S[8];
+  const double A = e * i - f * h, Bc = -(d * i - f * g), C = d * h - e * g;
+  const double det = a * A + b * Bc + c * C;
+  if (!(fabs(det) > 0.0)) return false;
+  const double id = 1.0 / det;
+  Pi[0] = A * id;  Pi[1] = -(b * i - c * h) * id; Pi[2] = (b * f - c * e) * id;
+  Pi[3] = Bc * id; Pi[4] = (a * i - c * g) * id;  Pi[5] = -(a * f - c * d) * id;
+  Pi[6] = C * id;  Pi[7] = -(a * h - b * g) * id; Pi[8] = (a * e - b * d) * id;
+  return true;
+}
+
+// f = -lp, g[3], H[9] (of -lp), chi2; all lanes receive all values.
+__device__ void mono_nlp(const double* __restrict__ blob, int npad, const DevProblem& P, int theta_prior,
+                         const double* th, double& f, double* g, double* H, double& chi2, int lane) {
+  double v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = 0.0;
+  for (int i = lane; i < P.N; i += 32) {
+    const double w = blob[2 * npad + i], w2 = w * w;
+    const double t = blob[i] / th[2];
+    const double e = exp(-t);
+    const double m = th[0] + th[1] * e;
+    const double r = blob[npad + i] - m;
+    const double J0 = 1.0, J1 = e, J2 = th[1] * e * t / th[2];
+    const double m23 = e * t / th[2];
+    const double m33 = th[1] * e * (t * t - 2.0 * t) / (th[2] * th[2]);
+    v[0] += 0.5 * r * r * w2;
+    v[1] -= r * w2 * J0; v[2] -= r * w2 * J1; v[3] -= r * w2 * J2;
+    v[4] += w2 * J0 * J0; v[5] += w2 * J0 * J1; v[6] += w2 * J0 * J2;
+    v[7] += w2 * J1 * J1; v[8] += w2 * J1 * J2 - w2 * r * m23;
+    v[9] += w2 * J2 * J2 - w2 * r * m33;
+    v[10] += r * r * w2;
+  }
+  const double red = warp_reduce_scatter<16>(v, lane);
+  double a[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) a[k] = __shfl_sync(FOCT_FULL, red, k);
+  f = a[0]; g[0] = a[1]; g[1] = a[2]; g[2] = a[3];
+  H[0] = a[4]; H[1] = a[5]; H[2] = a[6]; H[3] = a[5]; H[4] = a[7]; H[5] = a[8]; H[6] = a[6]; H[7] = a[8]; H[8] = a[9];
+  chi2 = a[10];
+  if (theta_prior == 0) {
+    const double d[3] = {th[0] - P.theta0[0], th[1] - P.theta0[1], th[2] - P.theta0[2]};
+    for (int r = 0; r < 3; ++r) {
+      double vv = 0.0;
+      for (int c = 0; c < 3; ++c) { vv += P.Pinv[r * 3 + c] * d[c]; H[r * 3 + c] += P.Pinv[r * 3 + c]; }
+      f += 0.5 * d[r] * vv; g[r] += vv;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) map_kernel(const double* __restrict__ blobs, size_t blob_stride, int npad,
+                                                  const DevProblem* __restrict__ probs, int n, int theta_prior,
+                                                  const double* __restrict__ init, double* theta_out,
+                                                  double* hess_out, double* br_out, int* status_out) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= n) return;
+  const DevProblem P = probs[j];
+  const double* blob = blobs + (size_t)j * blob_stride;
+  double th[3], g[3], H[9], c2, f;
+  if (init) {
+    th[0] = init[j * 3]; th[1] = init[j * 3 + 1]; th[2] = init[j * 3 + 2];
+  } else {
+    // log-linear start: theta1 just below min(y), regress log(y - theta1) on x
+    double ymin = CUDART_INF, ymax = -CUDART_INF;
+    for (int i = lane; i < P.N; i += 32) { ymin = fmin(ymin, blob[npad + i]); ymax = fmax(ymax, blob[npad + i]); }
+    for (int o = 16; o > 0; o >>= 1) {
+      ymin = fmin(ymin, __shfl_xor_sync(FOCT_FULL, ymin, o));
+      ymax = fmax(ymax, __shfl_xor_sync(FOCT_FULL, ymax, o));
+    }
+    const double th1 = ymin - 0.05 * (ymax - ymin);
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = lane; i < P.N; i += 32) {
+      const double yy = blob[npad + i] - th1;
+      if (yy > 0.0) {
+        const double x = blob[i] / P.c, ly = log(yy);
+        v[0] += x; v[1] += ly; v[2] += x * x; v[3] += x * ly; v[4] += 1.0;
+      }
+    }
+    const double red = warp_reduce_scatter<8>(v, lane);
+    const double sx = __shfl_sync(FOCT_FULL, red, 0), sy = __shfl_sync(FOCT_FULL, red, 1);
+    const double sxx = __shfl_sync(FOCT_FULL, red, 2), sxy = __shfl_sync(FOCT_FULL, red, 3);
+    const double nn = __shfl_sync(FOCT_FULL, red, 4);
+    const double slope = (nn * sxy - sx * sy) / (nn * sxx - sx * sx);
+    const double icpt = (sy - slope * sx) / nn;
+    th[0] = th1; th[1] = exp(icpt);
+    th[2] = slope < 0.0 ? -P.c / slope : (blob[P.N - 1] - blob[0]) / P.c;
+  }
+  mono_nlp(blob, npad, P, theta_prior, th, f, g, H, c2, lane);
+  double mu = 1e-3;
+  int st = 1;
+  for (int it = 0; it < 200; ++it) {
+    double A[9], Ai[9], step[3], tn[3], gn[3], Hn[9], c2n, fn;
+    for (int k = 0; k < 9; ++k) A[k] = H[k];
+    for (int a = 0; a < 3; ++a) A[a * 3 + a] += mu * fabs(H[a * 3 + a]) + 1e-300;
+    if (!dev_inv3(A, Ai)) { mu *= 10.0; continue; }
+    for (int a = 0; a < 3; ++a) step[a] = -(Ai[a * 3] * g[0] + Ai[a * 3 + 1] * g[1] + Ai[a * 3 + 2] * g[2]);
+    for (int a = 0; a < 3; ++a) tn[a] = th[a] + step[a];
+    mono_nlp(blob, npad, P, theta_prior, tn, fn, gn, Hn, c2n, lane);
+    if (isfinite(fn) && fn <= f) {
+      double rel = 0.0;
+      for (int a = 0; a < 3; ++a) rel = fmax(rel, fabs(step[a]) / (fabs(th[a]) + 1e-300));
+      for (int a = 0; a < 3; ++a) { th[a] = tn[a]; g[a] = gn[a]; }
+      for (int k = 0; k < 9; ++k) H[k] = Hn[k];
+      c2 = c2n; f = fn;
+      mu = mu * 0.2 > 1e-12 ? mu * 0.2 : 1e-12;
+      if (rel < 1e-12) { st = 0; break; }
+    } else {
+      mu *= 5.0;
+      if (mu > 1e12) break;
+    }
+  }
+  if (lane == 0) {
+    for (int a = 0; a < 3; ++a) theta_out[j * 3 + a] = th[a];
+    if (hess_out) for (int k = 0; k < 9; ++k) hess_out[(size_t)j * 9 + k] = -H[k];
+    if (br_out) br_out[j] = c2 / P.br_ndf;
+    if (status_out) status_out[j] = st;
+  }
+}
+
+static int inv3(const double* S, double* Pi) {
+  const double a = S[0], b = S[1], c = S[2], d = S[3], e = S[4], f = S[5], g = S[6], h = S[7], i = S[8];
+  const double A = e * i - f * h, Bc = -(d * i - f * g), C = d * h - e * g;
+  const double det = a * A + b * Bc + c * C;
+  if (!(std::fabs(det) > 0.0) || !std::isfinite(det)) return 1;
+  const double id = 1.0 / det;
+  Pi[0] = A * id;  Pi[1] = -(b * i - c * h) * id; Pi[2] = (b * f - c * e) * id;
+  Pi[3] = Bc * id; Pi[4] = (a * i - c * g) * id;  Pi[5] = -(a * f - c * d) * id;
+  Pi[6] = C * id;  Pi[7] = -(a * h - b * g) * id; Pi[8] = (a * e - b * d) * id;
+  return 0;
+}
+
+}  // namespace foct
+
+using namespace foct;
+
+// ------------------------------------------------------------------ plan
+struct foct_plan {
+  int kind = 0, n = 0, NN = 0, D = 0, P_out = 0, npad = 0, device = 0;
+  size_t blob_stride = 0;
+  foct_model_spec spec{};
+  foct_sampler_cfg cfg{};
+  int n_saved = 0, n_post = 0;
+  bool want_draws = false, want_summary = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double *d_blobs = nullptr, *d_draws = nullptr, *d_sparams = nullptr, *d_summary = nullptr, *d_stepsize = nullptr,
+         *d_invm = nullptr, *d_nleap = nullptr, *d_ndiv = nullptr, *d_init = nullptr;
+  DevProblem* d_probs = nullptr;
+  int* d_counter = nullptr;
+  const InstEntry* inst = nullptr;
+  int grid = 0, block = 0, blocks_per_sm = 0, regs = 0;
+  size_t smem = 0;
+  bool ran = false;
+};
+
+static void plan_free(foct_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  cudaFree(p->d_blobs); cudaFree(p->d_draws); cudaFree(p->d_sparams); cudaFree(p->d_summary);
+  cudaFree(p->d_stepsize); cudaFree(p->d_invm); cudaFree(p->d_nleap); cudaFree(p->d_ndiv); cudaFree(p->d_init);
+  cudaFree(p->d_probs); cudaFree(p->d_counter);
+  if (p->ev0) cudaEventDestroy(p->ev0);
+  if (p->ev1) cudaEventDestroy(p->ev1);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+static int check_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n < 1)
+    return fail(FOCT_ENODEV, "no CUDA device available (%s); fitoct_b200 has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  return 0;
+}
+
+static DevSpec dev_spec(const foct_model_spec& s) {
+  DevSpec d;
+  d.ygp_prior = s.ygp_prior; d.lambda_prior = s.lambda_prior; d.theta_prior = s.theta_prior;
+  d.sigma_mean = s.sigma_mean; d.sigma_sd = s.sigma_sd;
+  return d;
+}
+
+// Validate a batch, upload it and build blobs + DevProblem[] on `device`.
+static int build_device_batch(int kind, const foct_problem* P, int n, const foct_model_spec* spec, int device,
+                              cudaStream_t st, int* NN_out, int* npad_out, size_t* stride_out, double** d_blobs,
+                              DevProblem** d_probs) {
+  if (!P || n < 1 || !spec) return fail(FOCT_EINVAL, "empty batch or NULL argument");
+  if (kind != FOCT_EXPGP && kind != FOCT_MONOEXP) return fail(FOCT_EINVAL, "unknown model kind %d", kind);
+  const int NN = kind == FOCT_EXPGP ? P[0].Nn : 0;
+  if (kind == FOCT_EXPGP && (NN < 1 || NN > FOCT_MAX_NN)) return fail(FOCT_EINVAL, "Nn=%d outside 1..%d", NN, FOCT_MAX_NN);
+  int maxN = 0;
+  size_t total = 0;
+  for (int j = 0; j < n; ++j) {
+    if (P[j].N < 4 || !P[j].x || !P[j].y || !P[j].uy) return fail(FOCT_EINVAL, "problem %d: N=%d or NULL data", j, P[j].N);
+    if (kind == FOCT_EXPGP && P[j].Nn != NN) return fail(FOCT_EINVAL, "problem %d: Nn=%d differs from batch Nn=%d", j, P[j].Nn, NN);
+    if (P[j].dataType != 1 && P[j].dataType != 2) return fail(FOCT_EINVAL, "problem %d: dataType=%d not in {1,2}", j, P[j].dataType);
+    if (kind == FOCT_EXPGP && !(P[j].rho > 0.0)) return fail(FOCT_EINVAL, "problem %d: rho must be > 0 (resolve rho_scale==0 to 1/Nn as FitOCT.R:119 does)", j);
+    if (P[j].N - 3 - NN < 1 && spec->br_ndf == 0) return fail(FOCT_EINVAL, "problem %d: N=%d too small for %d parameters", j, P[j].N, 3 + NN);
+    maxN = std::max(maxN, P[j].N);
+    total += 3 * (size_t)P[j].N;
+  }
+  const int npad = (maxN + 31) / 32 * 32;
+  const size_t stride = (size_t)(3 + NN) * npad;
+  if (stride * sizeof(double) > 200 * 1024) return fail(FOCT_EINVAL, "profile of %d points x %d control points does not fit shared memory", maxN, NN);
+
+  double* h_up = nullptr;
+  HostMeta* h_meta = nullptr;
+  CU(cudaSetDevice(device));
+  CU(cudaMallocHost(&h_up, total * sizeof(double)));
+  if (cudaMallocHost(&h_meta, (size_t)n * sizeof(HostMeta)) != cudaSuccess) { cudaFreeHost(h_up); return fail(FOCT_ENOMEM, "pinned alloc"); }
+  size_t off = 0;
+  int bad = -1;
+  for (int j = 0; j < n; ++j) {
+    const int N = P[j].N;
+    std::memcpy(h_up + off, P[j].x, N * sizeof(double));
+    std::memcpy(h_up + off + N, P[j].y, N * sizeof(double));
+    std::memcpy(h_up + off + 2 * (size_t)N, P[j].uy, N * sizeof(double));
+    HostMeta& M = h_meta[j];
+    M.off = off; M.N = N; M.dataType = P[j].dataType; M.gridType = P[j].gridType; M.prior_PD = P[j].prior_PD;
+    M.rho = P[j].rho; M.lambda_rate = P[j].lambda_rate; M.id = P[j].id;
+    for (int k = 0; k < 3; ++k) M.theta0[k] = P[j].theta0[k];
+    for (int k = 0; k < 9; ++k) M.Pinv[k] = 0.0;
+    if (spec->theta_prior == 0 && inv3(P[j].Sigma0, M.Pinv)) bad = j;
+    for (int i = 0; i < N; ++i)
+      if (!(P[j].uy[i] > 0.0)) bad = j;
+    off += 3 * (size_t)N;
+  }
+  int rc = 0;
+  double* d_up = nullptr;
+  HostMeta* d_meta = nullptr;
+  int* d_status = nullptr;
+  *d_blobs = nullptr; *d_probs = nullptr;
+  do {
+    if (bad >= 0) { rc = fail(FOCT_EINVAL, "problem %d: singular Sigma0 or non-positive uy", bad); break; }
+#define CUB(call) if ((call) != cudaSuccess) { rc = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); break; }
+    CUB(cudaMalloc(&d_up, total * sizeof(double)));
+    CUB(cudaMalloc(&d_meta, (size_t)n * sizeof(HostMeta)));
+    CUB(cudaMalloc(&d_status, sizeof(int)));
+    CUB(cudaMalloc(d_blobs, (size_t)n * stride * sizeof(double)));
+    CUB(cudaMalloc(d_probs, (size_t)n * sizeof(DevProblem)));
+    CUB(cudaMemcpyAsync(d_up, h_up, total * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUB(cudaMemcpyAsync(d_meta, h_meta, (size_t)n * sizeof(HostMeta), cudaMemcpyHostToDevice, st));
+    CUB(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    const int grid = std::min(n, 148 * 8);
+    setup_kernel<<<grid, 128, 0, st>>>(d_up, d_meta, n, NN, npad, stride, *d_blobs, *d_probs, spec->kernel, spec->jitter,
+                                       spec->br_ndf, d_status);
+    CUB(cudaGetLastError());
+    int h_status = 0;
+    CUB(cudaMemcpyAsync(&h_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUB(cudaStreamSynchronize(st));
+    if (h_status) { rc = fail(FOCT_EINVAL, "problem %d: degenerate depth grid or Kgg not positive definite (rho, jitter?)", h_status - 1); break; }
+#undef CUB
+  } while (0);
+  cudaFree(d_up); cudaFree(d_meta); cudaFree(d_status);
+  cudaFreeHost(h_up); cudaFreeHost(h_meta);
+  if (rc) { cudaFree(*d_blobs); cudaFree(*d_probs); *d_blobs = nullptr; *d_probs = nullptr; return rc; }
+  *NN_out = NN; *npad_out = npad; *stride_out = stride;
+  return 0;
+}
+
+// ------------------------------------------------------------------ ABI: trivia
+extern "C" int foct_version(void) { return FOCT_ABI_VERSION; }
+extern "C" const char* foct_last_error(void) { return g_err.c_str(); }
+extern "C" int foct_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+extern "C" void foct_model_spec_default(foct_model_spec* s, int kind) {
+  s->modulation = 0; s->kernel = 0; s->jitter = 1e-9; s->ygp_prior = 0; s->lambda_prior = 0;
+  s->sigma_mean = 1.0; s->sigma_sd = 0.1; s->theta_prior = kind == FOCT_EXPGP ? 0 : 1; s->br_ndf = 0;
+}
+extern "C" void foct_sampler_cfg_default(foct_sampler_cfg* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->chains = 4; c->n_warmup = 500; c->n_iter = 1500;  // FitOCT.R:43-44, server.R:469
+  c->adapt_delta = 0.8; c->max_treedepth = 10; c->stepsize0 = 1.0; c->seed = 1234;
+}
+extern "C" int foct_dims(int kind, int Nn, int* D, int* P_out) {
+  if (kind == FOCT_EXPGP) {
+    if (Nn < 1 || Nn > FOCT_MAX_NN) return fail(FOCT_EINVAL, "Nn=%d outside 1..%d", Nn, FOCT_MAX_NN);
+    if (D) *D = Nn + 5;
+    if (P_out) *P_out = Nn + 7;
+  } else if (kind == FOCT_MONOEXP) {
+    if (D) *D = 3;
+    if (P_out) *P_out = 5;
+  } else {
+    return fail(FOCT_EINVAL, "unknown model kind %d", kind);
+  }
+  return 0;
+}
+extern "C" int foct_expgp_grid(int Nn, int gridType, double* xGP) {
+  if (Nn < 1 || Nn > FOCT_MAX_NN || !xGP) return fail(FOCT_EINVAL, "Nn=%d outside 1..%d", Nn, FOCT_MAX_NN);
+  const double dx = 1.0 / (Nn + 1);
+  const double lo = gridType == FOCT_GRID_INTERNAL ? 0.5 * dx : 0.0, hi = gridType == FOCT_GRID_INTERNAL ? 1.0 - 0.5 * dx : 1.0;
+  for (int k = 0; k < Nn; ++k) xGP[k] = Nn == 1 ? lo : lo + (hi - lo) * (double)k / (double)(Nn - 1);
+  return 0;
+}
+
+// ------------------------------------------------------------------ ABI: basis / logp / predict
+extern "C" int foct_expgp_basis(const foct_problem* P, const foct_model_spec* spec, double* B_out) {
+  if (int rc = check_device()) return rc;
+  if (!B_out) return fail(FOCT_EINVAL, "NULL output");
+  int dev = 0, NN, npad;
+  size_t stride;
+  double* d_blobs;
+  DevProblem* d_probs;
+  CU(cudaGetDevice(&dev));
+  if (int rc = build_device_batch(FOCT_EXPGP, P, 1, spec, dev, 0, &NN, &npad, &stride, &d_blobs, &d_probs)) return rc;
+  cudaError_t e = cudaMemcpy2D(B_out, (size_t)P->N * sizeof(double), d_blobs + 3 * (size_t)npad, (size_t)npad * sizeof(double),
+                               (size_t)P->N * sizeof(double), NN, cudaMemcpyDeviceToHost);
+  cudaFree(d_blobs); cudaFree(d_probs);
+  if (e != cudaSuccess) return fail(FOCT_ECUDA, "copy of basis failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int foct_logp_grad(int kind, const foct_problem* P, int n, const foct_model_spec* spec, const double* q,
+                              int n_q, double* lp, double* grad, double* chi2) {
+  if (int rc = check_device()) return rc;
+  if (!q || !lp || !grad || n_q < 1) return fail(FOCT_EINVAL, "NULL q/lp/grad or n_q < 1");
+  int dev = 0, NN, npad;
+  size_t stride;
+  double* d_blobs;
+  DevProblem* d_probs;
+  CU(cudaGetDevice(&dev));
+  if (int rc = build_device_batch(kind, P, n, spec, dev, 0, &NN, &npad, &stride, &d_blobs, &d_probs)) return rc;
+  const int D = kind == FOCT_EXPGP ? NN + 5 : 3;
+  const size_t nq = (size_t)n * n_q;
+  double *d_q = nullptr, *d_lp = nullptr, *d_g = nullptr, *d_c2 = nullptr;
+  int rc = 0;
+  do {
+#define CUB(call) if ((call) != cudaSuccess) { rc = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); break; }
+    CUB(cudaMalloc(&d_q, nq * D * sizeof(double)));
+    CUB(cudaMalloc(&d_g, nq * D * sizeof(double)));
+    CUB(cudaMalloc(&d_lp, nq * sizeof(double)));
+    CUB(cudaMalloc(&d_c2, nq * sizeof(double)));
+    CUB(cudaMemcpy(d_q, q, nq * D * sizeof(double), cudaMemcpyHostToDevice));
+    LogpParams K;
+    K.blobs = d_blobs; K.blob_stride = stride; K.npad = npad; K.probs = d_probs; K.n_problems = n;
+    K.spec = dev_spec(*spec); K.q = d_q; K.n_q = n_q; K.lp = d_lp; K.grad = d_g; K.chi2 = d_c2;
+    const InstEntry* inst = inst_for(NN);
+    CUB(inst->launch_logp(spec->modulation, std::min(n, 148 * 4), 128, stride * sizeof(double), 0, K));
+    CUB(cudaDeviceSynchronize());
+    CUB(cudaMemcpy(lp, d_lp, nq * sizeof(double), cudaMemcpyDeviceToHost));
+    CUB(cudaMemcpy(grad, d_g, nq * D * sizeof(double), cudaMemcpyDeviceToHost));
+    if (chi2) CUB(cudaMemcpy(chi2, d_c2, nq * sizeof(double), cudaMemcpyDeviceToHost));
+#undef CUB
+  } while (0);
+  cudaFree(d_q); cudaFree(d_g); cudaFree(d_lp); cudaFree(d_c2); cudaFree(d_blobs); cudaFree(d_probs);
+  return rc;
+}
+
+extern "C" int foct_predict(int kind, const foct_problem* P, const foct_model_spec* spec, const double* draws,
+                            int n_draws, double* m, double* resid, double* dL) {
+  if (int rc = check_device()) return rc;
+  if (!draws || n_draws < 1) return fail(FOCT_EINVAL, "no draws");
+  int dev = 0, NN, npad;
+  size_t stride;
+  double* d_blobs;
+  DevProblem* d_probs;
+  CU(cudaGetDevice(&dev));
+  if (int rc = build_device_batch(kind, P, 1, spec, dev, 0, &NN, &npad, &stride, &d_blobs, &d_probs)) return rc;
+  const int P_out = kind == FOCT_EXPGP ? NN + 7 : 5;
+  const size_t tot = (size_t)n_draws * P->N;
+  double *d_dr = nullptr, *d_m = nullptr, *d_r = nullptr, *d_dl = nullptr;
+  int rc = 0;
+  do {
+#define CUB(call) if ((call) != cudaSuccess) { rc = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); break; }
+    CUB(cudaMalloc(&d_dr, (size_t)n_draws * P_out * sizeof(double)));
+    CUB(cudaMalloc(&d_m, tot * sizeof(double)));
+    CUB(cudaMalloc(&d_r, tot * sizeof(double)));
+    CUB(cudaMalloc(&d_dl, tot * sizeof(double)));
+    CUB(cudaMemcpy(d_dr, draws, (size_t)n_draws * P_out * sizeof(double), cudaMemcpyHostToDevice));
+    predict_kernel<<<(int)std::min<size_t>((tot + 255) / 256, 148 * 16), 256>>>(d_blobs, npad, P->N, NN, spec->modulation, P_out,
+                                                                                d_dr, n_draws, d_m, d_r, d_dl);
+    CUB(cudaGetLastError());
+    CUB(cudaDeviceSynchronize());
+    if (m) CUB(cudaMemcpy(m, d_m, tot * sizeof(double), cudaMemcpyDeviceToHost));
+    if (resid) CUB(cudaMemcpy(resid, d_r, tot * sizeof(double), cudaMemcpyDeviceToHost));
+    if (dL) CUB(cudaMemcpy(dL, d_dl, tot * sizeof(double), cudaMemcpyDeviceToHost));
+#undef CUB
+  } while (0);
+  cudaFree(d_dr); cudaFree(d_m); cudaFree(d_r); cudaFree(d_dl); cudaFree(d_blobs); cudaFree(d_probs);
+  return rc;
+}
+
+// ------------------------------------------------------------------ ABI: plan
+static int validate_cfg(const foct_sampler_cfg* c) {
+  if (!c) return fail(FOCT_EINVAL, "NULL sampler cfg");
+  if (c->chains < 1 || c->chains > FOCT_MAX_CHAINS) return fail(FOCT_EINVAL, "chains=%d outside 1..%d", c->chains, FOCT_MAX_CHAINS);
+  if (c->n_warmup < 0 || c->n_iter < c->n_warmup || c->n_iter < 1) return fail(FOCT_EINVAL, "need 0 <= n_warmup <= n_iter, n_iter >= 1 (nb_iter = nb_warmup + nb_sample, FitOCT.R:121)");
+  if (c->max_treedepth > FOCT_STACK_LEVELS + 1) return fail(FOCT_EINVAL, "max_treedepth=%d > %d", c->max_treedepth, FOCT_STACK_LEVELS + 1);
+  if (c->init_mode < 0 || c->init_mode > 2 || (c->init_mode == 2 && !c->init)) return fail(FOCT_EINVAL, "bad init_mode / init");
+  return 0;
+}
+
+static int plan_create_on(int device, int kind, const foct_problem* P, int n, const foct_model_spec* spec,
+                          const foct_sampler_cfg* cfg, const double* init_slice, int want_draws, int want_summary,
+                          foct_plan** out) {
+  if (int rc = validate_cfg(cfg)) return rc;
+  foct_plan* p = new foct_plan();
+  p->device = device; p->kind = kind; p->n = n; p->spec = *spec; p->cfg = *cfg;
+  p->cfg.init = nullptr; p->cfg.devices = nullptr; p->cfg.n_devices = 0;
+  p->want_draws = want_draws != 0; p->want_summary = want_summary != 0;
+  p->n_post = cfg->n_iter - cfg->n_warmup;
+  p->n_saved = cfg->save_warmup ? cfg->n_iter : p->n_post;
+#define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int rc_ = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); plan_free(p); return rc_; } } while (0)
+  CUP(cudaSetDevice(device));
+  CUP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  CUP(cudaEventCreate(&p->ev0));
+  CUP(cudaEventCreate(&p->ev1));
+  if (int rc = build_device_batch(kind, P, n, spec, device, p->stream, &p->NN, &p->npad, &p->blob_stride, &p->d_blobs, &p->d_probs)) {
+    plan_free(p);
+    return rc;
+  }
+  p->D = kind == FOCT_EXPGP ? p->NN + 5 : 3;
+  p->P_out = p->D + 2;
+  const size_t pc = (size_t)n * cfg->chains;
+  const bool need_draws = p->want_draws || p->want_summary;
+  if (need_draws) {
+    CUP(cudaMalloc(&p->d_draws, pc * p->n_saved * p->P_out * sizeof(double)));
+    if (p->want_draws) CUP(cudaMalloc(&p->d_sparams, pc * p->n_saved * 6 * sizeof(double)));
+  }
+  if (p->want_summary) CUP(cudaMalloc(&p->d_summary, (size_t)n * p->P_out * FOCT_N_SUMMARY_COLS * sizeof(double)));
+  CUP(cudaMalloc(&p->d_stepsize, pc * sizeof(double)));
+  CUP(cudaMalloc(&p->d_invm, pc * p->D * sizeof(double)));
+  CUP(cudaMalloc(&p->d_nleap, pc * 2 * sizeof(double)));
+  CUP(cudaMalloc(&p->d_ndiv, pc * sizeof(double)));
+  CUP(cudaMalloc(&p->d_counter, sizeof(int)));
+  if (cfg->init_mode == 2) {
+    CUP(cudaMalloc(&p->d_init, pc * p->D * sizeof(double)));
+    CUP(cudaMemcpy(p->d_init, init_slice, pc * p->D * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  p->inst = inst_for(p->NN);
+  p->block = 32 * std::min(cfg->chains, FOCT_CTA_CHAINS);
+  p->smem = p->blob_stride * sizeof(double);
+  CUP(p->inst->nuts_occupancy(spec->modulation, p->block, p->smem, &p->blocks_per_sm, &p->regs));
+  if (p->blocks_per_sm < 1) { plan_free(p); return fail(FOCT_EINVAL, "sampling kernel does not fit an SM (smem %zu B)", p->smem); }
+  cudaDeviceProp prop;
+  CUP(cudaGetDeviceProperties(&prop, device));
+  const int groups = (cfg->chains + FOCT_CTA_CHAINS - 1) / FOCT_CTA_CHAINS;
+  p->grid = (int)std::min<long long>((long long)n * groups, (long long)prop.multiProcessorCount * p->blocks_per_sm);
+#undef CUP
+  *out = p;
+  return 0;
+}
+
+extern "C" int foct_plan_create(int kind, const foct_problem* P, int n, const foct_model_spec* spec,
+                                const foct_sampler_cfg* cfg, int want_draws, int want_summary, foct_plan** plan) {
+  if (int rc = check_device()) return rc;
+  if (!plan) return fail(FOCT_EINVAL, "NULL plan pointer");
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (cfg && cfg->n_devices == 1 && cfg->devices) dev = cfg->devices[0];
+  return plan_create_on(dev, kind, P, n, spec, cfg, cfg ? cfg->init : nullptr, want_draws, want_summary, plan);
+}
+
+extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
+  if (!p) return fail(FOCT_EINVAL, "NULL plan");
+  CU(cudaSetDevice(p->device));
+  SamplerParams K;
+  std::memset(&K, 0, sizeof(K));
+  K.blobs = p->d_blobs; K.blob_stride = p->blob_stride; K.npad = p->npad; K.probs = p->d_probs; K.n_problems = p->n;
+  K.spec = dev_spec(p->spec);
+  const foct_sampler_cfg& c = p->cfg;
+  K.chains = c.chains; K.n_warmup = c.n_warmup; K.n_iter = c.n_iter; K.max_depth = c.max_treedepth > 0 ? c.max_treedepth : 10;
+  K.save_warmup = c.save_warmup; K.init_mode = c.init_mode;
+  K.adapt_delta = c.adapt_delta; K.stepsize0 = c.stepsize0; K.gamma = c.gamma; K.kappa = c.kappa; K.t0 = c.t0;
+  K.init_buffer = c.init_buffer; K.term_buffer = c.term_buffer; K.window = c.window;
+  K.seed = seed; K.init = p->d_init;
+  K.draws = p->d_draws; K.sparams = p->d_sparams; K.stepsize = p->d_stepsize; K.inv_metric = p->d_invm;
+  K.n_leapfrog = p->d_nleap; K.n_divergent = p->d_ndiv; K.work_counter = p->d_counter;
+  CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), p->stream));
+  CU(cudaEventRecord(p->ev0, p->stream));
+  CU(p->inst->launch_nuts(p->spec.modulation, p->grid, p->block, p->smem, p->stream, K));
+  CU(cudaEventRecord(p->ev1, p->stream));
+  if (p->want_summary) {
+    const int off = c.save_warmup ? c.n_warmup : 0;
+    CU(launch_summary(p->d_draws, p->n, p->n_saved, off, p->n_post, c.chains, p->P_out, p->d_summary, p->stream));
+  }
+  p->ran = true;
+  return 0;
+}
+
+extern "C" int foct_plan_sync(foct_plan* p, float* kernel_ms) {
+  if (!p) return fail(FOCT_EINVAL, "NULL plan");
+  CU(cudaSetDevice(p->device));
+  CU(cudaStreamSynchronize(p->stream));
+  if (kernel_ms) {
+    *kernel_ms = 0.f;
+    if (p->ran) CU(cudaEventElapsedTime(kernel_ms, p->ev0, p->ev1));
+  }
+  return 0;
+}
+
+extern "C" int foct_plan_fetch(foct_plan* p, foct_result* R) {
+  if (!p || !R) return fail(FOCT_EINVAL, "NULL plan/result");
+  if (!p->ran) return fail(FOCT_EINVAL, "plan has not been run");
+  CU(cudaSetDevice(p->device));
+  CU(cudaStreamSynchronize(p->stream));
+  const size_t pc = (size_t)p->n * p->cfg.chains;
+  if (R->draws) {
+    if (!p->want_draws) return fail(FOCT_EINVAL, "plan was created without draws");
+    CU(cudaMemcpy(R->draws, p->d_draws, pc * p->n_saved * p->P_out * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (R->sampler_params) {
+    if (!p->d_sparams) return fail(FOCT_EINVAL, "plan was created without draws");
+    CU(cudaMemcpy(R->sampler_params, p->d_sparams, pc * p->n_saved * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (R->summary) {
+    if (!p->want_summary) return fail(FOCT_EINVAL, "plan was created without summary");
+    CU(cudaMemcpy(R->summary, p->d_summary, (size_t)p->n * p->P_out * FOCT_N_SUMMARY_COLS * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (R->stepsize) CU(cudaMemcpy(R->stepsize, p->d_stepsize, pc * sizeof(double), cudaMemcpyDeviceToHost));
+  if (R->inv_metric) CU(cudaMemcpy(R->inv_metric, p->d_invm, pc * p->D * sizeof(double), cudaMemcpyDeviceToHost));
+  if (R->n_leapfrog) CU(cudaMemcpy(R->n_leapfrog, p->d_nleap, pc * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (R->n_divergent) CU(cudaMemcpy(R->n_divergent, p->d_ndiv, pc * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" void foct_plan_destroy(foct_plan* p) { plan_free(p); }
+
+// ------------------------------------------------------------------ ABI: one-shot sampling, sharded over devices
+static int sample_shard(int device, int kind, const foct_problem* P, int first, int n, const foct_model_spec* spec,
+                        const foct_sampler_cfg* cfg, foct_result* R, int D, int P_out) {
+  const int C = cfg->chains;
+  const int n_saved = cfg->save_warmup ? cfg->n_iter : cfg->n_iter - cfg->n_warmup;
+  foct_plan* p = nullptr;
+  const double* init_slice = cfg->init_mode == 2 && cfg->init ? cfg->init + (size_t)first * C * D : nullptr;
+  int rc = plan_create_on(device, kind, P + first, n, spec, cfg, init_slice, R->draws || R->sampler_params, R->summary != nullptr, &p);
+  if (rc) return rc;
+  rc = foct_plan_run(p, cfg->seed);
+  if (!rc) {
+    foct_result S = *R;
+    const size_t pc0 = (size_t)first * C;
+    if (S.draws) S.draws += pc0 * n_saved * P_out;
+    if (S.sampler_params) S.sampler_params += pc0 * n_saved * 6;
+    if (S.summary) S.summary += (size_t)first * P_out * FOCT_N_SUMMARY_COLS;
+    if (S.stepsize) S.stepsize += pc0;
+    if (S.inv_metric) S.inv_metric += pc0 * D;
+    if (S.n_leapfrog) S.n_leapfrog += pc0 * 2;
+    if (S.n_divergent) S.n_divergent += pc0;
+    if (S.sampler_params && !S.draws) { /* plan allocated both; fetch copes */ }
+    rc = foct_plan_fetch(p, &S);
+  }
+  plan_free(p);
+  return rc;
+}
+
+extern "C" int foct_sample(int kind, const foct_problem* P, int n, const foct_model_spec* spec,
+                           const foct_sampler_cfg* cfg, foct_result* R) {
+  if (int rc = check_device()) return rc;
+  if (!P || !spec || !cfg || !R || n < 1) return fail(FOCT_EINVAL, "NULL argument or empty batch");
+  if (int rc = validate_cfg(cfg)) return rc;
+  int D, P_out;
+  if (int rc = foct_dims(kind, P[0].Nn, &D, &P_out)) return rc;
+  std::vector<int> devs;
+  if (cfg->n_devices > 0 && cfg->devices) devs.assign(cfg->devices, cfg->devices + cfg->n_devices);
+  else { int d = 0; CU(cudaGetDevice(&d)); devs.push_back(d); }
+  const int ndev_avail = foct_device_count();
+  for (int d : devs) if (d < 0 || d >= ndev_avail) return fail(FOCT_EINVAL, "device %d not present (%d devices)", d, ndev_avail);
+  const int G = (int)std::min<size_t>(devs.size(), (size_t)n);
+  if (G == 1) return sample_shard(devs[0], kind, P, 0, n, spec, cfg, R, D, P_out);
+  // independent contiguous shards, one host thread per GPU, no collective
+  std::vector<std::thread> th;
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  for (int gidx = 0; gidx < G; ++gidx) {
+    const int first = (int)((long long)n * gidx / G), last = (int)((long long)n * (gidx + 1) / G);
+    th.emplace_back([&, gidx, first, last]() {
+      rcs[gidx] = sample_shard(devs[gidx], kind, P, first, last - first, spec, cfg, R, D, P_out);
+      if (rcs[gidx]) errs[gidx] = g_err;
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int gidx = 0; gidx < G; ++gidx)
+    if (rcs[gidx]) { g_err = errs[gidx]; return rcs[gidx]; }
+  return 0;
+}
+
+extern "C" int foct_expgp_sample(const foct_problem* P, int n, const foct_model_spec* spec, const foct_sampler_cfg* cfg,
+                                 foct_result* R) {
+  return foct_sample(FOCT_EXPGP, P, n, spec, cfg, R);
+}
+extern "C" int foct_monoexp_sample(const foct_problem* P, int n, const foct_model_spec* spec, const foct_sampler_cfg* cfg,
+                                   foct_result* R) {
+  return foct_sample(FOCT_MONOEXP, P, n, spec, cfg, R);
+}
+
+
+// ------------------------------------------------------------------ ABI: MonoExp MAP
+extern "C" int foct_monoexp_map(const foct_problem* P, int n, const foct_model_spec* spec, const double* init,
+                                double* theta, double* hessian, double* br, int* status) {
+  if (int rc = check_device()) return rc;
+  if (!theta) return fail(FOCT_EINVAL, "NULL theta output");
+  int dev = 0, NN, npad;
+  size_t stride;
+  double* d_blobs;
+  DevProblem* d_probs;
+  CU(cudaGetDevice(&dev));
+  if (int rc = build_device_batch(FOCT_MONOEXP, P, n, spec, dev, 0, &NN, &npad, &stride, &d_blobs, &d_probs)) return rc;
+  double *d_init = nullptr, *d_th = nullptr, *d_H = nullptr, *d_br = nullptr;
+  int* d_st = nullptr;
+  int rc = 0;
+  do {
+#define CUB(call) if ((call) != cudaSuccess) { rc = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); break; }
+    CUB(cudaMalloc(&d_th, (size_t)n * 3 * sizeof(double)));
+    CUB(cudaMalloc(&d_H, (size_t)n * 9 * sizeof(double)));
+    CUB(cudaMalloc(&d_br, (size_t)n * sizeof(double)));
+    CUB(cudaMalloc(&d_st, (size_t)n * sizeof(int)));
+    if (init) {
+      CUB(cudaMalloc(&d_init, (size_t)n * 3 * sizeof(double)));
+      CUB(cudaMemcpy(d_init, init, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    map_kernel<<<(n + 3) / 4, 128>>>(d_blobs, stride, npad, d_probs, n, spec->theta_prior, d_init, d_th, d_H, d_br, d_st);
+    CUB(cudaGetLastError());
+    CUB(cudaDeviceSynchronize());
+    CUB(cudaMemcpy(theta, d_th, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (hessian) CUB(cudaMemcpy(hessian, d_H, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (br) CUB(cudaMemcpy(br, d_br, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (status) CUB(cudaMemcpy(status, d_st, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+#undef CUB
+  } while (0);
+  cudaFree(d_init); cudaFree(d_th); cudaFree(d_H); cudaFree(d_br); cudaFree(d_st); cudaFree(d_blobs); cudaFree(d_probs);
+  return rc;
+}
+
+// ------------------------------------------------------------------ ABI: fp64 peak
+extern "C" int foct_fp64_peak(int device, double* tflops, double* sm_mhz) {
+  if (int rc = check_device()) return rc;
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int grid = prop.multiProcessorCount * 8, block = 256, iters = 1 << 16;
+  double* d_out = nullptr;
+  CU(cudaMalloc(&d_out, (size_t)grid * block * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    CU(cudaEventRecord(e0));
+    dfma_peak_kernel<<<grid, block>>>(d_out, iters, 0.999999, 1e-9);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+  const double flops = 2.0 * 8.0 * (double)iters * (double)grid * block;
+  if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+  if (sm_mhz) *sm_mhz = prop.clockRate / 1000.0;
+  return 0;
+}

@@ -1,0 +1,343 @@
+// foct_nuts.cuh — on-device multinomial NUTS with Stan-style windowed adaptation, one warp per chain.
+//
+// Restates Stan's published diag_e NUTS (MODEL_SPEC §7; SURVEY a-7..a-10) in ITERATIVE form: the recursive
+// build_tree becomes a leaf loop with an O(depth) stack of pending "init" subtrees kept in per-lane local
+// memory; merges, the three U-turn checks per merge, multinomial proposal selection and the random-number
+// draw sites are exactly those of the recursion, so the CPU oracle (recursive) and this kernel consume the
+// same Philox variates and build the same trees.
+#pragma once
+#include "foct_device.cuh"
+
+namespace foct {
+
+struct SamplerParams {
+  const double* blobs;      // [n_problems][blob_stride] staged profile blobs
+  size_t blob_stride;       // doubles per blob = (3 + NN) * npad
+  int npad;
+  const DevProblem* probs;
+  int n_problems;
+  DevSpec spec;
+  int chains, n_warmup, n_iter, max_depth, save_warmup, init_mode;
+  double adapt_delta, stepsize0, gamma, kappa, t0;
+  int init_buffer, term_buffer, window;
+  unsigned long long seed;
+  const double* init;       // [n_problems][chains][D] or nullptr
+  double* draws;            // [n_problems][n_saved][chains][P_out] or nullptr
+  double* sparams;          // [n_problems][n_saved][chains][6] or nullptr
+  double* stepsize;         // [n_problems][chains]
+  double* inv_metric;       // [n_problems][chains][D]
+  double* n_leapfrog;       // [n_problems][chains][2]
+  double* n_divergent;      // [n_problems][chains]
+  int* work_counter;        // dynamic profile scheduler
+};
+
+__device__ __forceinline__ double lse2(double a, double b) {
+  if (a == -CUDART_INF) return b;
+  if (b == -CUDART_INF) return a;
+  const double mx = fmax(a, b), mn = fmin(a, b);
+  return mx + log1p(exp(mn - mx));
+}
+
+// The three generalised U-turn checks of one merge (init ++ final), each a pair of dot products:
+//   around the merged tree, init + first state of final, final + last state of init.
+__device__ __forceinline__ bool merge_persists(double invM, double i_rho, double i_pbeg, double i_pend, double f_rho,
+                                               double f_pbeg, double f_pend, int lane) {
+  const double ps_b = invM * i_pbeg, ps_e = invM * f_pend, ps_fb = invM * f_pbeg, ps_ie = invM * i_pend;
+  const double r_sub = i_rho + f_rho, r_b = i_rho + f_pbeg, r_c = f_rho + i_pend;
+  double v[8];
+  v[0] = ps_e * r_sub; v[1] = ps_b * r_sub;
+  v[2] = ps_fb * r_b;  v[3] = ps_b * r_b;
+  v[4] = ps_e * r_c;   v[5] = ps_ie * r_c;
+  v[6] = lane == 0 ? 1.0 : 0.0; v[7] = v[6];
+  const double s = warp_reduce_scatter<8>(v, lane);
+  return __all_sync(FOCT_FULL, s > 0.0);
+}
+
+// One leapfrog step of the integrator state (q, p, g, V, chi2) of this lane.  Not inlined on purpose: the
+// sweep inside gets a register allocation of its own and the tree state of the caller is parked by the ABI.
+template <int NN, int MOD>
+__device__ __noinline__ void leapfrog(const double* __restrict__ blob, int npad, const DevProblem* P, const DevSpec* S,
+                                      double eps, double invM, double* zq, double* zp, double* zg, double* zV,
+                                      double* zc2, int lane) {
+  double p = fma(0.5 * eps, *zg, *zp);
+  double q = fma(eps * invM, p, *zq);
+  const Eval ev = warp_logp_grad<NN, MOD>(blob, npad, *P, *S, q, lane);
+  p = fma(0.5 * eps, ev.g, p);
+  *zq = q; *zp = p; *zg = ev.g; *zV = -ev.lp; *zc2 = ev.chi2;
+}
+
+template <int NN, int MOD>
+__device__ void run_chain(const SamplerParams& K, const DevProblem& P, const double* __restrict__ blob, int prob,
+                          int chain, int lane) {
+  using DM = Dims<NN>;
+  constexpr int D = DM::D;
+  constexpr int P_OUT = DM::P_OUT;
+  const bool act = lane < D;
+  const int npad = K.npad;
+  Rng rng;
+  rng.seed(K.seed, P.id, chain);
+  uint32_t rb[4];
+
+  // ---- initial point (MODEL_SPEC §7 init_mode)
+  double q = 0.0;
+  if (act) {
+    rng.block(0, SITE_INIT, 0, (uint32_t)lane, 0, rb);
+    if (K.init_mode == 2 && K.init) {
+      q = K.init[((size_t)prob * K.chains + chain) * D + lane];
+    } else if (K.init_mode == 1) {
+      q = -2.0 + 4.0 * u53(rb[0], rb[1]);
+    } else {
+      if (lane < 3) q = P.theta0[lane];
+      else if (lane < 3 + NN) q = 0.01 * normal_from(rb);
+      else if (lane == 3 + NN) q = log(0.1);
+      else q = 0.0;
+    }
+  }
+  Eval ev = warp_logp_grad<NN, MOD>(blob, npad, P, K.spec, q, lane);
+  double g = ev.g, V = -ev.lp, c2 = ev.chi2;
+  const double invM0 = 1.0;
+  double invM = invM0;
+  double eps = K.stepsize0 > 0.0 ? K.stepsize0 : 1.0;
+
+  // ---- adaptation state (Stan windowed_adaptation / welford_var_estimator / stepsize_adaptation)
+  int a_num_warmup, a_init_buffer, a_term_buffer, a_base_window;
+  {
+    int ib = K.init_buffer > 0 ? K.init_buffer : 75, tb = K.term_buffer > 0 ? K.term_buffer : 50;
+    int bw = K.window > 0 ? K.window : 25, nw = K.n_warmup;
+    if (nw < 20) {
+      a_num_warmup = a_init_buffer = a_term_buffer = a_base_window = 0;
+    } else {
+      if (ib + bw + tb > nw) { ib = (int)(0.15 * nw); tb = (int)(0.1 * nw); bw = nw - (ib + tb); }
+      a_num_warmup = nw; a_init_buffer = ib; a_term_buffer = tb; a_base_window = bw;
+    }
+  }
+  int a_counter = 0, a_wsize = a_base_window, a_next = a_init_buffer + a_base_window - 1;
+  double w_n = 0.0, w_mean = 0.0, w_m2 = 0.0;
+  const double da_delta = K.adapt_delta > 0.0 ? K.adapt_delta : 0.8;
+  const double da_gamma = K.gamma > 0.0 ? K.gamma : 0.05, da_kappa = K.kappa > 0.0 ? K.kappa : 0.75;
+  const double da_t0 = K.t0 > 0.0 ? K.t0 : 10.0;
+  double da_mu = log(10.0 * eps), da_counter = 0.0, da_sbar = 0.0, da_xbar = 0.0;
+  const int max_depth = K.max_depth > 0 ? (K.max_depth <= FOCT_STACK_LEVELS + 1 ? K.max_depth : FOCT_STACK_LEVELS + 1) : 10;
+  const double log08 = log(0.8);
+
+  double nlf_warm = 0.0, nlf_samp = 0.0, ndiv = 0.0;
+  const int n_saved = K.save_warmup ? K.n_iter : K.n_iter - K.n_warmup;
+
+  // Stan's init_stepsize heuristic; `it_site` tags the RNG sites of this call.
+  auto init_stepsize = [&](uint32_t it_site) {
+    if (!(eps > 0.0) || eps > 1e7) return;
+    uint32_t attempt = 0;
+    int direction = 0;
+    for (;;) {
+      double zq = q, zg = g, zV = V, zc2 = c2, zp = 0.0;
+      if (act) {
+        rng.block(it_site, SITE_INITEPS, attempt, (uint32_t)lane, 0, rb);
+        zp = normal_from(rb) / sqrt(invM);
+      }
+      ++attempt;
+      const double H0 = zV + 0.5 * warp_sum(invM * zp * zp);
+      leapfrog<NN, MOD>(blob, npad, &P, &K.spec, eps, invM, &zq, &zp, &zg, &zV, &zc2, lane);
+      double h = zV + 0.5 * warp_sum(invM * zp * zp);
+      if (isnan(h)) h = CUDART_INF;
+      const double dH = H0 - h;
+      if (direction == 0) { direction = dH > log08 ? 1 : -1; continue; }
+      if (direction == 1 && !(dH > log08)) break;
+      if (direction == -1 && !(dH < log08)) break;
+      eps = direction == 1 ? 2.0 * eps : 0.5 * eps;
+      if (eps > 1e7 || eps == 0.0 || attempt > 200) break;
+    }
+  };
+
+  if (K.n_warmup > 0) init_stepsize(0);
+
+  // pending "init" subtrees, one slot per level (local memory; touched only at merges)
+  double st_rho[FOCT_STACK_LEVELS], st_pbeg[FOCT_STACK_LEVELS], st_pend[FOCT_STACK_LEVELS];
+  double st_qp[FOCT_STACK_LEVELS], st_gp[FOCT_STACK_LEVELS];
+  double st_lsw[FOCT_STACK_LEVELS], st_V[FOCT_STACK_LEVELS], st_c2[FOCT_STACK_LEVELS], st_H[FOCT_STACK_LEVELS];
+
+  for (int it = 0; it < K.n_iter; ++it) {
+    // ================================================================ one NUTS transition
+    double p = 0.0;
+    if (act) {
+      rng.block((uint32_t)it, SITE_MOM, 0, (uint32_t)lane, 0, rb);
+      p = normal_from(rb) / sqrt(invM);
+    }
+    const double H0 = V + 0.5 * warp_sum(invM * p * p);
+    // trajectory ends (q, p, g) and the running sample
+    double fq = q, fp = p, fg = g, bq = q, bp = p, bg = g;
+    double sq = q, sg = g, sV = V, sc2 = c2, sH = H0;
+    double rho = p, lsw = 0.0, sum_metro = 0.0;
+    int n_leap = 0, depth = 0;
+    bool divergent = false;
+
+    while (depth < max_depth) {
+      rng.block((uint32_t)it, SITE_DIR, (uint32_t)depth, 0, 0, rb);
+      const bool fwd = u53(rb[0], rb[1]) > 0.5;
+      const double u_top = u53(rb[2], rb[3]);
+      // integrator starts from the end being extended; the old trajectory is the "init" half of the top merge
+      double zq = fwd ? fq : bq, zp = fwd ? fp : bp, zg = fwd ? fg : bg, zV = 0.0, zc2 = 0.0;
+      const double old_end_p = zp, other_end_p = fwd ? bp : fp;
+      const double eps_s = fwd ? eps : -eps;
+      // current (growing) subtree
+      double c_lsw = -CUDART_INF, c_rho = 0.0, c_pbeg = 0.0, c_pend = 0.0, c_qp = 0.0, c_gp = 0.0;
+      double c_V = 0.0, c_c2 = 0.0, c_H = 0.0;
+      bool valid = true;
+      const uint32_t n_leaves = 1u << depth;
+      for (uint32_t n = 0; n < n_leaves; ++n) {
+        leapfrog<NN, MOD>(blob, npad, &P, &K.spec, eps_s, invM, &zq, &zp, &zg, &zV, &zc2, lane);
+        ++n_leap;
+        double h = zV + 0.5 * warp_sum(invM * zp * zp);
+        if (isnan(h)) h = CUDART_INF;
+        if (h - H0 > 1000.0) divergent = true;
+        const double dw = H0 - h;
+        sum_metro += dw > 0.0 ? 1.0 : exp(dw);
+        c_lsw = dw; c_rho = zp; c_pbeg = zp; c_pend = zp; c_qp = zq; c_gp = zg; c_V = zV; c_c2 = zc2; c_H = h;
+        if (divergent) { valid = false; break; }
+        // merge completed siblings upward: bit k of n set  <=>  slot k holds the init half
+        int k = 0;
+        for (; (n >> k) & 1u; ++k) {
+          const double i_lsw = st_lsw[k];
+          const double lsw_sub = lse2(i_lsw, c_lsw);
+          bool take_final = true;
+          if (!(c_lsw > lsw_sub)) {
+            rng.block((uint32_t)it, SITE_MERGE, (uint32_t)depth, n, (uint32_t)(k + 1), rb);
+            take_final = u53(rb[0], rb[1]) < exp(c_lsw - lsw_sub);
+          }
+          const double i_rho = st_rho[k], i_pbeg = st_pbeg[k], i_pend = st_pend[k];
+          const bool persist = merge_persists(invM, i_rho, i_pbeg, i_pend, c_rho, c_pbeg, c_pend, lane);
+          if (!take_final) { c_qp = st_qp[k]; c_gp = st_gp[k]; c_V = st_V[k]; c_c2 = st_c2[k]; c_H = st_H[k]; }
+          c_lsw = lsw_sub; c_rho = i_rho + c_rho; c_pbeg = i_pbeg;
+          if (!persist) { valid = false; break; }
+        }
+        if (!valid) break;
+        if (n + 1 < n_leaves) {
+          st_rho[k] = c_rho; st_pbeg[k] = c_pbeg; st_pend[k] = c_pend; st_qp[k] = c_qp; st_gp[k] = c_gp;
+          st_lsw[k] = c_lsw; st_V[k] = c_V; st_c2[k] = c_c2; st_H[k] = c_H;
+        }
+      }
+      if (fwd) { fq = zq; fp = zp; fg = zg; } else { bq = zq; bp = zp; bg = zg; }
+      if (!valid) break;
+      ++depth;
+      if (c_lsw > lsw || u_top < exp(c_lsw - lsw)) { sq = c_qp; sg = c_gp; sV = c_V; sc2 = c_c2; sH = c_H; }
+      lsw = lse2(lsw, c_lsw);
+      const bool persist = merge_persists(invM, rho, other_end_p, old_end_p, c_rho, c_pbeg, c_pend, lane);
+      rho += c_rho;
+      if (!persist) break;
+    }
+    const double accept = sum_metro / (double)n_leap;
+    q = sq; g = sg; V = sV; c2 = sc2;
+    const double eps_used = eps;
+
+    // ================================================================ bookkeeping, write-back, adaptation
+    const bool warm = it < K.n_warmup;
+    if (warm) nlf_warm += n_leap; else { nlf_samp += n_leap; ndiv += divergent ? 1.0 : 0.0; }
+    const int save_idx = K.save_warmup ? it : it - K.n_warmup;
+    if (save_idx >= 0) {
+      const size_t row = ((size_t)prob * n_saved + save_idx) * K.chains + chain;
+      if (K.draws) {
+        double v;
+        if (DM::GP) {
+          v = (lane == 3 + NN || lane == 4 + NN) ? exp(q) : q;
+        } else {
+          v = q;
+        }
+        if (lane == D) v = P.prior_PD ? CUDART_NAN : c2 / P.br_ndf;
+        if (lane == D + 1) v = -V;
+        if (lane < P_OUT) K.draws[row * P_OUT + lane] = v;
+      }
+      if (K.sparams && lane < 6) {
+        double v = accept;
+        if (lane == 1) v = eps_used;
+        if (lane == 2) v = (double)depth;
+        if (lane == 3) v = (double)n_leap;
+        if (lane == 4) v = divergent ? 1.0 : 0.0;
+        if (lane == 5) v = sH;
+        K.sparams[row * 6 + lane] = v;
+      }
+    }
+    if (warm) {
+      // dual averaging
+      da_counter += 1.0;
+      const double stat = accept > 1.0 ? 1.0 : accept;
+      const double eta = 1.0 / (da_counter + da_t0);
+      da_sbar = (1.0 - eta) * da_sbar + eta * (da_delta - stat);
+      const double x = da_mu - da_sbar * sqrt(da_counter) / da_gamma;
+      const double x_eta = pow(da_counter, -da_kappa);
+      da_xbar = (1.0 - x_eta) * da_xbar + x_eta * x;
+      eps = exp(x);
+      // windowed variance
+      const bool in_window = a_counter >= a_init_buffer && a_counter < a_num_warmup - a_term_buffer && a_counter != a_num_warmup;
+      if (in_window) {
+        w_n += 1.0;
+        const double delta = q - w_mean;
+        w_mean += delta / w_n;
+        w_m2 += (q - w_mean) * delta;
+      }
+      const bool end_window = a_counter == a_next && a_counter != a_num_warmup;
+      if (end_window) {
+        if (a_next != a_num_warmup - a_term_buffer - 1) {
+          a_wsize *= 2;
+          a_next = a_counter + a_wsize;
+          if (a_next != a_num_warmup - a_term_buffer - 1) {
+            const int boundary = a_next + 2 * a_wsize;
+            if (boundary >= a_num_warmup - a_term_buffer) a_next = a_num_warmup - a_term_buffer - 1;
+          }
+        }
+        const double var = w_m2 / (w_n - 1.0);
+        if (act) invM = (w_n / (w_n + 5.0)) * var + 1e-3 * (5.0 / (w_n + 5.0));
+        w_n = 0.0; w_mean = 0.0; w_m2 = 0.0;
+        ++a_counter;
+        init_stepsize((uint32_t)(it + 1));
+        da_mu = log(10.0 * eps);
+        da_counter = 0.0; da_sbar = 0.0; da_xbar = 0.0;
+      } else {
+        ++a_counter;
+      }
+      if (it == K.n_warmup - 1) eps = exp(da_xbar);
+    }
+  }
+  const size_t pc = (size_t)prob * K.chains + chain;
+  if (lane == 0) {
+    if (K.stepsize) K.stepsize[pc] = eps;
+    if (K.n_leapfrog) { K.n_leapfrog[pc * 2] = nlf_warm; K.n_leapfrog[pc * 2 + 1] = nlf_samp; }
+    if (K.n_divergent) K.n_divergent[pc] = ndiv;
+  }
+  if (K.inv_metric && act) K.inv_metric[pc * D + lane] = invM;
+}
+
+// Persistent CTAs of up to FOCT_CTA_CHAINS warps.  A work item is (profile, group of <= 4 chains); each CTA
+// repeatedly claims an item from the atomic work counter, stages the profile blob into shared memory with
+// one TMA bulk copy and runs its chains to completion.  Register budget follows the blob size: the more
+// control points, the fewer CTAs fit an SM by shared memory, the more registers each thread may use.
+#define FOCT_CTA_CHAINS 4
+template <int NN>
+struct NutsBounds {
+  static constexpr int MINB = NN <= 10 ? 4 : (NN <= 15 ? 3 : 2);
+};
+
+template <int NN, int MOD>
+__global__ void __launch_bounds__(32 * FOCT_CTA_CHAINS, NutsBounds<NN>::MINB) nuts_kernel(const SamplerParams K) {
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t mbar;
+  __shared__ int s_next;
+  __shared__ DevProblem s_prob;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int groups = (K.chains + FOCT_CTA_CHAINS - 1) / FOCT_CTA_CHAINS;
+  const int n_items = K.n_problems * groups;
+  mbar_init(&mbar);
+  uint32_t phase = 0;
+  for (;;) {
+    if (threadIdx.x == 0) s_next = atomicAdd(K.work_counter, 1);
+    __syncthreads();
+    const int w = s_next;
+    if (w >= n_items) break;
+    const int j = w / groups, chain = (w % groups) * FOCT_CTA_CHAINS + warp;
+    if (threadIdx.x == 0) s_prob = K.probs[j];
+    stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase);
+    __syncthreads();
+    if (chain < K.chains) run_chain<NN, MOD>(K, s_prob, smem, j, chain, lane);
+    __syncthreads();
+  }
+}
+
+}  // namespace foct

@@ -23,7 +23,7 @@ extern "C" {
 #define FOCT_ABI_VERSION 1
 
 #define FOCT_MAX_D 32        /* unconstrained dimensions live one-per-lane in a warp */
-#define FOCT_MAX_NN 27       /* => D = Nn + 5 <= 32 (reference UI range is 5..20, ShinyInterface/ui.R:200-207) */
+#define FOCT_MAX_NN 25       /* => D = Nn + 5 <= 30, P_out = Nn + 7 <= 32 (reference UI range is 5..20, ShinyInterface/ui.R:200-207) */
 #define FOCT_MAX_CHAINS 8
 #define FOCT_N_SAMPLER_PARAMS 6 /* accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__ */
 #define FOCT_N_SUMMARY_COLS 11  /* mean, se_mean, sd, 2.5%, 25%, 50%, 75%, 97.5%, n_eff, Rhat (rstan::summary), Bulk_ESS */
