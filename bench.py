@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — fitExpGP batch throughput (BASELINE.json metric: min-ESS/s and draws/s) on B200.
+
+One "step" = one complete NUTS fit (warm-up + sampling + on-device summary) of a batch of synthetic
+synthData.R-shaped profiles, 4 chains each (BASELINE.json configs[2], `config.workload`).  Weak scaling: every
+rank (one process per GPU, launched by torchrun for N > 1) fits its own shard of `--profiles` profiles; the
+shards are independent (no data-path collective) — torch.distributed is used only for the
+barrier and the max-over-ranks timing.
+
+  value      device-resident inputs (foct_plan_*), timed with CUDA events on the plan's stream
+  e2e        the one-shot C-ABI call foct_sample() with HOST buffers, H2D/D2H inside the timed region
+  roofline   fp64 FMA roofline of the sampling kernel: counted leapfrogs x F_grad(N, Nn) / kernel time
+             vs the DFMA peak measured in this run (MEASURED_PEAKS.json has no fp64 figure)
+  cpu_baseline / --impl reference
+             the CPU oracle (Stan's algorithm, analytic gradient — NOT rstan, which cannot run here:
+             BASELINE.md §3) on a bounded sample of the same workload, all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from fitoct_b200 import _abi as abi  # noqa: E402
+from fitoct_b200 import synth  # noqa: E402
+
+METRIC = "fitExpGP batch min-ESS/s"
+UNIT = "ESS/s"
+
+
+def f_grad(N: int, Nn: int) -> float:
+    """Algorithmic flops of one gradient evaluation, SURVEY §8(d): N (4 Nn + 23)."""
+    return float(N) * (4.0 * Nn + 23.0)
+
+
+def make_batch(n, first_id, Nn):
+    S = synth.make_profiles(n, first_id=first_id, modulated_only=True)
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=Nn, ids=S["ids"])
+    return S, b
+
+
+def min_ess_sum(summary, Nn):
+    """Sum over profiles of min over the Nn+5 sampled parameters of Bulk_ESS."""
+    cols = list(range(0, Nn + 5))  # theta, yGP, lambda, sigma  (br, lp__ are derived)
+    be = summary[:, cols, 10]
+    return float(np.nansum(np.nanmin(be, axis=1)))
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def start(self):
+        def run():
+            while not self._stop.is_set():
+                try:
+                    o = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                        "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                    self.rows.append([c.strip() for c in o.strip().split(",")])
+                except Exception:
+                    pass
+                self._stop.wait(0.5)
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nme in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement on host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    chains = 4
+    n = max(1, min(args.profiles, (cores // chains) * args.cpu_waves))
+    _, b = make_batch(n, 0, args.nn)
+    spec = abi.default_spec()
+    cfg = abi.default_cfg(n_warmup=args.n_warmup, n_iter=args.n_iter, seed=args.seed, chains=chains)
+    times, ess, threads = [], 0.0, cores
+    for s in range(args.warmup + args.steps):
+        cfg.seed = args.seed + s
+        t0 = time.perf_counter()
+        out = O.sample(abi.FOCT_EXPGP, b, n, spec, cfg, draws=True, summary=True)
+        dt = time.perf_counter() - t0
+        threads = out["threads"]
+        if s >= args.warmup:
+            times.append(dt)
+            ess = min_ess_sum(out["summary"], args.nn)
+    T = float(np.sum(times))
+    n_post = args.n_iter - args.n_warmup
+    val = ess * len(times) / T
+    dps = n * chains * n_post * len(times) / T
+    sample = f"{n} of {args.profiles} profiles x {chains} chains, full {args.n_warmup}/{n_post} iterations per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic (synthData.R-shaped)", "draws_per_s": dps,
+        "config": workload_config(args, n),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "draws_per_s": dps,
+                         "note": "CPU restatement (Stan algorithm, analytic gradient) - not rstan (R absent, BASELINE.md s3)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n):
+    return {"workload": f"batch of {n} synthetic synthData.R profiles x 4 chains, fitExpGP Nn={args.nn}, "
+                        f"warmup {args.n_warmup} + {args.n_iter - args.n_warmup} draws (BASELINE configs[2])",
+            "profiles_per_gpu": n, "chains": 4, "Nn": args.nn, "N": 481, "n_warmup": args.n_warmup,
+            "n_iter": args.n_iter, "adapt_delta": 0.8, "max_treedepth": 10,
+            "l2": "flushed between steps (256 MiB memset)", "parallelism": "independent profile shards, no collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profiles", type=int, default=1000, help="profiles per GPU")
+    ap.add_argument("--nn", type=int, default=10)
+    ap.add_argument("--n-warmup", type=int, default=500)
+    ap.add_argument("--n-iter", type=int, default=1500)
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--cpu-waves", type=int, default=1, help="CPU sample = cores/4 * waves profiles")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from fitoct_b200 import _lib as L
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: fitoct_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo", rank=rank, world_size=world)  # barrier/timing only; shards never talk
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    chains = 4
+    n = args.profiles
+    n_post = args.n_iter - args.n_warmup
+    S, batch = make_batch(n, rank * n, args.nn)
+    spec = abi.default_spec()
+    cfg = abi.default_cfg(n_warmup=args.n_warmup, n_iter=args.n_iter, seed=args.seed, chains=chains)
+    cfg.n_devices = 1
+    import ctypes as C
+    dev_arr = (C.c_int * 1)(local_rank)
+    cfg.devices = C.cast(dev_arr, C.POINTER(C.c_int))
+
+    peak_tf, _ = L.fp64_peak(local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    # ---------------- value: device-resident inputs, CUDA-event timing
+    plan = L.Plan(abi.FOCT_EXPGP, batch, n, spec, cfg, want_draws=False, want_summary=True)
+    for s in range(args.warmup):
+        flush.zero_()
+        plan.run(args.seed + s)
+        plan.sync()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    step_ms, samp_ms, summ_ms, ess_sum, leap = [], [], [], 0.0, 0.0
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        plan.run(args.seed + args.warmup + s)
+        plan.sync()
+        tm = plan.timing()
+        samp_ms.append(tm["sample_ms"]); summ_ms.append(tm["summary_ms"])
+        step_ms.append(tm["sample_ms"] + tm["summary_ms"])
+        out = plan.fetch()
+        ess_sum += min_ess_sum(out["summary"], args.nn)
+        leap += float(out["n_leapfrog"].sum())
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    tm = plan.timing()
+    rhat_max = float(np.nanmax(out["summary"][:, : args.nn + 5, 9]))
+    rhat_q99 = float(np.nanquantile(np.nanmax(out["summary"][:, : args.nn + 5, 9], axis=1), 0.99))
+    n_div = float(out["n_divergent"].sum())
+    plan.close()
+
+    T = float(np.sum(step_ms)) * 1e-3  # device time of the timed steps on this rank
+    stats = np.array([T, ess_sum, leap, float(np.sum(samp_ms)) * 1e-3], dtype=np.float64)
+    if world > 1:
+        tt = torch.from_numpy(stats.copy())
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        T_max, ess_all, leap_all, Ts_max = float(mx[0]), float(sm[1]), float(sm[2]), float(mx[3])
+    else:
+        T_max, ess_all, leap_all, Ts_max = stats[0], stats[1], stats[2], stats[3]
+    value = ess_all / T_max
+    draws_per_s = world * n * chains * n_post * args.steps / T_max
+
+    # ---------------- e2e: host buffers through foct_sample (H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        L.sample(abi.FOCT_EXPGP, batch, min(n, 64), spec, cfg, draws=False, summary=True)  # warm the path
+        barrier()
+        t0 = time.perf_counter()
+        e_ess = 0.0
+        for s in range(args.steps):
+            cfg.seed = args.seed + args.warmup + s
+            o2 = L.sample(abi.FOCT_EXPGP, batch, n, spec, cfg, draws=False, summary=True)
+            e_ess += min_ess_sum(o2["summary"], args.nn)
+        barrier()
+        Te = time.perf_counter() - t0
+        cfg.seed = args.seed
+        es = np.array([Te, e_ess])
+        if world > 1:
+            a = torch.from_numpy(es.copy()); m2 = a.clone(); dist.all_reduce(m2, op=dist.ReduceOp.MAX)
+            s2 = a.clone(); dist.all_reduce(s2, op=dist.ReduceOp.SUM)
+            Te, e_all = float(m2[0]), float(s2[1])
+        else:
+            e_all = e_ess
+        D, P_out = abi.dims(abi.FOCT_EXPGP, args.nn)
+        h2d = n * (3 * 481 * 8 + 200)
+        d2h = n * (P_out * abi.FOCT_N_SUMMARY_COLS * 8 + chains * 8 * (1 + D + 2 + 1))
+        e2e = {"value": e_all / Te, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "draws_per_s": world * n * chains * n_post * args.steps / Te, "ms_per_step": 1e3 * Te / args.steps}
+
+    # ---------------- cpu baseline (rank 0, N = 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        nc = max(1, min(n, (cores // chains) * args.cpu_waves))
+        _, bc = make_batch(nc, 0, args.nn)
+        t0 = time.perf_counter()
+        oc = O.sample(abi.FOCT_EXPGP, bc, nc, spec, cfg, draws=True, summary=True)
+        dt = time.perf_counter() - t0
+        cpu = {"value": min_ess_sum(oc["summary"], args.nn) / dt, "unit": UNIT, "cores": oc["threads"], "kind": "port",
+               "sample": f"{nc} of {n} profiles x {chains} chains, full {args.n_warmup}/{n_post} iterations, {dt:.1f} s",
+               "draws_per_s": nc * chains * n_post / dt, "grad_per_s": float(oc["n_leapfrog"].sum()) / dt,
+               "note": "CPU restatement (Stan algorithm, analytic gradient) - not rstan (R absent, BASELINE.md s3)"}
+
+    if rank == 0:
+        achieved = leap_all / world * f_grad(481, args.nn) / Ts_max / 1e12  # per-GPU TFLOP/s of the sampling kernel
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * T_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (synthData.R-shaped, fitoct_b200/synth.py)",
+            "draws_per_s": draws_per_s, "grad_per_s": leap_all / Ts_max,
+            "config": workload_config(args, n),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf, "traffic": None,
+                         "peak_source": "DFMA-chain microbenchmark measured in this run (foct_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no fp64 figure",
+                         "kernel": "foct::nuts_kernel", "algorithmic_flop_per_grad": f_grad(481, args.nn),
+                         "leapfrogs_per_step": leap_all / world / args.steps,
+                         "hbm_writeback_gbs": (n * chains * n_post * (args.nn + 7) * 8 * args.steps / Ts_max) / 1e9,
+                         "launch": {k: tm[k] for k in ("grid", "block", "blocks_per_sm", "regs", "smem_bytes")}},
+            "kernel_ms": {"sample": float(np.mean(samp_ms)), "summary": float(np.mean(summ_ms))},
+            "quality": {"rhat_max": rhat_max, "rhat_q99_of_profile_max": rhat_q99, "divergent_post_warmup": n_div,
+                        "mean_min_bulk_ess_per_profile": ess_all / (world * n * args.steps)},
+            "clocks": clk, "e2e": e2e, "gpu_launches": 2 * args.steps,
+            "wall_s_timed_region": t_wall,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

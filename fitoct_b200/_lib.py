@@ -20,7 +20,7 @@ EXPORTS = (
     "foct_version", "foct_device_count", "foct_last_error", "foct_model_spec_default", "foct_sampler_cfg_default",
     "foct_dims", "foct_expgp_grid", "foct_expgp_basis", "foct_logp_grad", "foct_sample", "foct_expgp_sample",
     "foct_monoexp_sample", "foct_monoexp_map", "foct_predict", "foct_plan_create", "foct_plan_run",
-    "foct_plan_sync", "foct_plan_fetch", "foct_plan_destroy", "foct_fp64_peak",
+    "foct_plan_sync", "foct_plan_timing", "foct_plan_fetch", "foct_plan_destroy", "foct_fp64_peak",
 )
 
 _LIB = None
@@ -62,6 +62,7 @@ def lib():
         L.foct_plan_run.argtypes = [C.c_void_p, C.c_ulonglong]
         L.foct_plan_sync.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.foct_plan_fetch.argtypes = [C.c_void_p, RS]
+        L.foct_plan_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)] + [ip] * 5
         L.foct_plan_destroy.argtypes = [C.c_void_p]
         L.foct_plan_destroy.restype = None
         L.foct_fp64_peak.argtypes = [C.c_int, dp, dp]
@@ -160,6 +161,13 @@ class Plan:
         ms = C.c_float()
         check(lib().foct_plan_sync(self._h, C.byref(ms)))
         return float(ms.value)
+
+    def timing(self) -> dict:
+        a, b = C.c_float(), C.c_float()
+        g = [C.c_int() for _ in range(5)]
+        check(lib().foct_plan_timing(self._h, C.byref(a), C.byref(b), *[C.byref(v) for v in g]))
+        return dict(sample_ms=float(a.value), summary_ms=float(b.value), grid=g[0].value, block=g[1].value,
+                    blocks_per_sm=g[2].value, regs=g[3].value, smem_bytes=g[4].value)
 
     def fetch(self):
         out, R = alloc_result(self.kind, self.n, self.Nn, self.cfg, self.want_draws, self.want_summary)

@@ -1,0 +1,203 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Same names, argument meaning and error behaviour as the calls the reference makes:
+
+    FitOCTLib::fitExpGP(x, y, uy, dataType, Nn, gridType, method, theta0, Sigma0, lambda_rate, rho_scale,
+                        nb_warmup, nb_iter, prior_PD, open_progress)            FitOCT.R:110-124, priPost.R:2-16
+    FitOCTLib::fitMonoExp(x, y, uy, dataType)                                   FitOCT.R:95
+
+and the same return shapes (`list(fit, method, xGP, prior_PD)`, plotExpGP.R:29-32;
+`list(best.theta, cor.theta, fit$par$..., fit$hessian, method)`, FitOCT.R:96-97, plotMonoExp.R:14-16).
+The R side of the drop-in (r-pkg/) is a logic-free shim over the same C ABI; R is absent from this image,
+so this Python mirror is what the tests and benchmarks drive.  Everything numerical happens in the CUDA
+library (fitoct_b200._lib); nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _abi as abi
+from . import _lib as L
+
+# FitOCT.R:37-53 defaults, overridden by ctrlParams.yaml (FitOCT.R:55-63)
+CTRL_DEFAULTS = dict(
+    depthSel=None, dataType=2, subSample=1, smooth_df=15, method="sample", nb_warmup=500, nb_sample=1000,
+    modRange=0.5, ru_theta=0.05, lambda_rate=0.1, gridType="internal", Nn=10, rho_scale=0.1, priPost=True,
+    priorType="abc",
+)
+
+
+def load_ctrl_params(path: str | None = "ctrlParams.yaml") -> dict:
+    """Defaults <- YAML overrides, like FitOCT.R:37-63.  Unknown keys are kept (the R script assigns them too)."""
+    import os
+
+    pars = dict(CTRL_DEFAULTS)
+    if path and os.path.exists(path):
+        import yaml
+
+        with open(path) as fh:
+            loaded = yaml.safe_load(fh) or {}
+        pars.update(loaded)
+    return pars
+
+
+def resolve_rho(rho_scale: float, Nn: int) -> float:
+    """`ifelse(rho_scale==0, 1./Nn, rho_scale)` — FitOCT.R:119, priPost.R:11, server.R:420-422."""
+    return 1.0 / Nn if rho_scale == 0 else float(rho_scale)
+
+
+@dataclass
+class StanFit:
+    """stanfit-like result (SURVEY a-11): what plotExpGP.R:9-11,41-47 and server.R:88-104 read."""
+
+    par_names: list
+    draws: np.ndarray           # [n_saved, chains, P_out], warm-up first when saved
+    sampler_params: np.ndarray  # [n_saved, chains, 6]
+    n_warmup: int
+    n_iter: int
+    save_warmup: bool
+    summary_table: np.ndarray   # [P_out, 11] over post-warm-up draws (computed on the device)
+    stepsize: np.ndarray
+    inv_metric: np.ndarray
+    n_divergent: np.ndarray
+
+    def _post(self):
+        return self.draws[self.n_warmup:] if self.save_warmup else self.draws
+
+    def _cols(self, pars):
+        if pars is None:
+            return list(range(len(self.par_names)))
+        if isinstance(pars, str):
+            pars = [pars]
+        idx = []
+        for p in pars:
+            hit = [i for i, nme in enumerate(self.par_names) if nme == p or nme.startswith(p + "[")]
+            if not hit:
+                raise KeyError(f"no parameter {p!r}; have {self.par_names}")
+            idx += hit
+        return idx
+
+    def extract(self, pars=None, inc_warmup=False) -> dict:
+        """rstan::extract: post-warm-up draws, chains merged (plotExpGP.R:11)."""
+        d = self.draws if (inc_warmup and self.save_warmup) else self._post()
+        flat = d.reshape(-1, d.shape[-1])
+        groups: dict = {}
+        for i in self._cols(pars):
+            groups.setdefault(self.par_names[i].split("[")[0], []).append(i)
+        return {k: (flat[:, v[0]] if len(v) == 1 and "[" not in self.par_names[v[0]] else flat[:, v]) for k, v in groups.items()}
+
+    def as_matrix(self, pars=None) -> np.ndarray:
+        """as.matrix(fit, pars=...) — plotExpGP.R:44."""
+        d = self._post()
+        return d.reshape(-1, d.shape[-1])[:, self._cols(pars)]
+
+    def summary(self, pars=None) -> dict:
+        """rstan::summary(fit)$summary with the rstan column names (server.R:88-104)."""
+        idx = self._cols(pars)
+        return {"rownames": [self.par_names[i] for i in idx], "colnames": list(abi.SUMMARY_COL_NAMES),
+                "summary": self.summary_table[idx]}
+
+    def __str__(self):
+        s = self.summary()
+        head = f"{'':12s}" + "".join(f"{c:>10s}" for c in s["colnames"])
+        rows = [f"{n:12s}" + "".join(f"{v:10.4g}" for v in r) for n, r in zip(s["rownames"], s["summary"])]
+        return "\n".join([f"Inference for fitoct_b200 model: {self.draws.shape[1]} chains, iter={self.n_iter}, "
+                          f"warmup={self.n_warmup}", head] + rows)
+
+
+def _grid_code(gridType):
+    if isinstance(gridType, str):
+        if gridType not in ("internal", "extremal"):
+            raise ValueError("gridType must be 'internal' or 'extremal' (ShinyInterface/ui.R:211-218)")
+        return 0 if gridType == "internal" else 1
+    return int(gridType)
+
+
+def _one_problem(x, y, uy, dataType, Nn, gridType, theta0, Sigma0, lambda_rate, rho, prior_PD, pid=0):
+    return dict(x=x, y=y, uy=uy, dataType=dataType, Nn=Nn, gridType=_grid_code(gridType), rho=rho,
+                lambda_rate=lambda_rate, theta0=theta0, Sigma0=Sigma0, prior_PD=prior_PD, id=pid)
+
+
+def _stanfit_from(out, j, kind, Nn, cfg):
+    return StanFit(par_names=abi.param_names(kind, Nn), draws=out["draws"][j], sampler_params=out["sampler_params"][j],
+                   n_warmup=cfg.n_warmup, n_iter=cfg.n_iter, save_warmup=bool(cfg.save_warmup),
+                   summary_table=out["summary"][j], stepsize=out["stepsize"][j], inv_metric=out["inv_metric"][j],
+                   n_divergent=out["n_divergent"][j])
+
+
+def fitExpGP(x, y, uy, dataType=2, Nn=10, gridType="internal", method="sample", theta0=None, Sigma0=None,
+             lambda_rate=0.1, rho_scale=0.1, nb_warmup=500, nb_iter=1500, prior_PD=0, open_progress=False, *,
+             chains=4, seed=1234, spec=None, control=None, init=None):
+    """Drop-in for FitOCTLib::fitExpGP (FitOCT.R:110-124).  Returns dict(fit, method, xGP, prior_PD).
+
+    `rho_scale` is taken as already resolved by the caller when non-zero; 0 is resolved to 1/Nn here too, so
+    both calling styles of the reference work.  `control` accepts rstan's adapt_delta / max_treedepth.
+    """
+    if theta0 is None or Sigma0 is None:
+        raise ValueError("theta0 and Sigma0 are required (estimateExpPrior output, FitOCT.R:103-107)")
+    if method not in ("sample", "optim", "vb"):
+        raise ValueError("method must be one of 'sample', 'optim', 'vb' (FitOCT.R:42)")
+    if method != "sample":
+        raise NotImplementedError(f"method={method!r}: SURVEY §8(f) rows N1/N4 ('next'); only 'sample' is on the hot path")
+    spec = spec or abi.default_spec(abi.FOCT_EXPGP)
+    control = control or {}
+    cfg = abi.default_cfg(chains=chains, n_warmup=int(nb_warmup), n_iter=int(nb_iter), seed=int(seed), save_warmup=1,
+                          adapt_delta=float(control.get("adapt_delta", 0.8)),
+                          max_treedepth=int(control.get("max_treedepth", 10)))
+    keep = None
+    if init is not None:
+        keep = np.ascontiguousarray(init, dtype=np.float64).reshape(chains, Nn + 5)
+        cfg.init_mode = 2
+        cfg.init = abi.as_ptr(keep)
+    batch = abi.make_problems([_one_problem(x, y, uy, dataType, Nn, gridType, theta0, Sigma0, lambda_rate,
+                                            resolve_rho(rho_scale, Nn), prior_PD)])
+    out = L.sample(abi.FOCT_EXPGP, batch, 1, spec, cfg, draws=True, summary=True)
+    fit = _stanfit_from(out, 0, abi.FOCT_EXPGP, Nn, cfg)
+    return dict(fit=fit, method=method, xGP=L.grid(Nn, _grid_code(gridType)), prior_PD=prior_PD)
+
+
+def fitExpGP_batch(x, Y, UY, theta0, Sigma0, *, dataType=2, Nn=10, gridType="internal", lambda_rate=0.1, rho_scale=0.1,
+                   nb_warmup=500, nb_iter=1500, prior_PD=0, chains=4, seed=1234, spec=None, control=None,
+                   devices=None, ids=None, keep_draws=False):
+    """Batch form of fitExpGP: one call for a whole directory of profiles, sharded over
+    `devices` as independent shards.  Returns the device-computed summaries (and the draws on request)."""
+    spec = spec or abi.default_spec(abi.FOCT_EXPGP)
+    control = control or {}
+    cfg = abi.default_cfg(chains=chains, n_warmup=int(nb_warmup), n_iter=int(nb_iter), seed=int(seed),
+                          adapt_delta=float(control.get("adapt_delta", 0.8)),
+                          max_treedepth=int(control.get("max_treedepth", 10)))
+    batch = abi.make_problems_dense(x, Y, UY, theta0, Sigma0, dataType=dataType, Nn=Nn, gridType=_grid_code(gridType),
+                                    rho=resolve_rho(rho_scale, Nn), lambda_rate=lambda_rate, prior_PD=prior_PD, ids=ids)
+    n = np.asarray(Y).shape[0]
+    out = L.sample(abi.FOCT_EXPGP, batch, n, spec, cfg, draws=keep_draws, summary=True, devices=devices)
+    out["par_names"] = abi.param_names(abi.FOCT_EXPGP, Nn)
+    out["xGP"] = L.grid(Nn, _grid_code(gridType))
+    return out
+
+
+def fitMonoExp(x, y, uy, dataType=2, method="optim", *, nb_warmup=500, nb_iter=1500, chains=4, seed=1234, spec=None):
+    """Drop-in for FitOCTLib::fitMonoExp (FitOCT.R:95).  method='optim' is what the reference uses (MAP +
+    Hessian); method='sample' is BASELINE.json configs[0] (4-chain NUTS, D = 3)."""
+    spec = spec or abi.default_spec(abi.FOCT_MONOEXP)
+    batch = abi.make_problems([_one_problem(x, y, uy, dataType, 0, 0, (0, 0, 1), np.eye(3), 0.0, 1.0, 0)])
+    theta, H, br, st = L.monoexp_map(batch, 1, spec)
+    best = theta[0]
+    cov = np.linalg.inv(-H[0])
+    sd = np.sqrt(np.diag(cov))
+    cor = cov / np.outer(sd, sd)
+    if method == "optim":
+        row = np.array([[best[0], best[1], best[2], br[0], 0.0]])
+        m, resid, _ = L.predict(abi.FOCT_MONOEXP, batch, 0, spec, row)
+        fit = dict(par=dict(theta=best, m=m[0], resid=resid[0], br=br[0]), hessian=H[0], return_code=int(st[0]))
+        return dict(best_theta=best, cor_theta=cor, fit=fit, method="optim")
+    if method != "sample":
+        raise ValueError("method must be 'optim' or 'sample'")
+    cfg = abi.default_cfg(chains=chains, n_warmup=int(nb_warmup), n_iter=int(nb_iter), seed=int(seed), save_warmup=1)
+    init = np.ascontiguousarray(np.tile(best, (chains, 1)))
+    cfg.init_mode = 2
+    cfg.init = abi.as_ptr(init)
+    out = L.sample(abi.FOCT_MONOEXP, batch, 1, spec, cfg, draws=True, summary=True)
+    fit = _stanfit_from(out, 0, abi.FOCT_MONOEXP, 0, cfg)
+    return dict(best_theta=fit.summary_table[:3, 0], cor_theta=cor, fit=fit, method="sample")

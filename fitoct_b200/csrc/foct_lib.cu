@@ -340,7 +340,7 @@ struct foct_plan {
   int n_saved = 0, n_post = 0;
   bool want_draws = false, want_summary = false;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   double *d_blobs = nullptr, *d_draws = nullptr, *d_sparams = nullptr, *d_summary = nullptr, *d_stepsize = nullptr,
          *d_invm = nullptr, *d_nleap = nullptr, *d_ndiv = nullptr, *d_init = nullptr;
   DevProblem* d_probs = nullptr;
@@ -359,6 +359,7 @@ static void plan_free(foct_plan* p) {
   cudaFree(p->d_probs); cudaFree(p->d_counter);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
+  if (p->ev2) cudaEventDestroy(p->ev2);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -607,6 +608,7 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
   CUP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   CUP(cudaEventCreate(&p->ev0));
   CUP(cudaEventCreate(&p->ev1));
+  CUP(cudaEventCreate(&p->ev2));
   if (int rc = build_device_batch(kind, P, n, spec, device, p->stream, &p->NN, &p->npad, &p->blob_stride, &p->d_blobs, &p->d_probs)) {
     plan_free(p);
     return rc;
@@ -676,6 +678,7 @@ extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
     const int off = c.save_warmup ? c.n_warmup : 0;
     CU(launch_summary(p->d_draws, p->n, p->n_saved, off, p->n_post, c.chains, p->P_out, p->d_summary, p->stream));
   }
+  CU(cudaEventRecord(p->ev2, p->stream));
   p->ran = true;
   return 0;
 }
@@ -688,6 +691,23 @@ extern "C" int foct_plan_sync(foct_plan* p, float* kernel_ms) {
     *kernel_ms = 0.f;
     if (p->ran) CU(cudaEventElapsedTime(kernel_ms, p->ev0, p->ev1));
   }
+  return 0;
+}
+
+extern "C" int foct_plan_timing(foct_plan* p, float* sample_ms, float* summary_ms, int* grid, int* block,
+                                int* blocks_per_sm, int* regs, int* smem_bytes) {
+  if (!p) return fail(FOCT_EINVAL, "NULL plan");
+  CU(cudaSetDevice(p->device));
+  if (p->ran) {
+    CU(cudaEventSynchronize(p->ev2));
+    if (sample_ms) CU(cudaEventElapsedTime(sample_ms, p->ev0, p->ev1));
+    if (summary_ms) CU(cudaEventElapsedTime(summary_ms, p->ev1, p->ev2));
+  }
+  if (grid) *grid = p->grid;
+  if (block) *block = p->block;
+  if (blocks_per_sm) *blocks_per_sm = p->blocks_per_sm;
+  if (regs) *regs = p->regs;
+  if (smem_bytes) *smem_bytes = (int)p->smem;
   return 0;
 }
 

@@ -160,6 +160,10 @@ int foct_plan_create(int kind, const foct_problem* P, int n_problems, const foct
 int foct_plan_run(foct_plan* plan, unsigned long long seed); /* async on the plan's stream */
 int foct_plan_sync(foct_plan* plan, float* kernel_ms /* CUDA-event time of the sampling kernel, may be NULL */);
 int foct_plan_fetch(foct_plan* plan, foct_result* R);
+/* CUDA-event durations of the last run (sampling kernel; summary kernel) and the launch geometry of the
+ * sampling kernel — what bench.py's roofline is computed from.  Any pointer may be NULL. */
+int foct_plan_timing(foct_plan* plan, float* sample_ms, float* summary_ms, int* grid, int* block,
+                     int* blocks_per_sm, int* regs, int* smem_bytes);
 void foct_plan_destroy(foct_plan* plan);
 
 /* Measured fp64 FMA throughput of the device (DFMA-chain microbenchmark), the roofline denominator for

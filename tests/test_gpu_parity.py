@@ -1,0 +1,281 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle and the golden vectors.
+
+Tolerances: log density / gradient / chi2 1e-12 relative in fp64 (BASELINE.json north_star), where the
+gradient tolerance is relative to |g| + sum|summands| (a component that cancels to ~0 has no meaningful
+relative error); integer sampler outputs (treedepth, n_leapfrog, divergent) bit-exact while the two
+implementations still follow the same trajectory; posterior summaries within 3-4 MCSE."""
+import numpy as np
+import pytest
+
+from conftest import case_to_batch, grad_tol_ok
+from fitoct_b200 import _abi as abi
+from fitoct_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def rand_q(rng, theta0, Nn, n_q, wide=False):
+    D = Nn + 5
+    q = np.zeros((n_q, D))
+    s = 0.1 if wide else 0.02
+    q[:, :3] = theta0 * (1 + s * rng.standard_normal((n_q, 3)))
+    q[:, 3:3 + Nn] = (0.2 if wide else 0.05) * rng.standard_normal((n_q, Nn))
+    q[:, 3 + Nn] = np.log(0.1) + (1.0 if wide else 0.3) * rng.standard_normal(n_q)
+    q[:, 4 + Nn] = (0.7 if wide else 0.2) * rng.standard_normal(n_q)
+    return q
+
+
+@pytest.mark.parametrize("idx", range(7))
+def test_logp_grad_vs_golden(L, O, golden, idx):
+    case = golden[idx]
+    batch, spec = case_to_batch(case)
+    q = np.array(case["q"])[None]
+    lp, g, chi2 = L.logp_grad(case["kind"], batch, 1, spec, q)
+    # golden values were computed with the double-rounded exact basis; the device builds its own basis, so the
+    # golden comparison allows for cond(Kgg)*eps in B, and the 1e-12 check is done against the oracle fed the
+    # device basis (test_logp_grad_vs_oracle_random).
+    loose = 1e-12 if case["kind"] == 1 or case["prior_PD"] else 2e-8
+    for k, e in enumerate(case["expected"]):
+        assert abs(lp[0, k] - float(e["lp"])) <= loose * abs(float(e["lp"]))
+    if case["kind"] == 0:
+        B = L.basis(batch, 0, spec)
+        assert np.abs(B - np.array(case["basis"])).max() <= 2e-7 * np.abs(np.array(case["basis"])).max()
+        lpo, go, c2o, at = O.logp_grad(0, batch, 0, spec, q[0], B=B, want_abs=True)
+    else:
+        lpo, go, c2o, at = O.logp_grad(1, batch, 0, spec, q[0], want_abs=True)
+    assert np.all(np.abs(lp[0] - lpo) <= RTOL * np.abs(lpo))
+    assert grad_tol_ok(g[0], go, at, RTOL)
+    if not case["prior_PD"]:
+        assert np.all(np.abs(chi2[0] - c2o) <= RTOL * c2o)
+    else:
+        assert np.all(np.isnan(chi2[0]))
+
+
+@pytest.mark.parametrize("Nn", [1, 5, 10, 11, 12, 15, 20, 25])
+@pytest.mark.parametrize("mod", [0, 1])
+def test_logp_grad_vs_oracle_random(L, O, Nn, mod):
+    rng = np.random.default_rng(100 * Nn + mod)
+    n = 3
+    S = synth.make_profiles(n, first_id=Nn)
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=Nn, gridType=Nn % 2,
+                                rho=max(1.0 / Nn, 0.06), ids=S["ids"])
+    spec = abi.default_spec()
+    spec.modulation = mod
+    q = np.stack([rand_q(rng, S["theta0"][j], Nn, 5, wide=True) for j in range(n)])
+    lp, g, chi2 = L.logp_grad(0, b, n, spec, q)
+    for j in range(n):
+        B = L.basis(b, j, spec)
+        Bo = O.basis(b, j, spec)
+        assert np.abs(B - Bo).max() <= 1e-6 * np.abs(Bo).max()
+        lpo, go, c2o, at = O.logp_grad(0, b, j, spec, q[j], B=B, want_abs=True)
+        ok = np.isfinite(lpo)
+        assert np.array_equal(np.isfinite(lp[j]), ok)
+        assert np.all(np.abs(lp[j][ok] - lpo[ok]) <= RTOL * np.abs(lpo[ok]))
+        assert grad_tol_ok(g[j][ok], go[ok], at[ok], RTOL)
+        assert np.all(np.abs(chi2[j][ok] - c2o[ok]) <= RTOL * c2o[ok])
+
+
+def test_logp_adversarial_points(L, O):
+    # SURVEY §8c ladder (1): tiny/huge sigma, dL -> -1 (theta3*s crosses zero => non-finite), x tail
+    S = synth.make_profiles(1, first_id=1)
+    Nn = 10
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=Nn)
+    spec = abi.default_spec()
+    base = rand_q(np.random.default_rng(0), S["theta0"][0], Nn, 1)[0]
+    qs = []
+    for sig in (-8.0, 6.0):
+        q = base.copy(); q[4 + Nn] = sig; qs.append(q)
+    q = base.copy(); q[3 + Nn] = -12.0; qs.append(q)           # lambda ~ 6e-6
+    q = base.copy(); q[3:3 + Nn] = -1.05; qs.append(q)          # s < 0 over most of the profile
+    q = base.copy(); q[3:3 + Nn] = -0.98; qs.append(q)          # s ~ 0.02: huge decay rate, exp underflow
+    q = base.copy(); q[2] = 1e-3; qs.append(q)                  # theta3 tiny
+    q = base.copy(); q[2] = -300.0; qs.append(q)                # negative decay length => overflow
+    q = np.array(qs)[None]
+    lp, g, chi2 = L.logp_grad(0, b, 1, spec, q)
+    B = L.basis(b, 0, spec)
+    lpo, go, c2o, at = O.logp_grad(0, b, 0, spec, q[0], B=B, want_abs=True)
+    fin = np.isfinite(lpo)
+    assert np.array_equal(np.isfinite(lp[0]), fin)               # non-finite states agree (=> divergent, H7)
+    assert fin.sum() >= 4 and (~fin).sum() >= 1
+    assert np.all(np.abs(lp[0][fin] - lpo[fin]) <= RTOL * np.abs(lpo[fin]))
+    assert grad_tol_ok(g[0][fin], go[fin], at[fin], RTOL)
+
+
+def test_ragged_batch_and_empty_errors(L, O):
+    rng = np.random.default_rng(5)
+    S = synth.make_profiles(4)
+    Ns = [481, 33, 200, 64]
+    profs = []
+    for j, N in enumerate(Ns):
+        sel = np.sort(rng.choice(481, N, replace=False))
+        profs.append(dict(x=S["x"][sel], y=S["Y"][j][sel], uy=S["UY"][j][sel], Nn=6, gridType=j % 2, rho=0.2,
+                          theta0=S["theta0"][j], Sigma0=S["Sigma0"][j], id=j, dataType=1 + j % 2))
+    b = abi.make_problems(profs)
+    spec = abi.default_spec()
+    q = np.stack([rand_q(rng, S["theta0"][j], 6, 2) for j in range(4)])
+    lp, g, chi2 = L.logp_grad(0, b, 4, spec, q)
+    for j in range(4):
+        lpo, go, c2o, at = O.logp_grad(0, b, j, spec, q[j], B=L.basis(b, j, spec), want_abs=True)
+        assert np.all(np.abs(lp[j] - lpo) <= RTOL * np.abs(lpo))
+        assert grad_tol_ok(g[j], go, at, RTOL)
+    # error behaviour: empty batch, mixed Nn, bad dataType, non-positive uy, too few points
+    with pytest.raises(L.FitOCTError):
+        L.logp_grad(0, b, 0, spec, np.zeros((0, 1, 11)))
+    profs[1]["Nn"] = 7
+    with pytest.raises(L.FitOCTError, match="Nn"):
+        L.logp_grad(0, abi.make_problems(profs), 4, spec, q)
+    profs[1]["Nn"] = 6; profs[2]["dataType"] = 3
+    with pytest.raises(L.FitOCTError, match="dataType"):
+        L.logp_grad(0, abi.make_problems(profs), 4, spec, q)
+    profs[2]["dataType"] = 2; profs[0]["uy"] = profs[0]["uy"].copy(); profs[0]["uy"][3] = 0.0
+    with pytest.raises(L.FitOCTError, match="uy"):
+        L.logp_grad(0, abi.make_problems(profs), 4, spec, q)
+    tiny = [dict(x=[1.0, 2.0, 3.0], y=[1.0, 2.0, 3.0], uy=[1.0, 1.0, 1.0], Nn=6, theta0=(1, 1, 1), Sigma0=np.eye(3))]
+    with pytest.raises(L.FitOCTError):
+        L.logp_grad(0, abi.make_problems(tiny), 1, spec, np.zeros((1, 1, 11)))
+
+
+@pytest.mark.parametrize("Nn,chains", [(10, 4), (5, 1), (15, 8), (20, 3)])
+def test_sampler_builds_the_same_trees_as_the_oracle(L, O, Nn, chains):
+    # same Philox draw sites => identical tree depth / leapfrog count / divergence flags and (to rounding) the
+    # same draws, until floating-point chaos separates the trajectories.  Checked over the first transitions,
+    # which include the init_stepsize heuristic and the first dual-averaging updates.
+    S = synth.make_profiles(2, modulated_only=True, first_id=3)
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=Nn, ids=S["ids"])
+    spec = abi.default_spec()
+    cfg = abi.default_cfg(n_warmup=25, n_iter=40, seed=2024 + Nn, save_warmup=1, chains=chains)
+    out = L.sample(0, b, 2, spec, cfg)
+    ref = O.sample(0, b, 2, spec, cfg)
+    K = 6
+    np.testing.assert_array_equal(out["sampler_params"][:, :K, :, 2:5], ref["sampler_params"][:, :K, :, 2:5])
+    np.testing.assert_allclose(out["sampler_params"][:, :K, :, [0, 1, 5]], ref["sampler_params"][:, :K, :, [0, 1, 5]], rtol=1e-7)
+    np.testing.assert_allclose(out["draws"][:, :K], ref["draws"][:, :K], rtol=1e-7, atol=1e-9)
+    assert np.isfinite(out["draws"]).all()
+    assert out["draws"].shape == (2, 40, chains, Nn + 7)
+    assert np.all(out["n_leapfrog"].sum(axis=2) == out["sampler_params"][..., 3].sum(axis=1))
+
+
+def test_monoexp_sampler_and_prior_pd(L, O):
+    S = synth.make_profiles(5)
+    b = abi.make_problems_dense(S["x"], S["Y"][:1], S["UY"][:1], S["theta0"][:1], S["Sigma0"][:1], Nn=0)
+    spec = abi.default_spec(abi.FOCT_MONOEXP)
+    th, _, _, _ = L.monoexp_map(b, 1, spec)
+    init = np.ascontiguousarray(np.tile(th[0], (4, 1)))
+    cfg = abi.default_cfg(n_warmup=25, n_iter=40, seed=5, save_warmup=1)
+    cfg.init_mode = 2; cfg.init = abi.as_ptr(init)
+    out = L.sample(abi.FOCT_MONOEXP, b, 1, spec, cfg)
+    ref = O.sample(abi.FOCT_MONOEXP, b, 1, spec, cfg)
+    np.testing.assert_array_equal(out["sampler_params"][:, :6, :, 2:5], ref["sampler_params"][:, :6, :, 2:5])
+    np.testing.assert_allclose(out["draws"][:, :6], ref["draws"][:, :6], rtol=1e-7)
+    # prior predictive run (priPost.R:2-16): likelihood off, br column NaN (plotExpGP.R:42-43)
+    b2 = abi.make_problems_dense(S["x"], S["Y"][1:2], S["UY"][1:2], S["theta0"][1:2], S["Sigma0"][1:2], Nn=10, prior_PD=1)
+    cfg = abi.default_cfg(n_warmup=25, n_iter=40, seed=6, save_warmup=1)
+    out = L.sample(0, b2, 1, abi.default_spec(), cfg)
+    ref = O.sample(0, b2, 1, abi.default_spec(), cfg)
+    assert np.all(np.isnan(out["draws"][..., 15])) and np.all(np.isnan(out["summary"][0, 15]))
+    np.testing.assert_array_equal(out["sampler_params"][:, :6, :, 2:5], ref["sampler_params"][:, :6, :, 2:5])
+    np.testing.assert_allclose(out["draws"][:, :6, :, :15], ref["draws"][:, :6, :, :15], rtol=1e-7, atol=1e-9)
+
+
+def test_summary_kernel_vs_oracle(L, O):
+    S = synth.make_profiles(3, modulated_only=True)
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=10)
+    for n_warmup, n_iter, chains in ((60, 260, 4), (60, 211, 3), (20, 50, 1)):   # even, odd (dropped middle draw), 1 chain
+        cfg = abi.default_cfg(n_warmup=n_warmup, n_iter=n_iter, seed=3, chains=chains)
+        out = L.sample(0, b, 3, abi.default_spec(), cfg)
+        for j in range(3):
+            so = O.summary(out["draws"][j])
+            np.testing.assert_allclose(out["summary"][j], so, rtol=1e-9, atol=1e-12)
+    # warm-up saved: the summary still covers post-warm-up draws only
+    cfg = abi.default_cfg(n_warmup=60, n_iter=160, seed=3, save_warmup=1)
+    out = L.sample(0, b, 1, abi.default_spec(), cfg)
+    np.testing.assert_allclose(out["summary"][0], O.summary(out["draws"][0, 60:]), rtol=1e-9, atol=1e-12)
+
+
+def test_map_and_predict_vs_oracle(L, O):
+    S = synth.make_profiles(10)
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=0)
+    for prior in (1, 0):
+        spec = abi.default_spec(abi.FOCT_MONOEXP)
+        spec.theta_prior = prior
+        th, H, br, st = L.monoexp_map(b, 10, spec)
+        tho, Ho, bro, sto = O.monoexp_map(b, 10, spec)
+        assert np.all(st == 0) and np.all(sto == 0)
+        np.testing.assert_allclose(th, tho, rtol=1e-9)
+        np.testing.assert_allclose(H, Ho, rtol=1e-7)
+        np.testing.assert_allclose(br, bro, rtol=1e-9)
+    b10 = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=10)
+    rows = np.zeros((4, 17))
+    rng = np.random.default_rng(0)
+    rows[:, :3] = S["theta0"][2]; rows[:, 3:13] = 0.05 * rng.standard_normal((4, 10)); rows[:, 13:15] = 1.0
+    for mod in (0, 1):
+        spec = abi.default_spec(); spec.modulation = mod
+        m, r, dl = L.predict(0, b10, 2, spec, rows)
+        mo, ro, dlo = O.predict(0, b10, 2, spec, rows)
+        np.testing.assert_allclose(dl, dlo, rtol=0, atol=1e-9)     # basis built independently on each side
+        np.testing.assert_allclose(m, mo, rtol=1e-8)
+
+
+def test_shard_invariance_and_determinism(L):
+    # a profile's chains depend only on (seed, profile id, chain): not on batch composition, order or device shard
+    S = synth.make_profiles(6, modulated_only=True)
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=10, ids=S["ids"])
+    cfg = abi.default_cfg(n_warmup=40, n_iter=80, seed=99)
+    full = L.sample(0, b, 6, abi.default_spec(), cfg)
+    again = L.sample(0, b, 6, abi.default_spec(), cfg)
+    np.testing.assert_array_equal(full["draws"], again["draws"])
+    sub = abi.make_problems_dense(S["x"], S["Y"][[4, 1]], S["UY"][[4, 1]], S["theta0"][[4, 1]], S["Sigma0"][[4, 1]],
+                                  Nn=10, ids=S["ids"][[4, 1]])
+    part = L.sample(0, sub, 2, abi.default_spec(), cfg)
+    np.testing.assert_array_equal(part["draws"][0], full["draws"][4])
+    np.testing.assert_array_equal(part["draws"][1], full["draws"][1])
+    np.testing.assert_array_equal(part["summary"][1], full["summary"][1])
+    if L.device_count() >= 2:
+        two = L.sample(0, b, 6, abi.default_spec(), cfg, devices=[0, 1])
+        np.testing.assert_array_equal(two["draws"], full["draws"])
+
+
+def test_posterior_matches_cpu_within_mcse(L, O):
+    # BASELINE.json: posterior means / quantiles of A0, l, sigma and the control points within 3 MCSE.
+    # Independent seeds on the two sides; 4 chains x 1000 draws each; z = diff / sqrt(mcse_gpu^2 + mcse_cpu^2).
+    S = synth.make_profiles(2, modulated_only=True, first_id=1)
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=10, ids=S["ids"])
+    spec = abi.default_spec()
+    g = L.sample(0, b, 2, spec, abi.default_cfg(n_warmup=500, n_iter=1500, seed=1))
+    c = O.sample(0, b, 2, spec, abi.default_cfg(n_warmup=500, n_iter=1500, seed=2))
+    zs = []
+    for j in range(2):
+        sg, sc = g["summary"][j], c["summary"][j]
+        assert np.all(sg[:15, 9] < 1.03) and np.all(sc[:15, 9] < 1.03)
+        z = (sg[:15, 0] - sc[:15, 0]) / np.sqrt(sg[:15, 1] ** 2 + sc[:15, 1] ** 2)
+        zs.append(z)
+        # medians: MCSE of a quantile ~ 1.25 * mcse of the mean for near-normal marginals
+        zq = (sg[:15, 5] - sc[:15, 5]) / (1.25 * np.sqrt(sg[:15, 1] ** 2 + sc[:15, 1] ** 2))
+        assert np.all(np.abs(zq) < 4.0), zq
+    zs = np.concatenate(zs)
+    assert np.all(np.abs(zs) < 4.0), zs          # 30 comparisons: a 3-sigma bound would fail ~8 % of the time by chance
+    assert np.mean(np.abs(zs) < 3.0) >= 0.9
+
+
+def test_api_mirror_fitExpGP_and_fitMonoExp(L):
+    from fitoct_b200 import api
+
+    S = synth.make_profiles(2)
+    x = S["x"]
+    mono = api.fitMonoExp(x, S["Y"][0], S["UY"][0], dataType=2)
+    assert mono["method"] == "optim" and mono["fit"]["par"]["m"].shape == (481,)          # plotMonoExp.R:14-16
+    assert np.allclose(mono["fit"]["par"]["resid"], S["Y"][0] - mono["fit"]["par"]["m"])
+    assert np.all(np.abs(np.diag(mono["cor_theta"]) - 1) < 1e-12)
+    assert abs(mono["best_theta"][2] - 300) < 15
+    Sig = np.diag((0.05 * mono["best_theta"]) ** 2)
+    fit = api.fitExpGP(x, S["Y"][1], S["UY"][1], dataType=2, Nn=10, gridType="internal", method="sample",
+                       theta0=mono["best_theta"], Sigma0=Sig, lambda_rate=0.1, rho_scale=0, nb_warmup=100, nb_iter=200,
+                       prior_PD=0)
+    assert set(fit) == {"fit", "method", "xGP", "prior_PD"} and fit["xGP"].shape == (10,)   # plotExpGP.R:29-32
+    sf = fit["fit"]
+    assert sf.draws.shape == (200, 4, 17)                                                   # traceplot(inc_warmup=TRUE)
+    assert np.mean(sf.extract("br")["br"]) == pytest.approx(sf.summary("br")["summary"][0, 0])   # plotExpGP.R:11
+    assert sf.as_matrix(["theta", "yGP", "lambda", "sigma", "br", "lp__"]).shape == (400, 17)
+    mono_s = api.fitMonoExp(x, S["Y"][0], S["UY"][0], method="sample", nb_warmup=100, nb_iter=200)
+    assert mono_s["fit"].draws.shape == (200, 4, 5)

@@ -1,0 +1,171 @@
+"""CPU: the oracle's NUTS / adaptation / summary / MAP against analytic answers.
+
+The only known-answer sampler target the reference itself holds is Tests/testGamma.R:19-47
+(lambda ~ exponential(1/10) on a lower=0 parameter, mean 10, sd 10, median 10 ln 2)."""
+import numpy as np
+import pytest
+
+from fitoct_b200 import _abi as abi
+from fitoct_b200 import synth
+
+
+def mcse_ok(x_chains, truth, n_eff, z=4.0):
+    sd = x_chains.std(ddof=1)
+    return abs(x_chains.mean() - truth) <= z * sd / np.sqrt(n_eff)
+
+
+def test_independent_normal_moments(O):
+    sd = np.array([1.0, 10.0, 0.1, 3.0, 0.5])
+    cfg = abi.default_cfg(n_warmup=300, n_iter=1800, seed=3)
+    dr, sp = O.sample_analytic(0, sd, cfg)
+    S = O.summary(dr)
+    for d in range(5):
+        assert abs(S[d, 0]) <= 4 * sd[d] / np.sqrt(S[d, 8])          # mean within 4 MCSE
+        assert abs(S[d, 2] / sd[d] - 1) < 0.06                       # sd
+        assert 0.99 < S[d, 9] < 1.01                                  # split-Rhat
+        assert S[d, 8] > 1500 and S[d, 10] > 1500
+    assert 0.7 < sp[..., 0].mean() < 0.95                             # adapted towards delta = 0.8
+    assert sp[..., 4].sum() == 0                                      # no divergences
+    # the metric adapts to the scales: a well-adapted chain needs short trees
+    assert sp[..., 2].mean() < 3.5
+
+
+def test_testGamma_exponential_known_answer(O):
+    # Tests/testGamma.R:27,35,42-47  (control adapt_delta 0.99, max_treedepth 12)
+    cfg = abi.default_cfg(n_warmup=500, n_iter=5500, seed=1234, adapt_delta=0.99, max_treedepth=12)
+    dr, sp = O.sample_analytic(1, np.array([0.1]), cfg)
+    lam = np.exp(dr[..., 0])
+    n_eff = O.summary(lam[..., None])[0, 8]
+    assert n_eff > 2000
+    assert abs(lam.mean() - 10.0) <= 4 * lam.std() / np.sqrt(n_eff)
+    assert abs(lam.std() / 10.0 - 1) < 0.08
+    assert abs(np.median(lam) - 10 * np.log(2)) < 0.4
+    assert sp[..., 0].mean() > 0.95
+
+
+def test_same_seed_same_chain_different_seed_differs(O):
+    cfg = abi.default_cfg(n_warmup=50, n_iter=100, seed=9)
+    a, _ = O.sample_analytic(0, np.ones(3), cfg)
+    b, _ = O.sample_analytic(0, np.ones(3), cfg)
+    cfg.seed = 10
+    c, _ = O.sample_analytic(0, np.ones(3), cfg)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert not np.array_equal(a[:, 0], a[:, 1])  # chains use distinct Philox keys
+
+
+def test_short_warmup_rules(O):
+    # warmup < 20: no metric adaptation (step size only); warmup 100 (ctrlParams.yaml:1) -> 15/75/10 split
+    S = synth.make_profiles(1, modulated_only=True)
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=5)
+    spec = abi.default_spec()
+    out = O.sample(0, b, 1, spec, abi.default_cfg(n_warmup=10, n_iter=20, seed=1), n_threads=4)
+    assert np.all(out["inv_metric"] == 1.0)
+    out = O.sample(0, b, 1, spec, abi.default_cfg(n_warmup=100, n_iter=120, seed=1), n_threads=4)
+    assert np.all(out["inv_metric"] != 1.0) and np.all(out["inv_metric"] > 0)
+    assert np.all(np.isfinite(out["draws"]))
+
+
+def numpy_ess(x):
+    """Independent numpy restatement of MODEL_SPEC §9 n_eff for chains x[c, t] (FFT autocovariance)."""
+    C, n = x.shape
+    acov = []
+    for c in range(C):
+        xc = x[c] - x[c].mean()
+        f = np.fft.rfft(xc, 2 * n)
+        acov.append(np.fft.irfft(f * np.conj(f))[:n] / n)
+    acov = np.array(acov)
+    mean_var = (acov[:, 0] * n / (n - 1)).mean()
+    var_plus = mean_var * (n - 1) / n + (x.mean(axis=1).var(ddof=1) if C > 1 else 0.0)
+    rho = np.zeros(n + 2)
+    rho_even, rho_odd = 1.0, 1 - (mean_var - acov[:, 1].mean()) / var_plus
+    rho[0], rho[1] = rho_even, rho_odd
+    s = 1
+    while s < n - 4 and rho_even + rho_odd > 0:
+        rho_even = 1 - (mean_var - acov[:, s + 1].mean()) / var_plus
+        rho_odd = 1 - (mean_var - acov[:, s + 2].mean()) / var_plus
+        if rho_even + rho_odd >= 0:
+            rho[s + 1], rho[s + 2] = rho_even, rho_odd
+        s += 2
+    max_s = s
+    if rho_even > 0:
+        rho[max_s + 1] = rho_even
+    for s in range(1, max_s - 2, 2):
+        if rho[s + 1] + rho[s + 2] > rho[s - 1] + rho[s]:
+            rho[s + 1] = (rho[s - 1] + rho[s]) / 2
+            rho[s + 2] = rho[s + 1]
+    tau = -1 + 2 * rho[: max_s + 1].sum() + rho[max_s + 1]
+    return min(C * n / tau, C * n * np.log10(C * n))
+
+
+@pytest.mark.parametrize("phi,n", [(0.0, 400), (0.7, 1000), (0.95, 777), (-0.5, 500)])
+def test_summary_against_numpy(O, phi, n):
+    rng = np.random.default_rng(int(1000 * abs(phi)) + n)
+    C = 4
+    x = np.zeros((n, C, 2))
+    e = rng.standard_normal((n, C, 2))
+    for t in range(1, n):
+        x[t] = phi * x[t - 1] + e[t]
+    x[..., 1] = 5.0 + 2.0 * x[..., 1] + np.arange(C)[None, :] * 0.3   # offset chains -> Rhat > 1
+    S = O.summary(x)
+    for p in range(2):
+        col = x[..., p]
+        flat = col.T.reshape(-1)
+        assert np.isclose(S[p, 0], flat.mean(), rtol=1e-12)
+        assert np.isclose(S[p, 2], flat.std(ddof=1), rtol=1e-12)
+        np.testing.assert_allclose(S[p, 3:8], np.quantile(flat, [0.025, 0.25, 0.5, 0.75, 0.975]), rtol=1e-12)
+        assert np.isclose(S[p, 8], numpy_ess(col.T), rtol=1e-9)
+        h = n // 2
+        halves = np.concatenate([col[:h].T, col[n - h:].T])
+        W = halves.var(axis=1, ddof=1).mean()
+        Bv = halves.mean(axis=1).var(ddof=1)
+        assert np.isclose(S[p, 9], np.sqrt((W * (h - 1) / h + Bv) / W), rtol=1e-10)
+        # rank-normalised split chains through the same estimator
+        from scipy.stats import norm, rankdata
+        order = np.concatenate([np.stack([col[:h, c], col[n - h:, c]]) for c in range(C)])  # [2C, h] oracle layout
+        z = norm.ppf((rankdata(order.reshape(-1), method="ordinal") - 0.375) / (order.size + 0.25)).reshape(order.shape)
+        assert np.isclose(S[p, 10], numpy_ess(z), rtol=1e-8)
+        assert np.isclose(S[p, 1], S[p, 2] / np.sqrt(S[p, 8]), rtol=1e-12)
+    if abs(phi) < 0.9:
+        assert S[1, 9] > S[0, 9]
+
+
+def test_summary_edge_cases(O):
+    x = np.ones((50, 2, 1))
+    S = O.summary(x)
+    assert S[0, 0] == 1.0 and S[0, 2] == 0.0 and np.isnan(S[0, 8]) and np.isnan(S[0, 9])
+    x = np.random.default_rng(0).standard_normal((50, 2, 1)); x[3, 1, 0] = np.nan
+    assert np.all(np.isnan(O.summary(x)))
+
+
+def test_monoexp_map_recovers_truth(O):
+    S = synth.make_profiles(10)
+    idx = np.where(S["mod_kind"] == 0)[0]
+    b = abi.make_problems_dense(S["x"], S["Y"][idx], S["UY"][idx], S["theta0"][idx], S["Sigma0"][idx], Nn=0)
+    theta, H, br, st = O.monoexp_map(b, len(idx), abi.default_spec(abi.FOCT_MONOEXP))
+    assert np.all(st == 0)
+    for j in range(len(idx)):
+        cov = np.linalg.inv(-H[j])
+        z = (theta[j] - np.array([1000.0, 2000.0, 300.0])) / np.sqrt(np.diag(cov))
+        assert np.all(np.abs(z) < 4.5), z
+        assert 0.75 < br[j] < 1.25
+        # gradient of lp vanishes at the optimum
+        _, g, _ = O.logp_grad(abi.FOCT_MONOEXP, b, j, abi.default_spec(abi.FOCT_MONOEXP), theta[j][None, :])
+        assert np.all(np.abs(g) < 1e-6)
+
+
+def test_expgp_parameter_recovery_and_rhat(O):
+    # SURVEY §8c ladder (4): truth of synthData.R is recovered, sigma factor ~ 1, split-Rhat < 1.05 at 300 draws
+    S = synth.make_profiles(2, modulated_only=True)
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=10)
+    out = O.sample(0, b, 2, abi.default_spec(), abi.default_cfg(n_warmup=300, n_iter=600, seed=5))
+    for j in range(2):
+        s = out["summary"][j]
+        assert np.all(s[:15, 9] < 1.06)
+        assert abs(s[14, 0] - 1.0) < 0.15            # sigma
+        assert 0.7 < s[15, 0] < 1.3                   # br
+        assert abs(s[2, 0] - 300.0) < 5 * s[2, 2]     # theta3 = 2*l0 (dataType 2)
+        m, _, dl = O.predict(0, b, j, abi.default_spec(), out["draws"][j, ::20, 0])
+        truth = synth.modulation(int(S["mod_kind"][j]), S["x"])
+        # posterior-mean modulation tracks the sinc curve of synthData.R:21 within a loose band
+        assert np.abs(dl.mean(axis=0) - truth)[40:].max() < 0.08
+    assert out["n_divergent"].sum() <= 2
