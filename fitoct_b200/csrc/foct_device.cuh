@@ -3,8 +3,10 @@
 //
 // Layout contract: one warp owns one chain; lane d (< D) owns component d of every
 // D-vector (q, p, grad, rho, ...); warp-uniform scalars are held redundantly by all lanes.  The profile
-// lives in shared memory as a "blob": cx[Npad] | y[Npad] | w[Npad] | B[NN][Npad] (control-point major),
-// padded points carry w = 0 so they contribute exactly nothing.
+// lives in shared memory as a "blob" of npass = Npad/32 pass blocks; block j holds, for points 32j..32j+31,
+// the rows cx | y | w | B_0 .. B_{NN-1}, 32 doubles each, so that one warp pass reads every operand at a
+// compile-time offset from a single per-lane pointer (conflict-free LDS.64, no address arithmetic).
+// Padded points carry w = 0 and contribute exactly nothing.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -35,7 +37,7 @@ struct DevProblem {
 // Batch-global model switches (MODEL_SPEC §8), passed by value as kernel parameters.
 struct DevSpec {
   int ygp_prior, lambda_prior, theta_prior;
-  double sigma_mean, sigma_sd;
+  double sigma_mean, sigma_sd, sigma_inv_sd;
 };
 
 // ---------------------------------------------------------------- RNG (MODEL_SPEC §7)
@@ -76,7 +78,63 @@ __device__ __forceinline__ double normal_from(const uint32_t (&r)[4]) {
   return sqrt(-2.0 * log(u0)) * cos(6.283185307179586476925286766559 * u1);
 }
 
+// ---------------------------------------------------------------- blob layout
+// Index (in doubles) of row r (0 cx, 1 y, 2 w, 3+k basis k) of point i inside a blob.
+__host__ __device__ __forceinline__ size_t blob_index(int i, int r, int NN) {
+  return ((size_t)(i >> 5) * (size_t)(3 + NN) + (size_t)r) * 32u + (size_t)(i & 31);
+}
+
+// ---------------------------------------------------------------- fp64 exp
+// exp(x) = 2^n (1 + r + r^2 P(r)), n = rint(x log2 e), |r| <= ln2/2, P of degree 9 (Chebyshev interpolant,
+// 0.14 ulp approximation error; coefficients derived with mpmath).  Coefficients live in
+// constant memory so every DFMA takes its addend from the constant bank: no per-call constant
+// materialisation in the issue stream, which is what made the libdevice exp cost ~50 issue slots here.
+__constant__ double FEXP_C[10] = {
+    0x1.0000000000001p-1,  0x1.5555555555556p-3,  0x1.5555555553d63p-5,  0x1.11111111109b3p-7,
+    0x1.6c16c1788bd90p-10, 0x1.a01a01a7c41d5p-13, 0x1.a019b90d2ae7ap-16, 0x1.71de0dae63bb3p-19,
+    0x1.289185613a3d6p-22, 0x1.af38a9b0ec855p-26};
+__constant__ double FEXP_K[4] = {0x1.71547652b82fep+0 /* log2 e */, 6755399441055744.0 /* 1.5 * 2^52 */,
+                                 -0x1.62e42fefa39efp-1 /* -ln2 hi */, -0x1.abc9e3b39803fp-56 /* -ln2 lo */};
+
+// Branch-free: |x| >= 700 saturates to 0 / +inf (exp(-700) ~ 1e-304 is below anything the model can resolve;
+// a positive argument that large only arises from a negative decay length, i.e. a state that is non-finite
+// anyway), NaN propagates.  Being branch-free lets ptxas interleave two points of the sweep.
+__device__ __forceinline__ double fexp(double x) {
+  const double t = fma(x, FEXP_K[0], FEXP_K[1]);
+  const double nd = t - FEXP_K[1];
+  const int n = __double2loint(t);
+  double r = fma(nd, FEXP_K[2], x);
+  r = fma(nd, FEXP_K[3], r);
+  double p = FEXP_C[9];
+#pragma unroll
+  for (int k = 8; k >= 0; --k) p = fma(p, r, FEXP_C[k]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  double res = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+  res = x < -700.0 ? 0.0 : res;
+  res = x > 700.0 ? CUDART_INF : res;
+  return res;
+}
+
+// Branch-free reciprocal: MUFU.RCP64H seed (~20 bits), one cubic and one quadratic Newton step (the fast
+// path of the CUDA division, without its exponent-range slow path: a == 0 or denormal yields NaN, i.e. a
+// non-finite state, instead of +-inf).
+__device__ __forceinline__ double frcp(double a) {
+  double x0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(a));
+  double e = fma(-a, x0, 1.0);
+  e = fma(e, e, e);
+  const double x1 = fma(x0, e, x0);
+  const double e2 = fma(-a, x1, 1.0);
+  return fma(x1, e2, x1);
+}
+
 // ---------------------------------------------------------------- warp helpers
+__device__ __forceinline__ double selp(bool c, double a, double b) {
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b), "r"((int)c));
+  return r;
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FOCT_FULL, v, o);
@@ -98,8 +156,8 @@ __device__ __forceinline__ double warp_reduce_scatter(double (&v)[KP], int lane)
       const bool upper = (lane & off) != 0;
 #pragma unroll
       for (int j = 0; j < half; ++j) {
-        double keep = upper ? v[j + half] : v[j];
-        double send = upper ? v[j] : v[j + half];
+        const double keep = selp(upper, v[j + half], v[j]);
+        const double send = selp(upper, v[j], v[j + half]);
         v[j] = keep + __shfl_xor_sync(FOCT_FULL, send, off);
       }
       width = half;
@@ -130,23 +188,74 @@ struct Dims {
   static constexpr int KP = D <= 8 ? 8 : (D <= 16 ? 16 : 32);
 };
 
+// One data point of the sweep: lane-private loads at compile-time offsets from pp, ~70 fp64 instructions,
+// no branches.  Raw sums go to acc[] (theta2 / theta3 factors are applied once, after the reduction).
+template <int NN, int MOD, int KP, int ZI>
+__device__ __forceinline__ void sweep_point(const double* __restrict__ pp, double th1, double th2, double th3, double r3,
+                                            double isig, const double (&yg)[NN > 0 ? NN : 1], double (&acc)[KP]) {
+  double b[NN > 0 ? NN : 1];
+  double dl0 = 0.0, dl1 = 0.0;  // two partial sums halve the dependent chain of the basis dot product
+#pragma unroll
+  for (int k = 0; k < NN; ++k) {
+    b[k] = pp[(3 + k) * 32];
+    if (k & 1) dl1 = fma(b[k], yg[k], dl1); else dl0 = fma(b[k], yg[k], dl0);
+  }
+  const double s = 1.0 + (dl0 + dl1);
+  const double cx = pp[0], y = pp[32], ws = pp[64] * isig;
+  if (MOD == 0) {
+    const double r = NN > 0 ? frcp(th3 * s) : r3;
+    const double t = cx * r;
+    const double e = fexp(-t);
+    const double m = fma(th2, e, th1);
+    const double z = (y - m) * ws;
+    const double gi = z * ws;
+    const double ge = gi * e;
+    const double qq = ge * t * r;
+    acc[ZI] = fma(z, z, acc[ZI]);
+    acc[0] += gi;
+    acc[1] += ge;
+    acc[2] = fma(qq, s, acc[2]);
+#pragma unroll
+    for (int k = 0; k < NN; ++k) acc[3 + k] = fma(qq, b[k], acc[3 + k]);
+  } else {
+    const double t = cx * r3;
+    const double e = fexp(-t);
+    const double es = e * s;
+    const double m = fma(th2, es, th1);
+    const double z = (y - m) * ws;
+    const double gi = z * ws;
+    const double ge = gi * e;
+    const double ges = gi * es;
+    acc[ZI] = fma(z, z, acc[ZI]);
+    acc[0] += gi;
+    acc[1] += ges;
+    acc[2] = fma(ges, t, acc[2]);
+#pragma unroll
+    for (int k = 0; k < NN; ++k) acc[3 + k] = fma(ge, b[k], acc[3 + k]);
+  }
+}
+
 // Fused sweep over the staged profile.  qd = this lane's component of q.  Everything a lane needs from
-// the other lanes is fetched with shuffles up front; the per-point loop touches only shared memory.
+// the other lanes is fetched with shuffles up front; the per-point loop touches only shared memory and
+// processes two passes (64 points per warp) per iteration so that two independent dependency chains are
+// in flight per warp (the fp64 pipe was latency-, not throughput-bound with one: profiles/r1_*v1*).
 template <int NN, int MOD>
 __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, int npad, const DevProblem& P,
                                                const DevSpec& S, double qd, int lane) {
   using DM = Dims<NN>;
   constexpr int D = DM::D;
   constexpr int KP = DM::KP;
+  constexpr int UNROLL = NN <= 16 ? 2 : 1;
+  (void)npad;
   const double th1 = bcast(qd, 0), th2 = bcast(qd, 1), th3 = bcast(qd, 2);
   double yg[NN > 0 ? NN : 1];
 #pragma unroll
   for (int k = 0; k < NN; ++k) yg[k] = bcast(qd, 3 + k);
   const double qlam = DM::GP ? bcast(qd, 3 + NN) : 0.0;
   const double qsig = DM::GP ? bcast(qd, 4 + NN) : 0.0;
-  const double lam = DM::GP ? exp(qlam) : 1.0;
-  const double sig = DM::GP ? exp(qsig) : 1.0;
-  const double isig = DM::GP ? exp(-qsig) : 1.0;
+  const double lam = DM::GP ? fexp(qlam) : 1.0;
+  const double sig = DM::GP ? fexp(qsig) : 1.0;
+  const double isig = DM::GP ? fexp(-qsig) : 1.0;
 
   double acc[KP];
 #pragma unroll
@@ -156,54 +265,19 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
   Eval out;
   double zz = 0.0;
   if (!P.prior_PD) {
-    const double* s_cx = blob;
-    const double* s_y = blob + npad;
-    const double* s_w = blob + 2 * npad;
-    const double* s_B = blob + 3 * npad;
     const double r3 = 1.0 / th3;
+    constexpr int ROWS = 3 + NN;
+    const double* pp = blob + lane;
+    int pass = 0;
+    if (UNROLL == 2) {
 #pragma unroll 1
-    for (int i = lane; i < P.npass * 32; i += 32) {
-      double b[NN > 0 ? NN : 1];
-      double dl = 0.0;
-#pragma unroll
-      for (int k = 0; k < NN; ++k) {
-        b[k] = s_B[k * npad + i];
-        dl = fma(b[k], yg[k], dl);
-      }
-      const double s = 1.0 + dl;
-      const double cx = s_cx[i], y = s_y[i], ws = s_w[i] * isig;
-      if (MOD == 0) {
-        const double r = DM::GP ? 1.0 / (th3 * s) : r3;
-        const double t = cx * r;
-        const double e = exp(-t);
-        const double m = fma(th2, e, th1);
-        const double z = (y - m) * ws;
-        const double gi = z * ws;
-        const double ge = gi * e;
-        const double qq = ge * t * r;  // x theta2 after the reduction
-        acc[ZI] = fma(z, z, acc[ZI]);
-        acc[0] += gi;
-        acc[1] += ge;
-        acc[2] = fma(qq, s, acc[2]);
-#pragma unroll
-        for (int k = 0; k < NN; ++k) acc[3 + k] = fma(qq, b[k], acc[3 + k]);
-      } else {
-        const double t = cx * r3;
-        const double e = exp(-t);
-        const double es = e * s;
-        const double m = fma(th2, es, th1);
-        const double z = (y - m) * ws;
-        const double gi = z * ws;
-        const double ge = gi * e;
-        const double ges = gi * es;
-        acc[ZI] = fma(z, z, acc[ZI]);
-        acc[0] += gi;
-        acc[1] += ges;
-        acc[2] = fma(ges, t, acc[2]);
-#pragma unroll
-        for (int k = 0; k < NN; ++k) acc[3 + k] = fma(ge, b[k], acc[3 + k]);
+      for (; pass + 2 <= P.npass; pass += 2, pp += 2 * ROWS * 32) {
+        sweep_point<NN, MOD, KP, ZI>(pp, th1, th2, th3, r3, isig, yg, acc);
+        sweep_point<NN, MOD, KP, ZI>(pp + ROWS * 32, th1, th2, th3, r3, isig, yg, acc);
       }
     }
+#pragma unroll 1
+    for (; pass < P.npass; ++pass, pp += ROWS * 32) sweep_point<NN, MOD, KP, ZI>(pp, th1, th2, th3, r3, isig, yg, acc);
     // sum z^2 travels in slot ZI: the log-sigma gradient slot for GP models, the last slot otherwise
     const double red = warp_reduce_scatter<KP>(acc, lane);
     zz = bcast(red, ZI);
@@ -241,14 +315,14 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
   if (DM::GP) {
     double sy = 0.0;
     if (S.ygp_prior == 0) {
-      const double il2 = 1.0 / (lam * lam);
+      const double il2 = fexp(-2.0 * qlam);
 #pragma unroll
       for (int k = 0; k < NN; ++k) sy = fma(yg[k], yg[k], sy);
       out.lp += -(double)NN * qlam - 0.5 * sy * il2;
       if (lane >= 3 && lane < 3 + NN) out.g -= qd * il2;
       if (lane == 3 + NN) out.g += sy * il2 - (double)NN;
     } else {
-      const double il = 1.0 / lam;
+      const double il = fexp(-qlam);
 #pragma unroll
       for (int k = 0; k < NN; ++k) sy += fabs(yg[k]);
       out.lp += -(double)NN * qlam - sy * il;
@@ -264,9 +338,9 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
       if (lane == 3 + NN) out.g += -rl;
     }
     if (S.sigma_sd > 0.0) {
-      const double u = (sig - S.sigma_mean) / S.sigma_sd;
+      const double u = (sig - S.sigma_mean) * S.sigma_inv_sd;
       out.lp += -0.5 * u * u;
-      if (lane == 4 + NN) out.g += -sig * u / S.sigma_sd;
+      if (lane == 4 + NN) out.g += -sig * u * S.sigma_inv_sd;
     }
     out.lp += qlam + qsig;
     if (lane == 3 + NN || lane == 4 + NN) out.g += 1.0;

@@ -136,9 +136,9 @@ __global__ void __launch_bounds__(128) setup_kernel(const double* __restrict__ u
     double* blob = blobs + (size_t)j * blob_stride;
     for (int i = threadIdx.x; i < npad; i += blockDim.x) {
       const bool in = i < N;
-      blob[i] = in ? (double)M.dataType * x[i] : 0.0;
-      blob[npad + i] = in ? y[i] : 0.0;
-      blob[2 * npad + i] = in ? 1.0 / uy[i] : 0.0;
+      blob[blob_index(i, 0, NN)] = in ? (double)M.dataType * x[i] : 0.0;
+      blob[blob_index(i, 1, NN)] = in ? y[i] : 0.0;
+      blob[blob_index(i, 2, NN)] = in ? 1.0 / uy[i] : 0.0;
       if (NN > 0) {
         double v[FOCT_MAX_NN];
         if (in) {
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(128) setup_kernel(const double* __restrict__ u
             v[k] = s / sL[k * NN + k];
           }
         }
-        for (int k = 0; k < NN; ++k) blob[(size_t)(3 + k) * npad + i] = in ? v[k] : 0.0;
+        for (int k = 0; k < NN; ++k) blob[blob_index(i, 3 + k, NN)] = in ? v[k] : 0.0;
       }
     }
     __syncthreads();
@@ -171,11 +171,11 @@ __global__ void predict_kernel(const double* __restrict__ blob, int npad, int N,
     const int j = (int)(t / N), i = (int)(t % N);
     const double* r = draws + (size_t)j * P_out;
     double dl = 0.0;
-    for (int k = 0; k < NN; ++k) dl = fma(blob[(size_t)(3 + k) * npad + i], r[3 + k], dl);
-    const double cx = blob[i];
+    for (int k = 0; k < NN; ++k) dl = fma(blob[blob_index(i, 3 + k, NN)], r[3 + k], dl);
+    const double cx = blob[blob_index(i, 0, NN)];
     const double m = mod == 0 ? r[0] + r[1] * exp(-cx / (r[2] * (1.0 + dl))) : r[0] + r[1] * exp(-cx / r[2]) * (1.0 + dl);
     if (m_out) m_out[t] = m;
-    if (resid) resid[t] = blob[npad + i] - m;
+    if (resid) resid[t] = blob[blob_index(i, 1, NN)] - m;
     if (dL) dL[t] = dl;
   }
 }
@@ -213,11 +213,11 @@ __device__ void mono_nlp(const double* __restrict__ blob, int npad, const DevPro
 #pragma unroll
   for (int k = 0; k < 16; ++k) v[k] = 0.0;
   for (int i = lane; i < P.N; i += 32) {
-    const double w = blob[2 * npad + i], w2 = w * w;
-    const double t = blob[i] / th[2];
+    const double w = blob[blob_index(i, 2, 0)], w2 = w * w;
+    const double t = blob[blob_index(i, 0, 0)] / th[2];
     const double e = exp(-t);
     const double m = th[0] + th[1] * e;
-    const double r = blob[npad + i] - m;
+    const double r = blob[blob_index(i, 1, 0)] - m;
     const double J0 = 1.0, J1 = e, J2 = th[1] * e * t / th[2];
     const double m23 = e * t / th[2];
     const double m33 = th[1] * e * (t * t - 2.0 * t) / (th[2] * th[2]);
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(128) map_kernel(const double* __restrict__ blo
   } else {
     // log-linear start: theta1 just below min(y), regress log(y - theta1) on x
     double ymin = CUDART_INF, ymax = -CUDART_INF;
-    for (int i = lane; i < P.N; i += 32) { ymin = fmin(ymin, blob[npad + i]); ymax = fmax(ymax, blob[npad + i]); }
+    for (int i = lane; i < P.N; i += 32) { ymin = fmin(ymin, blob[blob_index(i, 1, 0)]); ymax = fmax(ymax, blob[blob_index(i, 1, 0)]); }
     for (int o = 16; o > 0; o >>= 1) {
       ymin = fmin(ymin, __shfl_xor_sync(FOCT_FULL, ymin, o));
       ymax = fmax(ymax, __shfl_xor_sync(FOCT_FULL, ymax, o));
@@ -268,9 +268,9 @@ __global__ void __launch_bounds__(128) map_kernel(const double* __restrict__ blo
     const double th1 = ymin - 0.05 * (ymax - ymin);
     double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = lane; i < P.N; i += 32) {
-      const double yy = blob[npad + i] - th1;
+      const double yy = blob[blob_index(i, 1, 0)] - th1;
       if (yy > 0.0) {
-        const double x = blob[i] / P.c, ly = log(yy);
+        const double x = blob[blob_index(i, 0, 0)] / P.c, ly = log(yy);
         v[0] += x; v[1] += ly; v[2] += x * x; v[3] += x * ly; v[4] += 1.0;
       }
     }
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(128) map_kernel(const double* __restrict__ blo
     const double slope = (nn * sxy - sx * sy) / (nn * sxx - sx * sx);
     const double icpt = (sy - slope * sx) / nn;
     th[0] = th1; th[1] = exp(icpt);
-    th[2] = slope < 0.0 ? -P.c / slope : (blob[P.N - 1] - blob[0]) / P.c;
+    th[2] = slope < 0.0 ? -P.c / slope : (blob[blob_index(P.N - 1, 0, 0)] - blob[0]) / P.c;
   }
   mono_nlp(blob, npad, P, theta_prior, th, f, g, H, c2, lane);
   double mu = 1e-3;
@@ -376,7 +376,7 @@ static int check_device() {
 static DevSpec dev_spec(const foct_model_spec& s) {
   DevSpec d;
   d.ygp_prior = s.ygp_prior; d.lambda_prior = s.lambda_prior; d.theta_prior = s.theta_prior;
-  d.sigma_mean = s.sigma_mean; d.sigma_sd = s.sigma_sd;
+  d.sigma_mean = s.sigma_mean; d.sigma_sd = s.sigma_sd; d.sigma_inv_sd = s.sigma_sd > 0.0 ? 1.0 / s.sigma_sd : 0.0;
   return d;
 }
 
@@ -506,9 +506,12 @@ extern "C" int foct_expgp_basis(const foct_problem* P, const foct_model_spec* sp
   DevProblem* d_probs;
   CU(cudaGetDevice(&dev));
   if (int rc = build_device_batch(FOCT_EXPGP, P, 1, spec, dev, 0, &NN, &npad, &stride, &d_blobs, &d_probs)) return rc;
-  cudaError_t e = cudaMemcpy2D(B_out, (size_t)P->N * sizeof(double), d_blobs + 3 * (size_t)npad, (size_t)npad * sizeof(double),
-                               (size_t)P->N * sizeof(double), NN, cudaMemcpyDeviceToHost);
+  std::vector<double> h(stride);
+  cudaError_t e = cudaMemcpy(h.data(), d_blobs, stride * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(d_blobs); cudaFree(d_probs);
+  if (e == cudaSuccess)
+    for (int k = 0; k < NN; ++k)
+      for (int i = 0; i < P->N; ++i) B_out[(size_t)k * P->N + i] = h[blob_index(i, 3 + k, NN)];
   if (e != cudaSuccess) return fail(FOCT_ECUDA, "copy of basis failed: %s", cudaGetErrorString(e));
   return 0;
 }

@@ -31,11 +31,16 @@ struct SamplerParams {
   int* work_counter;        // dynamic profile scheduler
 };
 
-__device__ __forceinline__ double lse2(double a, double b) {
-  if (a == -CUDART_INF) return b;
-  if (b == -CUDART_INF) return a;
-  const double mx = fmax(a, b), mn = fmin(a, b);
-  return mx + log1p(exp(mn - mx));
+// log(exp(a) + exp(b)) and exp(b - lse) = w_b / (w_a + w_b) from ONE exponential (Stan computes
+// log_sum_exp and then exp(lsw_final - lsw_subtree); same quantities).
+__device__ __forceinline__ double lse_prob(double a, double b, double& prob_b) {
+  const double d = b - a;
+  const double ad = fabs(d);
+  const double e = fexp(-ad);
+  double lse = fmax(a, b) + log1p(e);
+  prob_b = (d >= 0.0 ? 1.0 : e) / (1.0 + e);
+  if (!(ad >= 0.0)) { lse = -CUDART_INF; prob_b = 0.0; }  // both weights zero
+  return lse;
 }
 
 // The three generalised U-turn checks of one merge (init ++ final), each a pair of dot products:
@@ -190,19 +195,22 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
         if (isnan(h)) h = CUDART_INF;
         if (h - H0 > 1000.0) divergent = true;
         const double dw = H0 - h;
-        sum_metro += dw > 0.0 ? 1.0 : exp(dw);
+        sum_metro += dw > 0.0 ? 1.0 : fexp(dw);
         c_lsw = dw; c_rho = zp; c_pbeg = zp; c_pend = zp; c_qp = zq; c_gp = zg; c_V = zV; c_c2 = zc2; c_H = h;
         if (divergent) { valid = false; break; }
         // merge completed siblings upward: bit k of n set  <=>  slot k holds the init half
         int k = 0;
+        int mb_group = -1;
         for (; (n >> k) & 1u; ++k) {
-          const double i_lsw = st_lsw[k];
-          const double lsw_sub = lse2(i_lsw, c_lsw);
-          bool take_final = true;
-          if (!(c_lsw > lsw_sub)) {
-            rng.block((uint32_t)it, SITE_MERGE, (uint32_t)depth, n, (uint32_t)(k + 1), rb);
-            take_final = u53(rb[0], rb[1]) < exp(c_lsw - lsw_sub);
+          double prob_final;
+          const double lsw_sub = lse_prob(st_lsw[k], c_lsw, prob_final);
+          // one Philox block serves the merges of four consecutive levels at this leaf (32-bit uniforms)
+          if ((k >> 2) != mb_group) {
+            mb_group = k >> 2;
+            rng.block((uint32_t)it, SITE_MERGE, (uint32_t)depth, n, (uint32_t)mb_group, rb);
           }
+          const uint32_t w = (k & 3) == 0 ? rb[0] : ((k & 3) == 1 ? rb[1] : ((k & 3) == 2 ? rb[2] : rb[3]));
+          const bool take_final = ((double)w + 0.5) * 0x1.0p-32 < prob_final;
           const double i_rho = st_rho[k], i_pbeg = st_pbeg[k], i_pend = st_pend[k];
           const bool persist = merge_persists(invM, i_rho, i_pbeg, i_pend, c_rho, c_pbeg, c_pend, lane);
           if (!take_final) { c_qp = st_qp[k]; c_gp = st_gp[k]; c_V = st_V[k]; c_c2 = st_c2[k]; c_H = st_H[k]; }
@@ -218,8 +226,14 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       if (fwd) { fq = zq; fp = zp; fg = zg; } else { bq = zq; bp = zp; bg = zg; }
       if (!valid) break;
       ++depth;
-      if (c_lsw > lsw || u_top < exp(c_lsw - lsw)) { sq = c_qp; sg = c_gp; sV = c_V; sc2 = c_c2; sH = c_H; }
-      lsw = lse2(lsw, c_lsw);
+      {
+        double prob_new;
+        const double lsw_all = lse_prob(lsw, c_lsw, prob_new);
+        // biased progressive sampling: accept with min(1, w_new / w_old) = min(1, prob_new / (1 - prob_new))
+        const double ratio = c_lsw > lsw ? 1.0 : fexp(c_lsw - lsw);
+        if (c_lsw > lsw || u_top < ratio) { sq = c_qp; sg = c_gp; sV = c_V; sc2 = c_c2; sH = c_H; }
+        lsw = lsw_all;
+      }
       const bool persist = merge_persists(invM, rho, other_end_p, old_end_p, c_rho, c_pbeg, c_pend, lane);
       rho += c_rho;
       if (!persist) break;
@@ -312,7 +326,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
 #define FOCT_CTA_CHAINS 4
 template <int NN>
 struct NutsBounds {
-  static constexpr int MINB = NN <= 10 ? 4 : (NN <= 15 ? 3 : 2);
+  static constexpr int MINB = NN <= 15 ? 3 : 2;
 };
 
 template <int NN, int MOD>

@@ -181,15 +181,7 @@ __global__ void __launch_bounds__(SUM_THREADS) summary_kernel(const double* __re
   dummy = 0.0;
   for (int e = threadIdx.x; e < S; e += SUM_THREADS) { const double d = A[e] - mean; ss = fma(d, d, ss); }
   block_sum2(ss, dummy, scratch);
-  const double sd = S > 1 ? sqrt(ss / (S - 1.0)) : CUDART_NAN;
-  // 3. n_eff on the unsplit chains
-  double n_eff = CUDART_NAN;
-  if (ss > 0.0) {
-    for (int e = threadIdx.x; e < S; e += SUM_THREADS) W[e] = A[e];
-    __syncthreads();
-    n_eff = ess_block(W, n, C, scratch);
-  }
-  __syncthreads();
+
   // 4. bitonic sort of (value, index)
   for (int e = threadIdx.x; e < Spad; e += SUM_THREADS) { W[e] = e < S ? A[e] : CUDART_INF; I[e] = e; }
   __syncthreads();
@@ -216,10 +208,23 @@ __global__ void __launch_bounds__(SUM_THREADS) summary_kernel(const double* __re
     const int hi = lo + 1 < S ? lo + 1 : lo;
     o[3 + threadIdx.x] = W[lo] + (hq - lo) * (W[hi] - W[lo]);
   }
+  // 3. n_eff on the unsplit chains (a column whose min == max is constant: sd 0, diagnostics NaN, like rstan)
+  __syncthreads();
+  const bool constant = W[0] == W[S - 1];
+  __syncthreads();
+  double n_eff = CUDART_NAN;
+  if (constant) ss = 0.0;
+  if (!constant) {
+    for (int e = threadIdx.x; e < S; e += SUM_THREADS) W[e] = A[e];
+    __syncthreads();
+    n_eff = ess_block(W, n, C, scratch);
+  }
+  __syncthreads();
   // 6. split-Rhat on the raw values
   const int h = n / 2;
   double rhat = CUDART_NAN, bulk = CUDART_NAN;
-  if (h >= 2 && ss > 0.0) {
+  const double sd = S > 1 ? sqrt(ss / (S - 1.0)) : CUDART_NAN;
+  if (h >= 2 && !constant) {
     const int C2 = 2 * C;
     double Wv = 0.0, gm = 0.0, gm2 = 0.0;
     double cmn[2 * FOCT_MAX_CHAINS];

@@ -450,10 +450,11 @@ static int build_tree(nuts_t* S, int depth, pspoint* z_propose, double* ps_beg, 
   if (lsw_final > lsw_subtree) {
     *z_propose = z_propose_final;
   } else {
-    uint32_t r[4]; double u[2];
-    rng_block(&S->rng, S->it, SITE_MERGE, (uint32_t)top_depth, leaf_base + (1u << depth) - 1u, (uint32_t)depth, r);
-    foct_oracle_uniform2(r, u);
-    if (u[0] < exp(lsw_final - lsw_subtree)) *z_propose = z_propose_final;
+    /* merge draw site: one Philox block per (leaf, group of four levels); 32-bit uniform (MODEL_SPEC §7) */
+    uint32_t r[4];
+    rng_block(&S->rng, S->it, SITE_MERGE, (uint32_t)top_depth, leaf_base + (1u << depth) - 1u, (uint32_t)((depth - 1) >> 2), r);
+    double u = ((double)r[(depth - 1) & 3] + 0.5) * 0x1.0p-32;
+    if (u < exp(lsw_final - lsw_subtree)) *z_propose = z_propose_final;
   }
   double rho_sub[MAXD], rho_ext[MAXD];
   for (int d = 0; d < D; ++d) { rho_sub[d] = rho_init[d] + rho_final[d]; rho[d] += rho_sub[d]; }
@@ -964,9 +965,10 @@ int foct_oracle_summary(const double* draws, int n, int C, int P, double* out) {
     mean /= S;
     double ss = 0.0;
     for (int i = 0; i < S; ++i) ss += (col[i] - mean) * (col[i] - mean);
-    double sd = S > 1 ? sqrt(ss / (S - 1.0)) : NAN;
     memcpy(sorted, col, sizeof(double) * S);
     qsort(sorted, S, sizeof(double), cmp_double);
+    if (sorted[0] == sorted[S - 1]) ss = 0.0; /* constant column: sd 0, diagnostics NaN (rstan prints NaN) */
+    double sd = S > 1 ? sqrt(ss / (S - 1.0)) : NAN;
     static const double probs[5] = {0.025, 0.25, 0.5, 0.75, 0.975};
     for (int k = 0; k < 5; ++k) { /* R type 7 */
       double hq = (S - 1) * probs[k];

@@ -1,0 +1,60 @@
+# Drop-in wrappers with the signatures the reference calls (FitOCT.R:95, 110-124; priPost.R:2-16;
+# ShinyInterface/server.R:341-343, 408-426).  Swap `FitOCTLib::fitExpGP` for `FitOCTb200::fitExpGP`.
+# NOT RUN in this repository's image (no R): kept logic-free; all numerics are behind .Call.
+
+.par_names <- function(kind, Nn) {
+  if (kind == 0L) c(paste0("theta[", 1:3, "]"), paste0("yGP[", seq_len(Nn), "]"), "lambda", "sigma", "br", "lp__")
+  else c(paste0("theta[", 1:3, "]"), "br", "lp__")
+}
+
+# Build a genuine rstan stanfit through rstan's own reader: one Stan-CSV per chain -> rstan::read_stan_csv.
+.as_stanfit <- function(res, kind, Nn, chains, nb_warmup, nb_iter) {
+  pn <- .par_names(kind, Nn)
+  P  <- length(pn)
+  sp <- c("accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__")
+  d  <- aperm(array(res$draws, c(P, chains, nb_iter)), c(3, 2, 1))          # [iter, chain, par]
+  s  <- aperm(array(res$sampler_params, c(6, chains, nb_iter)), c(3, 2, 1))
+  files <- character(chains)
+  for (k in seq_len(chains)) {
+    f <- tempfile(fileext = ".csv"); files[k] <- f
+    lp <- d[, k, P]
+    tab <- cbind(lp__ = lp, s[, k, ], d[, k, -P, drop = TRUE])
+    colnames(tab) <- c("lp__", sp, gsub("\\[(\\d+)\\]", ".\\1", pn[-P]))
+    con <- file(f, "w")
+    writeLines(c("# model = fitoct_b200", paste0("# id = ", k), "# method = sample (Default)",
+                 paste0("#     num_samples = ", nb_iter - nb_warmup), paste0("#     num_warmup = ", nb_warmup),
+                 "#     save_warmup = 1", "#     thin = 1", "#     algorithm = hmc (Default)",
+                 "#       engine = nuts (Default)"), con)
+    write.table(tab, con, sep = ",", row.names = FALSE, quote = FALSE)
+    writeLines(c("# Adaptation terminated", paste0("# Step size = ", res$stepsize[k]),
+                 "# Diagonal elements of inverse mass matrix:",
+                 paste0("# ", paste(matrix(res$inv_metric, ncol = chains)[, k], collapse = ", "))), con)
+    close(con)
+  }
+  rstan::read_stan_csv(files)
+}
+
+fitExpGP <- function(x, y, uy, dataType = 2, Nn = 10, gridType = "internal", method = "sample",
+                     theta0 = NULL, Sigma0 = NULL, lambda_rate = 0.1, rho_scale = 0.1,
+                     nb_warmup = 500, nb_iter = 1500, prior_PD = 0, open_progress = FALSE,
+                     chains = 4, seed = sample.int(.Machine$integer.max, 1)) {
+  stopifnot(method == "sample")   # optim / vb: SURVEY 8(f) N1 / N4
+  ctl <- list(dataType = dataType, Nn = Nn, gridType = as.integer(gridType == "extremal"),
+              rho = ifelse(rho_scale == 0, 1 / Nn, rho_scale), lambda_rate = lambda_rate,
+              theta0 = as.numeric(theta0), Sigma0 = as.numeric(Sigma0), prior_PD = prior_PD,
+              chains = chains, nb_warmup = nb_warmup, nb_iter = nb_iter, seed = seed)
+  res <- .Call("foct_R_sample", 0L, as.numeric(x), as.numeric(y), as.numeric(uy), ctl, PACKAGE = "FitOCTb200")
+  dx  <- 1 / (Nn + 1)
+  xGP <- if (gridType == "internal") seq(dx / 2, 1 - dx / 2, length.out = Nn) else seq(0, 1, length.out = Nn)
+  list(fit = .as_stanfit(res, 0L, Nn, chains, nb_warmup, nb_iter), method = method, xGP = xGP, prior_PD = prior_PD)
+}
+
+fitMonoExp <- function(x, y, uy, dataType = 2) {
+  r   <- .Call("foct_R_monoexp_map", as.numeric(x), as.numeric(y), as.numeric(uy), as.integer(dataType),
+               PACKAGE = "FitOCTb200")
+  cov <- solve(-r$hessian)
+  list(best.theta = r$theta, cor.theta = cov2cor(cov),
+       fit = list(par = list(theta = r$theta, m = r$m, resid = r$resid, br = r$br), hessian = r$hessian,
+                  return_code = r$status),
+       method = "optim")
+}

@@ -202,8 +202,9 @@ def test_map_and_predict_vs_oracle(L, O):
         th, H, br, st = L.monoexp_map(b, 10, spec)
         tho, Ho, bro, sto = O.monoexp_map(b, 10, spec)
         assert np.all(st == 0) and np.all(sto == 0)
-        np.testing.assert_allclose(th, tho, rtol=1e-9)
-        np.testing.assert_allclose(H, Ho, rtol=1e-7)
+        # both sides stop at a relative step < 1e-12; the optimum itself is only defined to ~sqrt(eps) * sd
+        np.testing.assert_allclose(th, tho, rtol=1e-7)
+        np.testing.assert_allclose(H, Ho, rtol=1e-6)
         np.testing.assert_allclose(br, bro, rtol=1e-9)
     b10 = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=10)
     rows = np.zeros((4, 17))
