@@ -105,11 +105,22 @@ __device__ __forceinline__ double fexp(double x) {
   const int n = __double2loint(t);
   double r = fma(nd, FEXP_K[2], x);
   r = fma(nd, FEXP_K[3], r);
-  double p = FEXP_C[9];
-#pragma unroll
-  for (int k = 8; k >= 0; --k) p = fma(p, r, FEXP_C[k]);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+  // Estrin evaluation of 1 + r + r^2 (c0 + c1 r + ... + c9 r^9): depth 4 instead of 11 dependent DFMAs for
+  // 3 extra multiplies (the sweep is latency-bound, not pipe-bound: profiles/r1_ncu_nuts_v2_summary.txt)
+  const double r2 = r * r;
+  const double q0 = 1.0 + r;
+  const double q1 = fma(FEXP_C[1], r, FEXP_C[0]);
+  const double q2 = fma(FEXP_C[3], r, FEXP_C[2]);
+  const double q3 = fma(FEXP_C[5], r, FEXP_C[4]);
+  const double q4 = fma(FEXP_C[7], r, FEXP_C[6]);
+  const double q5 = fma(FEXP_C[9], r, FEXP_C[8]);
+  const double r4 = r2 * r2;
+  const double s0 = fma(q1, r2, q0);
+  const double s1 = fma(q3, r2, q2);
+  const double s2 = fma(q5, r2, q4);
+  const double r8 = r4 * r4;
+  const double t0 = fma(s1, r4, s0);
+  const double p = fma(s2, r8, t0);
   double res = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
   res = x < -700.0 ? 0.0 : res;
   res = x > 700.0 ? CUDART_INF : res;
@@ -141,7 +152,6 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(FOCT_FULL, v, src); }
-
 // Transposed ("reduce-scatter") warp reduction of KP (= 8, 16 or 32) per-lane accumulators: KP-1 + (5-log2 KP)
 // 64-bit shuffles instead of 5*KP.  On return, the full sum of accumulator index a is returned to lane a
 // (a < KP); lanes >= KP get accumulator (lane mod KP).
@@ -188,50 +198,138 @@ struct Dims {
   static constexpr int KP = D <= 8 ? 8 : (D <= 16 ? 16 : 32);
 };
 
-// One data point of the sweep: lane-private loads at compile-time offsets from pp, ~70 fp64 instructions,
-// no branches.  Raw sums go to acc[] (theta2 / theta3 factors are applied once, after the reduction).
-template <int NN, int MOD, int KP, int ZI>
-__device__ __forceinline__ void sweep_point(const double* __restrict__ pp, double th1, double th2, double th3, double r3,
-                                            double isig, const double (&yg)[NN > 0 ? NN : 1], double (&acc)[KP]) {
-  double b[NN > 0 ? NN : 1];
-  double dl0 = 0.0, dl1 = 0.0;  // two partial sums halve the dependent chain of the basis dot product
+// U data points of the sweep processed in LOCKSTEP, statement by statement (ptxas keeps source order inside a
+// basic block, so writing the U independent dependency chains interleaved is what actually puts U chains in
+// flight; two inlined copies of a one-point body were scheduled back to back — profiles/r1_ncu_nuts_v2).
+// Lane-private loads at compile-time offsets from pp, ~52 fp64 instructions per point, no branches.
+// Raw sums go to acc[] (theta2 / theta3 factors are applied once, after the reduction).
+template <int NN, int MOD, int KP, int ZI, int U>
+__device__ __forceinline__ void sweep_points(const double* __restrict__ pp, double th1, double th2, double th3, double r3,
+                                             double isig, const double (&yg)[NN > 0 ? NN : 1], double (&acc)[KP]) {
+  constexpr int STRIDE = (3 + NN) * 32;
+  double b[U][NN > 0 ? NN : 1];
+  double dl0[U], dl1[U], s[U], cx[U], y[U], ws[U], r[U], t[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) { dl0[u] = 0.0; dl1[u] = 0.0; }
 #pragma unroll
   for (int k = 0; k < NN; ++k) {
-    b[k] = pp[(3 + k) * 32];
-    if (k & 1) dl1 = fma(b[k], yg[k], dl1); else dl0 = fma(b[k], yg[k], dl0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      b[u][k] = pp[u * STRIDE + (3 + k) * 32];
+      if (k & 1) dl1[u] = fma(b[u][k], yg[k], dl1[u]); else dl0[u] = fma(b[u][k], yg[k], dl0[u]);
+    }
   }
-  const double s = 1.0 + (dl0 + dl1);
-  const double cx = pp[0], y = pp[32], ws = pp[64] * isig;
-  if (MOD == 0) {
-    const double r = NN > 0 ? frcp(th3 * s) : r3;
-    const double t = cx * r;
-    const double e = fexp(-t);
-    const double m = fma(th2, e, th1);
-    const double z = (y - m) * ws;
-    const double gi = z * ws;
-    const double ge = gi * e;
-    const double qq = ge * t * r;
-    acc[ZI] = fma(z, z, acc[ZI]);
-    acc[0] += gi;
-    acc[1] += ge;
-    acc[2] = fma(qq, s, acc[2]);
 #pragma unroll
-    for (int k = 0; k < NN; ++k) acc[3 + k] = fma(qq, b[k], acc[3 + k]);
+  for (int u = 0; u < U; ++u) {
+    s[u] = 1.0 + (dl0[u] + dl1[u]);
+    cx[u] = pp[u * STRIDE];
+    y[u] = pp[u * STRIDE + 32];
+    ws[u] = pp[u * STRIDE + 64] * isig;
+  }
+  // reciprocal of the local decay length (length modulation with a GP); otherwise r3 is hoisted
+  if (MOD == 0 && NN > 0) {
+    double a[U], x0[U], e[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { a[u] = th3 * s[u]; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0[u]) : "d"(a[u])); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) e[u] = fma(-a[u], x0[u], 1.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) e[u] = fma(e[u], e[u], e[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) x0[u] = fma(x0[u], e[u], x0[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) e[u] = fma(-a[u], x0[u], 1.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = fma(x0[u], e[u], x0[u]);
   } else {
-    const double t = cx * r3;
-    const double e = fexp(-t);
-    const double es = e * s;
-    const double m = fma(th2, es, th1);
-    const double z = (y - m) * ws;
-    const double gi = z * ws;
-    const double ge = gi * e;
-    const double ges = gi * es;
-    acc[ZI] = fma(z, z, acc[ZI]);
-    acc[0] += gi;
-    acc[1] += ges;
-    acc[2] = fma(ges, t, acc[2]);
 #pragma unroll
-    for (int k = 0; k < NN; ++k) acc[3 + k] = fma(ge, b[k], acc[3 + k]);
+    for (int u = 0; u < U; ++u) r[u] = r3;
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) t[u] = cx[u] * r[u];
+  // e = exp(-t), same algorithm as fexp(), staged across the U points
+  double x[U], tt[U], nd[U], rr[U], r2[U], r4[U], r8[U], q0[U], q1[U], q2[U], q3[U], q4[U], q5[U], e[U];
+  int n[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) { x[u] = -t[u]; tt[u] = fma(x[u], FEXP_K[0], FEXP_K[1]); }
+#pragma unroll
+  for (int u = 0; u < U; ++u) { nd[u] = tt[u] - FEXP_K[1]; n[u] = __double2loint(tt[u]); }
+#pragma unroll
+  for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXP_K[2], x[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXP_K[3], rr[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    r2[u] = rr[u] * rr[u];
+    q0[u] = 1.0 + rr[u];
+    q1[u] = fma(FEXP_C[1], rr[u], FEXP_C[0]);
+    q2[u] = fma(FEXP_C[3], rr[u], FEXP_C[2]);
+    q3[u] = fma(FEXP_C[5], rr[u], FEXP_C[4]);
+    q4[u] = fma(FEXP_C[7], rr[u], FEXP_C[6]);
+    q5[u] = fma(FEXP_C[9], rr[u], FEXP_C[8]);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    r4[u] = r2[u] * r2[u];
+    q0[u] = fma(q1[u], r2[u], q0[u]);
+    q2[u] = fma(q3[u], r2[u], q2[u]);
+    q4[u] = fma(q5[u], r2[u], q4[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) { r8[u] = r4[u] * r4[u]; q0[u] = fma(q2[u], r4[u], q0[u]); }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const double p = fma(q4[u], r8[u], q0[u]);
+    double res = __hiloint2double(__double2hiint(p) + (n[u] << 20), __double2loint(p));
+    res = x[u] < -700.0 ? 0.0 : res;
+    e[u] = x[u] > 700.0 ? CUDART_INF : res;
+  }
+  if (MOD == 0) {
+    double m[U], z[U], gi[U], ge[U], qq[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) m[u] = fma(th2, e[u], th1);
+#pragma unroll
+    for (int u = 0; u < U; ++u) z[u] = (y[u] - m[u]) * ws[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) gi[u] = z[u] * ws[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) ge[u] = gi[u] * e[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) qq[u] = ge[u] * t[u] * r[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      acc[ZI] = fma(z[u], z[u], acc[ZI]);
+      acc[0] += gi[u];
+      acc[1] += ge[u];
+      acc[2] = fma(qq[u], s[u], acc[2]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < NN; ++k) acc[3 + k] = fma(qq[u], b[u][k], acc[3 + k]);
+  } else {
+    double es[U], m[U], z[U], gi[U], ge[U], ges[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) es[u] = e[u] * s[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) m[u] = fma(th2, es[u], th1);
+#pragma unroll
+    for (int u = 0; u < U; ++u) z[u] = (y[u] - m[u]) * ws[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) gi[u] = z[u] * ws[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { ge[u] = gi[u] * e[u]; ges[u] = gi[u] * es[u]; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      acc[ZI] = fma(z[u], z[u], acc[ZI]);
+      acc[0] += gi[u];
+      acc[1] += ges[u];
+      acc[2] = fma(ges[u], t[u], acc[2]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < NN; ++k) acc[3 + k] = fma(ge[u], b[u][k], acc[3 + k]);
   }
 }
 
@@ -245,7 +343,10 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
   using DM = Dims<NN>;
   constexpr int D = DM::D;
   constexpr int KP = DM::KP;
-  constexpr int UNROLL = NN <= 16 ? 2 : 1;
+#ifndef FOCT_UNROLL
+#define FOCT_UNROLL 2
+#endif
+  constexpr int UNROLL = NN <= 16 ? FOCT_UNROLL : 1;
   (void)npad;
   const double th1 = bcast(qd, 0), th2 = bcast(qd, 1), th3 = bcast(qd, 2);
   double yg[NN > 0 ? NN : 1];
@@ -269,15 +370,13 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
     constexpr int ROWS = 3 + NN;
     const double* pp = blob + lane;
     int pass = 0;
-    if (UNROLL == 2) {
+    if (UNROLL >= 2) {
 #pragma unroll 1
-      for (; pass + 2 <= P.npass; pass += 2, pp += 2 * ROWS * 32) {
-        sweep_point<NN, MOD, KP, ZI>(pp, th1, th2, th3, r3, isig, yg, acc);
-        sweep_point<NN, MOD, KP, ZI>(pp + ROWS * 32, th1, th2, th3, r3, isig, yg, acc);
-      }
+      for (; pass + UNROLL <= P.npass; pass += UNROLL, pp += UNROLL * ROWS * 32)
+        sweep_points<NN, MOD, KP, ZI, UNROLL>(pp, th1, th2, th3, r3, isig, yg, acc);
     }
 #pragma unroll 1
-    for (; pass < P.npass; ++pass, pp += ROWS * 32) sweep_point<NN, MOD, KP, ZI>(pp, th1, th2, th3, r3, isig, yg, acc);
+    for (; pass < P.npass; ++pass, pp += ROWS * 32) sweep_points<NN, MOD, KP, ZI, 1>(pp, th1, th2, th3, r3, isig, yg, acc);
     // sum z^2 travels in slot ZI: the log-sigma gradient slot for GP models, the last slot otherwise
     const double red = warp_reduce_scatter<KP>(acc, lane);
     zz = bcast(red, ZI);

@@ -326,7 +326,10 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
 #define FOCT_CTA_CHAINS 4
 template <int NN>
 struct NutsBounds {
-  static constexpr int MINB = NN <= 15 ? 3 : 2;
+#ifndef FOCT_MINB
+#define FOCT_MINB 3
+#endif
+  static constexpr int MINB = NN <= 15 ? FOCT_MINB : 2;
 };
 
 template <int NN, int MOD>
