@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(128) logp_kernel(const LogpParams K) {
     for (int iq = warp; iq < K.n_q; iq += nwarp) {
       const size_t r = (size_t)j * K.n_q + iq;
       const double qd = lane < D ? K.q[r * D + lane] : 0.0;
-      const Eval ev = warp_logp_grad<NN, MOD>(smem, K.npad, s_prob, K.spec, qd, lane);
+      const Eval ev = warp_logp_grad<NN, MOD>(smem, smem + K.blob_stride + (size_t)warp * K.npad, s_prob, K.spec, qd, lane);
       if (lane < D) K.grad[r * D + lane] = ev.g;
       if (lane == 0) {
         K.lp[r] = ev.lp;
