@@ -78,6 +78,7 @@ class SamplerCfg(C.Structure):
         ("window", C.c_int),
         ("n_devices", C.c_int),
         ("devices", C.POINTER(C.c_int)),
+        ("team_width", C.c_int),
     ]
 
 

@@ -1,0 +1,83 @@
+"""GPU (-m gpu): BASELINE.json's batch size (1,000 profiles x 4 chains, Nn = 10, 500 + 1000 iterations) checked through
+size-independent properties: convergence diagnostics, recovery of the synthData.R truth, determinism, agreement
+between the device-resident (plan) and the one-shot host-buffer paths, and additivity of the batch."""
+import numpy as np
+import pytest
+
+from fitoct_b200 import _abi as abi
+from fitoct_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+N_PROFILES = 1000
+
+
+@pytest.fixture(scope="module")
+def batch_run(L):
+    S = synth.make_profiles(N_PROFILES, modulated_only=True)
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=10, ids=S["ids"])
+    cfg = abi.default_cfg(n_warmup=500, n_iter=1500, seed=1234)
+    out = L.sample(abi.FOCT_EXPGP, b, N_PROFILES, abi.default_spec(), cfg, draws=False, summary=True)
+    return S, b, cfg, out
+
+
+def test_batch_converges(batch_run):
+    S, b, cfg, out = batch_run
+    s = out["summary"]
+    assert np.isfinite(s[:, :15]).all()
+    rhat = s[:, :15, 9].max(axis=1)
+    # north_star target R-hat < 1.01; with 4 x 1000 draws the split-Rhat estimator itself scatters by ~0.005
+    assert np.mean(rhat < 1.01) > 0.70
+    assert np.mean(rhat < 1.02) > 0.97
+    assert rhat.max() < 1.06
+    assert np.median(s[:, :15, 10].min(axis=1)) > 500            # min Bulk_ESS over parameters, per profile
+    assert out["n_divergent"].sum() <= 0.001 * N_PROFILES * 4 * 1000
+    assert np.all(out["stepsize"] > 1e-3) and np.all(out["inv_metric"] > 0)
+
+
+def test_batch_recovers_synthData_truth(batch_run):
+    S, b, cfg, out = batch_run
+    s = out["summary"]
+    truth = np.array([1000.0, 2000.0, 300.0])                      # a, b, 2*l0 (synthData.R:4-6, dataType 2)
+    z = (s[:, :3, 0] - truth) / s[:, :3, 2]
+    assert np.mean(np.abs(z) < 3) > 0.97
+    assert abs(np.mean(z)) < 0.35                                  # no systematic bias beyond the theta0 prior pull
+    assert abs(s[:, 14, 0].mean() - 1.0) < 0.03                    # sigma factor ~ 1: uy is the true sd
+    assert abs(s[:, 15, 0].mean() - 1.0) < 0.08                    # Birge ratio ~ 1
+    # 95 % interval coverage of theta3 across profiles
+    cover = np.mean((s[:, 2, 3] < 300.0) & (300.0 < s[:, 2, 7]))
+    assert 0.88 < cover <= 1.0
+
+
+def test_plan_path_equals_one_shot_path(L, batch_run):
+    S, b, cfg, out = batch_run
+    n = 64
+    sub = abi.make_problems_dense(S["x"], S["Y"][:n], S["UY"][:n], S["theta0"][:n], S["Sigma0"][:n], Nn=10, ids=S["ids"][:n])
+    cfg.team_width = 1   # same kernel variant as the 1000-profile batch (a 64-profile batch would pick the wide one)
+    plan = L.Plan(abi.FOCT_EXPGP, sub, n, abi.default_spec(), cfg, want_draws=False, want_summary=True)
+    plan.run(cfg.seed)
+    ms = plan.sync()
+    res = plan.fetch()
+    tm = plan.timing()
+    plan.close()
+    assert ms > 0 and tm["grid"] >= 1 and tm["regs"] > 0
+    # same seed, same profile ids => bit-identical to the slice of the big one-shot batch
+    np.testing.assert_array_equal(res["summary"], out["summary"][:n])
+    np.testing.assert_array_equal(res["n_leapfrog"], out["n_leapfrog"][:n])
+    np.testing.assert_array_equal(res["stepsize"], out["stepsize"][:n])
+    cfg.team_width = 0
+
+
+def test_leapfrog_accounting(L, batch_run):
+    # the roofline numerator: leapfrogs counted on device equal the n_leapfrog__ column of the draws
+    S, b, cfg, out = batch_run
+    n = 8
+    sub = abi.make_problems_dense(S["x"], S["Y"][:n], S["UY"][:n], S["theta0"][:n], S["Sigma0"][:n], Nn=10, ids=S["ids"][:n])
+    cfg2 = abi.default_cfg(n_warmup=500, n_iter=1500, seed=1234, save_warmup=1, team_width=1)
+    o = L.sample(abi.FOCT_EXPGP, sub, n, abi.default_spec(), cfg2, draws=True, summary=True)
+    np.testing.assert_array_equal(o["n_leapfrog"][..., 0], o["sampler_params"][:, :500, :, 3].sum(axis=1))
+    np.testing.assert_array_equal(o["n_leapfrog"][..., 1], o["sampler_params"][:, 500:, :, 3].sum(axis=1))
+    np.testing.assert_array_equal(o["n_leapfrog"], out["n_leapfrog"][:n])   # saving draws does not change the chains
+    td = o["sampler_params"][..., 2]
+    assert td.max() <= 10 and np.all(o["sampler_params"][..., 3] <= 2 ** td - 1 + 1e-9)
+    assert np.all((o["sampler_params"][..., 0] >= 0) & (o["sampler_params"][..., 0] <= 1))
