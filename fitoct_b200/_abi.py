@@ -78,7 +78,6 @@ class SamplerCfg(C.Structure):
         ("window", C.c_int),
         ("n_devices", C.c_int),
         ("devices", C.POINTER(C.c_int)),
-        ("team_width", C.c_int),
     ]
 
 

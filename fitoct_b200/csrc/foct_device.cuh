@@ -211,11 +211,11 @@ struct Dims {
 // flight; two inlined copies of a one-point body were scheduled back to back — profiles/r1_ncu_nuts_v2).
 // Lane-private loads at compile-time offsets from pp, ~52 fp64 instructions per point, no branches.
 // Raw sums go to acc[] (theta2 / theta3 factors are applied once, after the reduction).
-template <int NN, int MOD, int KP, int ZI, int U, bool SPLIT, int PSTRIDE>
+template <int NN, int MOD, int KP, int ZI, int U, bool SPLIT>
 __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, double* __restrict__ sq, double th1, double th2,
                                              double th3, double r3, double isig, const double (&yg)[NN > 0 ? NN : 1],
                                              double (&acc)[KP]) {
-  constexpr int STRIDE = (3 + NN) * 32 * PSTRIDE;  // distance between the U points handled together
+  constexpr int STRIDE = (3 + NN) * 32;
   double b[SPLIT ? 1 : U][NN > 0 ? NN : 1];  // SPLIT: basis values are consumed by the dot product and not kept
   double dl0[U], dl1[U], s[U], cx[U], y[U], ws[U], r[U], t[U];
 #pragma unroll
@@ -322,7 +322,7 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
     }
     if (SPLIT) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) sq[u * 32 * PSTRIDE] = qq[u];
+      for (int u = 0; u < U; ++u) sq[u * 32] = qq[u];
     } else {
 #pragma unroll
       for (int u = 0; u < U; ++u)
@@ -350,7 +350,7 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
     }
     if (SPLIT) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) sq[u * 32 * PSTRIDE] = ge[u];
+      for (int u = 0; u < U; ++u) sq[u * 32] = ge[u];
     } else {
 #pragma unroll
       for (int u = 0; u < U; ++u)
@@ -360,24 +360,13 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
   }
 }
 
-// A chain may be evaluated by a TEAM of W warps ("wide" mode, used when a batch is too small to fill the GPU, e.g.
-// the single-profile calls FitOCT.R makes): warp w sweeps passes w, w+W, ...; the partial sums are combined in a
-// fixed order through shared memory, so all W warps obtain bit-identical totals and run the (replicated) tree logic
-// in lockstep without any further communication.
-struct Team {
-  int w;          // this warp's index inside the team
-  double* part;   // [2][W][32] doubles of shared memory owned by this chain (double-buffered by call parity)
-  int bar_id;     // named barrier of this chain (1..), W * 32 threads
-  int parity;     // toggles every evaluation
-};
-
 // Fused sweep over the staged profile.  qd = this lane's component of q.  Everything a lane needs from
 // the other lanes is fetched with shuffles up front; the per-point loop touches only shared memory and
 // processes two passes (64 points per warp) per iteration so that two independent dependency chains are
 // in flight per warp (the fp64 pipe was latency-, not throughput-bound with one: profiles/r1_*v1*).
-template <int NN, int MOD, int W>
+template <int NN, int MOD>
 __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, double* __restrict__ scratch,
-                                               const DevProblem& P, const DevSpec& S, double qd, int lane, Team& team) {
+                                               const DevProblem& P, const DevSpec& S, double qd, int lane) {
   using DM = Dims<NN>;
   constexpr int D = DM::D;
   constexpr int KP = DM::KP;
@@ -409,40 +398,30 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
   if (!P.prior_PD) {
     const double r3 = 1.0 / th3;
     constexpr int ROWS = 3 + NN;
-    const int w0 = W > 1 ? team.w : 0;
-    const double* pp = blob + lane + (size_t)w0 * ROWS * 32;
-    double* sq = scratch + lane + w0 * 32;
-    int pass = w0;
+    const double* pp = blob + lane;
+    int pass = 0;
+    double* sq = scratch + lane;
     if (UNROLL >= 2) {
 #pragma unroll 1
-      for (; pass + (UNROLL - 1) * W < P.npass; pass += UNROLL * W, pp += UNROLL * W * ROWS * 32, sq += UNROLL * W * 32)
-        sweep_points<NN, MOD, KP, ZI, UNROLL, SPLIT, W>(pp, sq, th1, th2, th3, r3, isig, yg, acc);
+      for (; pass + UNROLL <= P.npass; pass += UNROLL, pp += UNROLL * ROWS * 32, sq += UNROLL * 32)
+        sweep_points<NN, MOD, KP, ZI, UNROLL, SPLIT>(pp, sq, th1, th2, th3, r3, isig, yg, acc);
     }
 #pragma unroll 1
-    for (; pass < P.npass; pass += W, pp += W * ROWS * 32, sq += W * 32)
-      sweep_points<NN, MOD, KP, ZI, 1, SPLIT, W>(pp, sq, th1, th2, th3, r3, isig, yg, acc);
+    for (; pass < P.npass; ++pass, pp += ROWS * 32, sq += 32)
+      sweep_points<NN, MOD, KP, ZI, 1, SPLIT>(pp, sq, th1, th2, th3, r3, isig, yg, acc);
     if (SPLIT) {
       // every lane re-reads only what it wrote itself: no synchronisation needed
-      const double* pb = blob + lane + 3 * 32 + (size_t)w0 * ROWS * 32;
-      const double* sr = scratch + lane + w0 * 32;
+      const double* pb = blob + lane + 3 * 32;
+      const double* sr = scratch + lane;
 #pragma unroll 2
-      for (int ps = w0; ps < P.npass; ps += W, pb += W * ROWS * 32, sr += W * 32) {
+      for (int ps = 0; ps < P.npass; ++ps, pb += ROWS * 32, sr += 32) {
         const double w = *sr;
 #pragma unroll
         for (int k = 0; k < NN; ++k) acc[3 + k] = fma(w, pb[k * 32], acc[3 + k]);
       }
     }
     // sum z^2 travels in slot ZI: the log-sigma gradient slot for GP models, the last slot otherwise
-    double red = warp_reduce_scatter<KP>(acc, lane);
-    if (W > 1) {
-      double* buf = team.part + team.parity * (W * 32);
-      team.parity ^= 1;
-      buf[team.w * 32 + lane] = red;
-      asm volatile("bar.sync %0, %1;" ::"r"(team.bar_id), "r"(W * 32) : "memory");
-      red = buf[lane];
-#pragma unroll
-      for (int v = 1; v < W; ++v) red += buf[v * 32 + lane];
-    }
+    const double red = warp_reduce_scatter<KP>(acc, lane);
     zz = bcast(red, ZI);
     // scale the raw sums into gradient components
     double scale = 1.0;

@@ -25,8 +25,7 @@ __global__ void __launch_bounds__(128) logp_kernel(const LogpParams K) {
     for (int iq = warp; iq < K.n_q; iq += nwarp) {
       const size_t r = (size_t)j * K.n_q + iq;
       const double qd = lane < D ? K.q[r * D + lane] : 0.0;
-      Team team = {0, nullptr, 0, 0};
-      const Eval ev = warp_logp_grad<NN, MOD, 1>(smem, smem + K.blob_stride + (size_t)warp * K.npad, s_prob, K.spec, qd, lane, team);
+      const Eval ev = warp_logp_grad<NN, MOD>(smem, smem + K.blob_stride + (size_t)warp * K.npad, s_prob, K.spec, qd, lane);
       if (lane < D) K.grad[r * D + lane] = ev.g;
       if (lane == 0) {
         K.lp[r] = ev.lp;
@@ -37,18 +36,19 @@ __global__ void __launch_bounds__(128) logp_kernel(const LogpParams K) {
   }
 }
 
-template <int NN, int MOD, int W>
-static cudaError_t launch_nuts_v(int grid, int block, size_t smem, cudaStream_t st, const SamplerParams& K) {
-  cudaError_t e = cudaFuncSetAttribute(nuts_kernel<NN, MOD, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  nuts_kernel<NN, MOD, W><<<grid, block, smem, st>>>(K);
-  return cudaGetLastError();
-}
-
 template <int NN>
-static cudaError_t launch_nuts(int mod, int wide, int grid, int block, size_t smem, cudaStream_t st, const SamplerParams& K) {
-  if (wide) return mod == 0 ? launch_nuts_v<NN, 0, FOCT_WIDE>(grid, block, smem, st, K) : launch_nuts_v<NN, 1, FOCT_WIDE>(grid, block, smem, st, K);
-  return mod == 0 ? launch_nuts_v<NN, 0, 1>(grid, block, smem, st, K) : launch_nuts_v<NN, 1, 1>(grid, block, smem, st, K);
+static cudaError_t launch_nuts(int mod, int grid, int block, size_t smem, cudaStream_t st, const SamplerParams& K) {
+  cudaError_t e;
+  if (mod == 0) {
+    e = cudaFuncSetAttribute(nuts_kernel<NN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    nuts_kernel<NN, 0><<<grid, block, smem, st>>>(K);
+  } else {
+    e = cudaFuncSetAttribute(nuts_kernel<NN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    nuts_kernel<NN, 1><<<grid, block, smem, st>>>(K);
+  }
+  return cudaGetLastError();
 }
 
 template <int NN>
@@ -66,22 +66,25 @@ static cudaError_t launch_logp(int mod, int grid, int block, size_t smem, cudaSt
   return cudaGetLastError();
 }
 
-template <int NN, int MOD, int W>
-static cudaError_t nuts_occupancy_v(int block, size_t smem, int* blocks_per_sm, int* regs) {
+template <int NN>
+static cudaError_t nuts_occupancy(int mod, int block, size_t smem, int* blocks_per_sm, int* regs) {
   cudaFuncAttributes fa;
-  cudaError_t e = cudaFuncSetAttribute(nuts_kernel<NN, MOD, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, nuts_kernel<NN, MOD, W>, block, smem);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncGetAttributes(&fa, nuts_kernel<NN, MOD, W>);
+  cudaError_t e;
+  if (mod == 0) {
+    e = cudaFuncSetAttribute(nuts_kernel<NN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, nuts_kernel<NN, 0>, block, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&fa, nuts_kernel<NN, 0>);
+  } else {
+    e = cudaFuncSetAttribute(nuts_kernel<NN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, nuts_kernel<NN, 1>, block, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&fa, nuts_kernel<NN, 1>);
+  }
   if (e == cudaSuccess && regs) *regs = fa.numRegs;
   return e;
-}
-
-template <int NN>
-static cudaError_t nuts_occupancy(int mod, int wide, int block, size_t smem, int* blocks_per_sm, int* regs) {
-  if (wide) return mod == 0 ? nuts_occupancy_v<NN, 0, FOCT_WIDE>(block, smem, blocks_per_sm, regs) : nuts_occupancy_v<NN, 1, FOCT_WIDE>(block, smem, blocks_per_sm, regs);
-  return mod == 0 ? nuts_occupancy_v<NN, 0, 1>(block, smem, blocks_per_sm, regs) : nuts_occupancy_v<NN, 1, 1>(block, smem, blocks_per_sm, regs);
 }
 
 #define FOCT_CAT_(a, b) a##b

@@ -23,10 +23,9 @@ struct LogpParams {
 
 struct InstEntry {
   int NN;  // 0 = mono-exponential
-  // wide = 0: one warp per chain (throughput); wide = 1: FOCT_WIDE warps per chain (latency, small batches)
-  cudaError_t (*launch_nuts)(int mod, int wide, int grid, int block, size_t smem, cudaStream_t st, const SamplerParams& K);
+  cudaError_t (*launch_nuts)(int mod, int grid, int block, size_t smem, cudaStream_t st, const SamplerParams& K);
   cudaError_t (*launch_logp)(int mod, int grid, int block, size_t smem, cudaStream_t st, const LogpParams& K);
-  cudaError_t (*nuts_occupancy)(int mod, int wide, int block, size_t smem, int* blocks_per_sm, int* regs);
+  cudaError_t (*nuts_occupancy)(int mod, int block, size_t smem, int* blocks_per_sm, int* regs);
 };
 
 #define FOCT_DECL_INST(NN) const InstEntry* foct_inst_##NN();

@@ -7,7 +7,6 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -347,7 +346,7 @@ struct foct_plan {
   DevProblem* d_probs = nullptr;
   int* d_counter = nullptr;
   const InstEntry* inst = nullptr;
-  int grid = 0, block = 0, blocks_per_sm = 0, regs = 0, wide = 0;
+  int grid = 0, block = 0, blocks_per_sm = 0, regs = 0;
   size_t smem = 0;
   bool ran = false;
 };
@@ -593,7 +592,6 @@ static int validate_cfg(const foct_sampler_cfg* c) {
   if (c->chains < 1 || c->chains > FOCT_MAX_CHAINS) return fail(FOCT_EINVAL, "chains=%d outside 1..%d", c->chains, FOCT_MAX_CHAINS);
   if (c->n_warmup < 0 || c->n_iter < c->n_warmup || c->n_iter < 1) return fail(FOCT_EINVAL, "need 0 <= n_warmup <= n_iter, n_iter >= 1 (nb_iter = nb_warmup + nb_sample, FitOCT.R:121)");
   if (c->max_treedepth > FOCT_STACK_LEVELS + 1) return fail(FOCT_EINVAL, "max_treedepth=%d > %d", c->max_treedepth, FOCT_STACK_LEVELS + 1);
-  if (c->team_width != 0 && c->team_width != 1 && c->team_width != FOCT_WIDE) return fail(FOCT_EINVAL, "team_width must be 0 (auto), 1 or %d", FOCT_WIDE);
   if (c->init_mode < 0 || c->init_mode > 2 || (c->init_mode == 2 && !c->init)) return fail(FOCT_EINVAL, "bad init_mode / init");
   return 0;
 }
@@ -637,17 +635,14 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
     CUP(cudaMemcpy(p->d_init, init_slice, pc * p->D * sizeof(double), cudaMemcpyHostToDevice));
   }
   p->inst = inst_for(p->NN);
+  p->block = 32 * std::min(cfg->chains, FOCT_CTA_CHAINS);
+  p->smem = (p->blob_stride + (size_t)FOCT_SCRATCH_ROWS * p->npad) * sizeof(double);  // blob (+ scratch rows if FOCT_SPLIT)
+  CUP(p->inst->nuts_occupancy(spec->modulation, p->block, p->smem, &p->blocks_per_sm, &p->regs));
+  if (p->blocks_per_sm < 1) { plan_free(p); return fail(FOCT_EINVAL, "sampling kernel does not fit an SM (smem %zu B)", p->smem); }
   cudaDeviceProp prop;
   CUP(cudaGetDeviceProperties(&prop, device));
   const int groups = (cfg->chains + FOCT_CTA_CHAINS - 1) / FOCT_CTA_CHAINS;
-  const long long n_items = (long long)n * groups;
-  // batches that cannot give every SM a CTA run the wide variant: FOCT_WIDE warps per chain (latency mode)
-  p->wide = cfg->team_width == 0 ? (n_items <= prop.multiProcessorCount ? 1 : 0) : (cfg->team_width > 1 ? 1 : 0);
-  p->block = 32 * std::min(cfg->chains, FOCT_CTA_CHAINS) * (p->wide ? FOCT_WIDE : 1);
-  p->smem = (p->blob_stride + (size_t)FOCT_SCRATCH_ROWS * p->npad) * sizeof(double);  // blob (+ scratch rows if FOCT_SPLIT)
-  CUP(p->inst->nuts_occupancy(spec->modulation, p->wide, p->block, p->smem, &p->blocks_per_sm, &p->regs));
-  if (p->blocks_per_sm < 1) { plan_free(p); return fail(FOCT_EINVAL, "sampling kernel does not fit an SM (smem %zu B)", p->smem); }
-  p->grid = (int)std::min<long long>(n_items, (long long)prop.multiProcessorCount * p->blocks_per_sm);
+  p->grid = (int)std::min<long long>((long long)n * groups, (long long)prop.multiProcessorCount * p->blocks_per_sm);
 #undef CUP
   *out = p;
   return 0;
@@ -680,7 +675,7 @@ extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
   K.n_leapfrog = p->d_nleap; K.n_divergent = p->d_ndiv; K.work_counter = p->d_counter;
   CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), p->stream));
   CU(cudaEventRecord(p->ev0, p->stream));
-  CU(p->inst->launch_nuts(p->spec.modulation, p->wide, p->grid, p->block, p->smem, p->stream, K));
+  CU(p->inst->launch_nuts(p->spec.modulation, p->grid, p->block, p->smem, p->stream, K));
   CU(cudaEventRecord(p->ev1, p->stream));
   if (p->want_summary) {
     const int off = c.save_warmup ? c.n_warmup : 0;

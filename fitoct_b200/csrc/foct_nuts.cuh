@@ -63,20 +63,20 @@ __device__ __forceinline__ bool merge_persists(double invM, double i_rho, double
 #ifndef FOCT_LEAPFROG_INLINE
 #define FOCT_LEAPFROG_INLINE __forceinline__
 #endif
-template <int NN, int MOD, int W>
+template <int NN, int MOD>
 __device__ FOCT_LEAPFROG_INLINE void leapfrog(const double* __restrict__ blob, double* __restrict__ scr, const DevProblem* P, const DevSpec* S,
                                       double eps, double invM, double* zq, double* zp, double* zg, double* zV,
-                                      double* zc2, int lane, Team& team) {
+                                      double* zc2, int lane) {
   double p = fma(0.5 * eps, *zg, *zp);
   double q = fma(eps * invM, p, *zq);
-  const Eval ev = warp_logp_grad<NN, MOD, W>(blob, scr, *P, *S, q, lane, team);
+  const Eval ev = warp_logp_grad<NN, MOD>(blob, scr, *P, *S, q, lane);
   p = fma(0.5 * eps, ev.g, p);
   *zq = q; *zp = p; *zg = ev.g; *zV = -ev.lp; *zc2 = ev.chi2;
 }
 
-template <int NN, int MOD, int W>
+template <int NN, int MOD>
 __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const double* __restrict__ blob,
-                          double* __restrict__ scr, int prob, int chain, int lane, Team& team) {
+                          double* __restrict__ scr, int prob, int chain, int lane) {
   using DM = Dims<NN>;
   constexpr int D = DM::D;
   constexpr int P_OUT = DM::P_OUT;
@@ -100,8 +100,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       else q = 0.0;
     }
   }
-  Eval ev = warp_logp_grad<NN, MOD, W>(blob, scr, P, K.spec, q, lane, team);
-  const bool writer = W == 1 || team.w == 0;  // one warp of the team owns the write-back
+  Eval ev = warp_logp_grad<NN, MOD>(blob, scr, P, K.spec, q, lane);
   double g = ev.g, V = -ev.lp, c2 = ev.chi2;
   const double invM0 = 1.0;
   double invM = invM0;
@@ -144,7 +143,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       }
       ++attempt;
       const double H0 = zV + 0.5 * warp_sum(invM * zp * zp);
-      leapfrog<NN, MOD, W>(blob, scr, &P, &K.spec, eps, invM, &zq, &zp, &zg, &zV, &zc2, lane, team);
+      leapfrog<NN, MOD>(blob, scr, &P, &K.spec, eps, invM, &zq, &zp, &zg, &zV, &zc2, lane);
       double h = zV + 0.5 * warp_sum(invM * zp * zp);
       if (isnan(h)) h = CUDART_INF;
       const double dH = H0 - h;
@@ -192,7 +191,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       bool valid = true;
       const uint32_t n_leaves = 1u << depth;
       for (uint32_t n = 0; n < n_leaves; ++n) {
-        leapfrog<NN, MOD, W>(blob, scr, &P, &K.spec, eps_s, invM, &zq, &zp, &zg, &zV, &zc2, lane, team);
+        leapfrog<NN, MOD>(blob, scr, &P, &K.spec, eps_s, invM, &zq, &zp, &zg, &zV, &zc2, lane);
         ++n_leap;
         double h = zV + 0.5 * warp_sum(invM * zp * zp);
         if (isnan(h)) h = CUDART_INF;
@@ -249,7 +248,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
     const bool warm = it < K.n_warmup;
     if (warm) nlf_warm += n_leap; else { nlf_samp += n_leap; ndiv += divergent ? 1.0 : 0.0; }
     const int save_idx = K.save_warmup ? it : it - K.n_warmup;
-    if (save_idx >= 0 && writer) {
+    if (save_idx >= 0) {
       const size_t row = ((size_t)prob * n_saved + save_idx) * K.chains + chain;
       if (K.draws) {
         double v;
@@ -314,16 +313,15 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
     }
   }
   const size_t pc = (size_t)prob * K.chains + chain;
-  if (lane == 0 && writer) {
+  if (lane == 0) {
     if (K.stepsize) K.stepsize[pc] = eps;
     if (K.n_leapfrog) { K.n_leapfrog[pc * 2] = nlf_warm; K.n_leapfrog[pc * 2 + 1] = nlf_samp; }
     if (K.n_divergent) K.n_divergent[pc] = ndiv;
   }
-  if (K.inv_metric && act && writer) K.inv_metric[pc * D + lane] = invM;
+  if (K.inv_metric && act) K.inv_metric[pc * D + lane] = invM;
 }
 
-#define FOCT_WIDE 4  // warps per chain in the wide variant
-// Persistent CTAs of up to FOCT_CTA_CHAINS chains (x W warps each).  A work item is (profile, group of <= 4 chains); each CTA
+// Persistent CTAs of up to FOCT_CTA_CHAINS warps.  A work item is (profile, group of <= 4 chains); each CTA
 // repeatedly claims an item from the atomic work counter, stages the profile blob into shared memory with
 // one TMA bulk copy and runs its chains to completion.  Register budget follows the blob size: the more
 // control points, the fewer CTAs fit an SM by shared memory, the more registers each thread may use.
@@ -336,20 +334,13 @@ struct NutsBounds {
   static constexpr int MINB = NN <= 15 ? FOCT_MINB : 2;
 };
 
-template <int NN, int MOD, int W>
-__global__ void __launch_bounds__(32 * FOCT_CTA_CHAINS * W, W == 1 ? NutsBounds<NN>::MINB : 1) nuts_kernel(const SamplerParams K) {
+template <int NN, int MOD>
+__global__ void __launch_bounds__(32 * FOCT_CTA_CHAINS, NutsBounds<NN>::MINB) nuts_kernel(const SamplerParams K) {
   extern __shared__ __align__(128) double smem[];
   __shared__ uint64_t mbar;
   __shared__ int s_next;
   __shared__ DevProblem s_prob;
-  __shared__ double s_part[W > 1 ? FOCT_CTA_CHAINS * 2 * W * 32 : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chain_local = warp / W;
-  Team team;
-  team.w = warp % W;
-  team.part = s_part + (W > 1 ? chain_local * 2 * W * 32 : 0);
-  team.bar_id = 1 + chain_local;
-  team.parity = 0;
   const int groups = (K.chains + FOCT_CTA_CHAINS - 1) / FOCT_CTA_CHAINS;
   const int n_items = K.n_problems * groups;
   mbar_init(&mbar);
@@ -357,14 +348,13 @@ __global__ void __launch_bounds__(32 * FOCT_CTA_CHAINS * W, W == 1 ? NutsBounds<
   for (;;) {
     if (threadIdx.x == 0) s_next = atomicAdd(K.work_counter, 1);
     __syncthreads();
-    const int item = s_next;
-    if (item >= n_items) break;
-    const int j = item / groups, chain = (item % groups) * FOCT_CTA_CHAINS + chain_local;
+    const int w = s_next;
+    if (w >= n_items) break;
+    const int j = w / groups, chain = (w % groups) * FOCT_CTA_CHAINS + warp;
     if (threadIdx.x == 0) s_prob = K.probs[j];
     stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase);
     __syncthreads();
-    if (chain < K.chains)
-      run_chain<NN, MOD, W>(K, s_prob, smem, smem + K.blob_stride + (size_t)chain_local * K.npad, j, chain, lane, team);
+    if (chain < K.chains) run_chain<NN, MOD>(K, s_prob, smem, smem + K.blob_stride + (size_t)warp * K.npad, j, chain, lane);
     __syncthreads();
   }
 }

@@ -92,10 +92,6 @@ typedef struct foct_sampler_cfg {
   /* devices to shard profiles over (independent shards, no collective); n_devices == 0 => current device */
   int n_devices;
   const int* devices;
-  /* warps per chain: 1 = one warp per chain (throughput), 4 = a team of 4 warps per chain (latency, for batches too
-   * small to fill the GPU, e.g. the single-profile calls of FitOCT.R), 0 = choose by batch size.  Draws are
-   * bit-reproducible for a given (seed, profile id, team_width); the two widths sum in a different order. */
-  int team_width;
 } foct_sampler_cfg;
 
 /* Caller-allocated outputs; any pointer may be NULL to skip that output.
