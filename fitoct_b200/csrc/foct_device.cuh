@@ -26,6 +26,14 @@
 #define FOCT_STACK_LEVELS 12  // subtree depth <= max_treedepth - 1 <= 12
 
 namespace foct {
+#ifdef FOCT_TIMING
+__device__ unsigned long long g_tim[8];  // 0 grad total, 1 sweep loop, 2 reduce, 3 prologue, 4 leaf total, 5 merge, 6 leaves, 7 merges
+#define FOCT_T(var) const long long var = clock64()
+#define FOCT_TADD(i, a, b) do { if (lane == 0) atomicAdd(&g_tim[i], (unsigned long long)((b) - (a))); } while (0)
+#else
+#define FOCT_T(var)
+#define FOCT_TADD(i, a, b)
+#endif
 
 // Per-profile constants the kernels read from global memory (written by the setup kernel).
 struct DevProblem {
@@ -97,31 +105,41 @@ __host__ __device__ __forceinline__ size_t blob_index(int i, int r, int NN) {
 // 0.14 ulp approximation error; coefficients derived with mpmath).  Coefficients live in
 // constant memory so every DFMA takes its addend from the constant bank: no per-call constant
 // materialisation in the issue stream, which is what made the libdevice exp cost ~50 issue slots here.
-__constant__ double FEXP_C[10] = {
-    0x1.0000000000001p-1,  0x1.5555555555556p-3,  0x1.5555555553d63p-5,  0x1.11111111109b3p-7,
-    0x1.6c16c1788bd90p-10, 0x1.a01a01a7c41d5p-13, 0x1.a019b90d2ae7ap-16, 0x1.71de0dae63bb3p-19,
-    0x1.289185613a3d6p-22, 0x1.af38a9b0ec855p-26};
-__constant__ double FEXP_K[4] = {0x1.71547652b82fep+0 /* log2 e */, 6755399441055744.0 /* 1.5 * 2^52 */,
-                                 -0x1.62e42fefa39efp-1 /* -ln2 hi */, -0x1.abc9e3b39803fp-56 /* -ln2 lo */};
+// Coefficients are compile-time literals on purpose: ptxas then feeds them to DFMA as uniform/immediate operands
+// instead of parking them in 28 vector registers for the whole sweep (which is what a __constant__ array led to).
+#define FEXP_C0 0x1.0000000000001p-1
+#define FEXP_C1 0x1.5555555555556p-3
+#define FEXP_C2 0x1.5555555553d63p-5
+#define FEXP_C3 0x1.11111111109b3p-7
+#define FEXP_C4 0x1.6c16c1788bd90p-10
+#define FEXP_C5 0x1.a01a01a7c41d5p-13
+#define FEXP_C6 0x1.a019b90d2ae7ap-16
+#define FEXP_C7 0x1.71de0dae63bb3p-19
+#define FEXP_C8 0x1.289185613a3d6p-22
+#define FEXP_C9 0x1.af38a9b0ec855p-26
+#define FEXP_L2E 0x1.71547652b82fep+0     /* log2 e */
+#define FEXP_MAGIC 6755399441055744.0     /* 1.5 * 2^52 */
+#define FEXP_NLN2HI (-0x1.62e42fefa39efp-1)
+#define FEXP_NLN2LO (-0x1.abc9e3b39803fp-56)
 
 // Branch-free: |x| >= 700 saturates to 0 / +inf (exp(-700) ~ 1e-304 is below anything the model can resolve;
 // a positive argument that large only arises from a negative decay length, i.e. a state that is non-finite
 // anyway), NaN propagates.  Being branch-free lets ptxas interleave two points of the sweep.
 __device__ __forceinline__ double fexp(double x) {
-  const double t = fma(x, FEXP_K[0], FEXP_K[1]);
-  const double nd = t - FEXP_K[1];
+  const double t = fma(x, FEXP_L2E, FEXP_MAGIC);
+  const double nd = t - FEXP_MAGIC;
   const int n = __double2loint(t);
-  double r = fma(nd, FEXP_K[2], x);
-  r = fma(nd, FEXP_K[3], r);
+  double r = fma(nd, FEXP_NLN2HI, x);
+  r = fma(nd, FEXP_NLN2LO, r);
   // Estrin evaluation of 1 + r + r^2 (c0 + c1 r + ... + c9 r^9): depth 4 instead of 11 dependent DFMAs for
   // 3 extra multiplies (the sweep is latency-bound, not pipe-bound: profiles/r1_ncu_nuts_v2_summary.txt)
   const double r2 = r * r;
   const double q0 = 1.0 + r;
-  const double q1 = fma(FEXP_C[1], r, FEXP_C[0]);
-  const double q2 = fma(FEXP_C[3], r, FEXP_C[2]);
-  const double q3 = fma(FEXP_C[5], r, FEXP_C[4]);
-  const double q4 = fma(FEXP_C[7], r, FEXP_C[6]);
-  const double q5 = fma(FEXP_C[9], r, FEXP_C[8]);
+  const double q1 = fma(FEXP_C1, r, FEXP_C0);
+  const double q2 = fma(FEXP_C3, r, FEXP_C2);
+  const double q3 = fma(FEXP_C5, r, FEXP_C4);
+  const double q4 = fma(FEXP_C7, r, FEXP_C6);
+  const double q5 = fma(FEXP_C9, r, FEXP_C8);
   const double r4 = r2 * r2;
   const double s0 = fma(q1, r2, q0);
   const double s1 = fma(q3, r2, q2);
@@ -268,22 +286,22 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
   double x[U], tt[U], nd[U], rr[U], r2[U], r4[U], r8[U], q0[U], q1[U], q2[U], q3[U], q4[U], q5[U], e[U];
   int n[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) { x[u] = -t[u]; tt[u] = fma(x[u], FEXP_K[0], FEXP_K[1]); }
+  for (int u = 0; u < U; ++u) { x[u] = -t[u]; tt[u] = fma(x[u], FEXP_L2E, FEXP_MAGIC); }
 #pragma unroll
-  for (int u = 0; u < U; ++u) { nd[u] = tt[u] - FEXP_K[1]; n[u] = __double2loint(tt[u]); }
+  for (int u = 0; u < U; ++u) { nd[u] = tt[u] - FEXP_MAGIC; n[u] = __double2loint(tt[u]); }
 #pragma unroll
-  for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXP_K[2], x[u]);
+  for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXP_NLN2HI, x[u]);
 #pragma unroll
-  for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXP_K[3], rr[u]);
+  for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXP_NLN2LO, rr[u]);
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     r2[u] = rr[u] * rr[u];
     q0[u] = 1.0 + rr[u];
-    q1[u] = fma(FEXP_C[1], rr[u], FEXP_C[0]);
-    q2[u] = fma(FEXP_C[3], rr[u], FEXP_C[2]);
-    q3[u] = fma(FEXP_C[5], rr[u], FEXP_C[4]);
-    q4[u] = fma(FEXP_C[7], rr[u], FEXP_C[6]);
-    q5[u] = fma(FEXP_C[9], rr[u], FEXP_C[8]);
+    q1[u] = fma(FEXP_C1, rr[u], FEXP_C0);
+    q2[u] = fma(FEXP_C3, rr[u], FEXP_C2);
+    q3[u] = fma(FEXP_C5, rr[u], FEXP_C4);
+    q4[u] = fma(FEXP_C7, rr[u], FEXP_C6);
+    q5[u] = fma(FEXP_C9, rr[u], FEXP_C8);
   }
 #pragma unroll
   for (int u = 0; u < U; ++u) {
@@ -367,6 +385,7 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
 template <int NN, int MOD>
 __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, double* __restrict__ scratch,
                                                const DevProblem& P, const DevSpec& S, double qd, int lane) {
+  FOCT_T(t_g0);
   using DM = Dims<NN>;
   constexpr int D = DM::D;
   constexpr int KP = DM::KP;
@@ -388,6 +407,54 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
   const double sig = DM::GP ? fexp(qsig) : 1.0;
   const double isig = DM::GP ? fexp(-qsig) : 1.0;
 
+  // priors + Jacobians (O(D), evaluated redundantly by every lane; each lane keeps its own component).  Done BEFORE
+  // the sweep, while q is fresh in registers: only two doubles stay live across the loop (computed after it, this
+  // block cost 1460 cycles per leaf in register reloads - scripts/timing_probe.py).
+  double pr_lp = 0.0, pr_g = 0.0;
+  if (S.theta_prior == 0) {
+    const double d0 = th1 - P.theta0[0], d1 = th2 - P.theta0[1], d2 = th3 - P.theta0[2];
+    const double v0 = P.Pinv[0] * d0 + P.Pinv[1] * d1 + P.Pinv[2] * d2;
+    const double v1 = P.Pinv[3] * d0 + P.Pinv[4] * d1 + P.Pinv[5] * d2;
+    const double v2 = P.Pinv[6] * d0 + P.Pinv[7] * d1 + P.Pinv[8] * d2;
+    pr_lp += -0.5 * (d0 * v0 + d1 * v1 + d2 * v2);
+    if (lane == 0) pr_g -= v0;
+    if (lane == 1) pr_g -= v1;
+    if (lane == 2) pr_g -= v2;
+  }
+  if (DM::GP) {
+    double sy = 0.0;
+    if (S.ygp_prior == 0) {
+      const double il2 = fexp(-2.0 * qlam);
+#pragma unroll
+      for (int k = 0; k < NN; ++k) sy = fma(yg[k], yg[k], sy);
+      pr_lp += -(double)NN * qlam - 0.5 * sy * il2;
+      if (lane >= 3 && lane < 3 + NN) pr_g -= qd * il2;
+      if (lane == 3 + NN) pr_g += sy * il2 - (double)NN;
+    } else {
+      const double il = fexp(-qlam);
+#pragma unroll
+      for (int k = 0; k < NN; ++k) sy += fabs(yg[k]);
+      pr_lp += -(double)NN * qlam - sy * il;
+      if (lane >= 3 && lane < 3 + NN) pr_g -= (qd > 0.0 ? 1.0 : (qd < 0.0 ? -1.0 : 0.0)) * il;
+      if (lane == 3 + NN) pr_g += sy * il - (double)NN;
+    }
+    const double rl = P.lambda_rate * lam;
+    if (S.lambda_prior == 0) {
+      pr_lp += qlam - rl;
+      if (lane == 3 + NN) pr_g += 1.0 - rl;
+    } else {
+      pr_lp += -rl;
+      if (lane == 3 + NN) pr_g += -rl;
+    }
+    if (S.sigma_sd > 0.0) {
+      const double u = (sig - S.sigma_mean) * S.sigma_inv_sd;
+      pr_lp += -0.5 * u * u;
+      if (lane == 4 + NN) pr_g += -sig * u * S.sigma_inv_sd;
+    }
+    pr_lp += qlam + qsig;
+    if (lane == 3 + NN || lane == 4 + NN) pr_g += 1.0;
+  }
+
   double acc[KP];
 #pragma unroll
   for (int k = 0; k < KP; ++k) acc[k] = 0.0;
@@ -399,6 +466,8 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
     const double r3 = 1.0 / th3;
     constexpr int ROWS = 3 + NN;
     const double* pp = blob + lane;
+    FOCT_T(t_l0);
+    FOCT_TADD(3, t_g0, t_l0);
     int pass = 0;
     double* sq = scratch + lane;
     if (UNROLL >= 2) {
@@ -421,8 +490,12 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
       }
     }
     // sum z^2 travels in slot ZI: the log-sigma gradient slot for GP models, the last slot otherwise
+    FOCT_T(t_l1);
+    FOCT_TADD(1, t_l0, t_l1);
     const double red = warp_reduce_scatter<KP>(acc, lane);
     zz = bcast(red, ZI);
+    FOCT_T(t_l2);
+    FOCT_TADD(2, t_l1, t_l2);
     // scale the raw sums into gradient components
     double scale = 1.0;
     if (MOD == 0) {
@@ -443,50 +516,10 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
     out.chi2 = CUDART_NAN;
   }
 
-  // priors + Jacobians (O(D), evaluated redundantly by every lane; each lane keeps its own component)
-  if (S.theta_prior == 0) {
-    const double d0 = th1 - P.theta0[0], d1 = th2 - P.theta0[1], d2 = th3 - P.theta0[2];
-    const double v0 = P.Pinv[0] * d0 + P.Pinv[1] * d1 + P.Pinv[2] * d2;
-    const double v1 = P.Pinv[3] * d0 + P.Pinv[4] * d1 + P.Pinv[5] * d2;
-    const double v2 = P.Pinv[6] * d0 + P.Pinv[7] * d1 + P.Pinv[8] * d2;
-    out.lp += -0.5 * (d0 * v0 + d1 * v1 + d2 * v2);
-    if (lane == 0) out.g -= v0;
-    if (lane == 1) out.g -= v1;
-    if (lane == 2) out.g -= v2;
-  }
-  if (DM::GP) {
-    double sy = 0.0;
-    if (S.ygp_prior == 0) {
-      const double il2 = fexp(-2.0 * qlam);
-#pragma unroll
-      for (int k = 0; k < NN; ++k) sy = fma(yg[k], yg[k], sy);
-      out.lp += -(double)NN * qlam - 0.5 * sy * il2;
-      if (lane >= 3 && lane < 3 + NN) out.g -= qd * il2;
-      if (lane == 3 + NN) out.g += sy * il2 - (double)NN;
-    } else {
-      const double il = fexp(-qlam);
-#pragma unroll
-      for (int k = 0; k < NN; ++k) sy += fabs(yg[k]);
-      out.lp += -(double)NN * qlam - sy * il;
-      if (lane >= 3 && lane < 3 + NN) out.g -= (qd > 0.0 ? 1.0 : (qd < 0.0 ? -1.0 : 0.0)) * il;
-      if (lane == 3 + NN) out.g += sy * il - (double)NN;
-    }
-    const double rl = P.lambda_rate * lam;
-    if (S.lambda_prior == 0) {
-      out.lp += qlam - rl;
-      if (lane == 3 + NN) out.g += 1.0 - rl;
-    } else {
-      out.lp += -rl;
-      if (lane == 3 + NN) out.g += -rl;
-    }
-    if (S.sigma_sd > 0.0) {
-      const double u = (sig - S.sigma_mean) * S.sigma_inv_sd;
-      out.lp += -0.5 * u * u;
-      if (lane == 4 + NN) out.g += -sig * u * S.sigma_inv_sd;
-    }
-    out.lp += qlam + qsig;
-    if (lane == 3 + NN || lane == 4 + NN) out.g += 1.0;
-  }
+  out.lp += pr_lp;
+  out.g += pr_g;
+  FOCT_T(t_g1);
+  FOCT_TADD(0, t_g0, t_g1);
   return out;
 }
 

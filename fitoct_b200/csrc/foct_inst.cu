@@ -97,3 +97,11 @@ const InstEntry* FOCT_CAT(foct_inst_, FOCT_INST_NN)() {
 }
 
 }  // namespace foct
+
+#ifdef FOCT_TIMING
+extern "C" int foct_debug_timing(unsigned long long* out, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, foct::g_tim, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(foct::g_tim, z, sizeof(z)); }
+  return (int)e;
+}
+#endif

@@ -38,7 +38,7 @@ __device__ __forceinline__ double lse_prob(double a, double b, double& prob_b) {
   const double ad = fabs(d);
   const double e = fexp(-ad);
   double lse = fmax(a, b) + log1p(e);
-  prob_b = (d >= 0.0 ? 1.0 : e) / (1.0 + e);
+  prob_b = (d >= 0.0 ? 1.0 : e) * frcp(1.0 + e);  // 1 + e in [1, 2]: the branch-free reciprocal is exact enough
   if (!(ad >= 0.0)) { lse = -CUDART_INF; prob_b = 0.0; }  // both weights zero
   return lse;
 }
@@ -191,6 +191,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       bool valid = true;
       const uint32_t n_leaves = 1u << depth;
       for (uint32_t n = 0; n < n_leaves; ++n) {
+        FOCT_T(t_f0);
         leapfrog<NN, MOD>(blob, scr, &P, &K.spec, eps_s, invM, &zq, &zp, &zg, &zV, &zc2, lane);
         ++n_leap;
         double h = zV + 0.5 * warp_sum(invM * zp * zp);
@@ -201,6 +202,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
         c_lsw = dw; c_rho = zp; c_pbeg = zp; c_pend = zp; c_qp = zq; c_gp = zg; c_V = zV; c_c2 = zc2; c_H = h;
         if (divergent) { valid = false; break; }
         // merge completed siblings upward: bit k of n set  <=>  slot k holds the init half
+        FOCT_T(t_m0);
         int k = 0;
         int mb_group = -1;
         for (; (n >> k) & 1u; ++k) {
@@ -219,11 +221,18 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
           c_lsw = lsw_sub; c_rho = i_rho + c_rho; c_pbeg = i_pbeg;
           if (!persist) { valid = false; break; }
         }
+        FOCT_T(t_m1);
+        FOCT_TADD(5, t_m0, t_m1);
+#ifdef FOCT_TIMING
+        if (lane == 0) { atomicAdd(&g_tim[6], 1ull); atomicAdd(&g_tim[7], (unsigned long long)k); }
+#endif
         if (!valid) break;
         if (n + 1 < n_leaves) {
           st_rho[k] = c_rho; st_pbeg[k] = c_pbeg; st_pend[k] = c_pend; st_qp[k] = c_qp; st_gp[k] = c_gp;
           st_lsw[k] = c_lsw; st_V[k] = c_V; st_c2[k] = c_c2; st_H[k] = c_H;
         }
+        FOCT_T(t_f1);
+        FOCT_TADD(4, t_f0, t_f1);
       }
       if (fwd) { fq = zq; fp = zp; fg = zg; } else { bq = zq; bp = zp; bg = zg; }
       if (!valid) break;
