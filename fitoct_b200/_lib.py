@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libfitoct_b200.so")
 EXPORTS = (
     "foct_version", "foct_device_count", "foct_last_error", "foct_model_spec_default", "foct_sampler_cfg_default",
     "foct_dims", "foct_expgp_grid", "foct_expgp_basis", "foct_logp_grad", "foct_sample", "foct_expgp_sample",
-    "foct_monoexp_sample", "foct_monoexp_map", "foct_predict", "foct_plan_create", "foct_plan_run",
+    "foct_monoexp_sample", "foct_monoexp_map", "foct_expgp_map", "foct_predict", "foct_plan_create", "foct_plan_run",
     "foct_plan_sync", "foct_plan_timing", "foct_plan_fetch", "foct_plan_destroy", "foct_fp64_peak",
 )
 
@@ -57,6 +57,7 @@ def lib():
         for name in ("foct_expgp_sample", "foct_monoexp_sample"):
             getattr(L, name).argtypes = [PP, C.c_int, MS, SC, RS]
         L.foct_monoexp_map.argtypes = [PP, C.c_int, MS, dp, dp, dp, dp, ip]
+        L.foct_expgp_map.argtypes = [PP, C.c_int, MS, dp, dp, dp, ip]
         L.foct_predict.argtypes = [C.c_int, PP, MS, dp, C.c_int, dp, dp, dp]
         L.foct_plan_create.argtypes = [C.c_int, PP, C.c_int, MS, SC, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.foct_plan_run.argtypes = [C.c_void_p, C.c_ulonglong]
@@ -195,6 +196,19 @@ def monoexp_map(batch: abi.ProblemBatch, n_problems: int, spec: abi.ModelSpec, i
     check(lib().foct_monoexp_map(batch.array, n_problems, C.byref(spec), ip, abi.as_ptr(theta), abi.as_ptr(H),
                                  abi.as_ptr(br), st.ctypes.data_as(C.POINTER(C.c_int))))
     return theta, H, br, st
+
+
+def expgp_map(batch: abi.ProblemBatch, n_problems: int, spec: abi.ModelSpec, init=None, hessian=True):
+    """fitExpGP(method='optim'): par [n, Nn+7] (theta, yGP, lambda, sigma, br, lp), hessian [n, D, D], status [n]."""
+    Nn = batch.array[0].Nn
+    D, P_out = abi.dims(abi.FOCT_EXPGP, Nn)
+    par = np.empty((n_problems, P_out))
+    H = np.empty((n_problems, D, D)) if hessian else None
+    st = np.empty(n_problems, dtype=np.int32)
+    ip = abi.as_ptr(np.ascontiguousarray(init, dtype=np.float64)) if init is not None else abi.c_double_p()
+    check(lib().foct_expgp_map(batch.array, n_problems, C.byref(spec), ip, abi.as_ptr(par), abi.as_ptr(H),
+                               st.ctypes.data_as(C.POINTER(C.c_int))))
+    return par, H, st
 
 
 def predict(kind, batch, j, spec, draws):

@@ -139,10 +139,21 @@ def fitExpGP(x, y, uy, dataType=2, Nn=10, gridType="internal", method="sample", 
         raise ValueError("theta0 and Sigma0 are required (estimateExpPrior output, FitOCT.R:103-107)")
     if method not in ("sample", "optim", "vb"):
         raise ValueError("method must be one of 'sample', 'optim', 'vb' (FitOCT.R:42)")
-    if method != "sample":
-        raise NotImplementedError(f"method={method!r}: SURVEY §8(f) rows N1/N4 ('next'); only 'sample' is on the hot path")
+    if method == "vb":
+        raise NotImplementedError("method='vb': SURVEY §8(f) row N4 ('next'); 'sample' and 'optim' are implemented")
     spec = spec or abi.default_spec(abi.FOCT_EXPGP)
     control = control or {}
+    if method == "optim":
+        # MAP + Hessian (MODEL_SPEC §10): the Shiny default (ui.R:107-114); consumers plotExpGP.R:13-17, server.R:164-173
+        batch = abi.make_problems([_one_problem(x, y, uy, dataType, Nn, gridType, theta0, Sigma0, lambda_rate,
+                                                resolve_rho(rho_scale, Nn), prior_PD)])
+        q0 = None if init is None else np.ascontiguousarray(init, dtype=np.float64).reshape(1, Nn + 5)
+        par, H, st = L.expgp_map(batch, 1, spec, init=q0, hessian=True)
+        row = par[0]
+        m, resid, dl = L.predict(abi.FOCT_EXPGP, batch, 0, spec, row[None, :])
+        fit = dict(par=dict(theta=row[:3], yGP=row[3:3 + Nn], **{"lambda": row[3 + Nn]}, sigma=row[4 + Nn], br=row[5 + Nn],
+                            m=m[0], resid=resid[0], dL=dl[0]), value=row[6 + Nn], hessian=H[0], return_code=int(st[0]))
+        return dict(fit=fit, method=method, xGP=L.grid(Nn, _grid_code(gridType)), prior_PD=prior_PD)
     cfg = abi.default_cfg(chains=chains, n_warmup=int(nb_warmup), n_iter=int(nb_iter), seed=int(seed), save_warmup=1,
                           adapt_delta=float(control.get("adapt_delta", 0.8)),
                           max_treedepth=int(control.get("max_treedepth", 10)))

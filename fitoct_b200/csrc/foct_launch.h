@@ -21,11 +21,26 @@ struct LogpParams {
   double* chi2;  // [n_problems][n_q] or nullptr
 };
 
+struct MapParams {
+  const double* blobs;
+  size_t blob_stride;
+  int npad;
+  const DevProblem* probs;
+  int n_problems;
+  DevSpec spec;
+  const double* init;  // [n_problems][D] unconstrained or nullptr
+  double* par;         // [n_problems][P_out] constrained optimum + br + lp (no Jacobian)
+  double* hessian;     // [n_problems][D][D] of lp without Jacobian, or nullptr
+  int* status;         // [n_problems] 0 converged, 1 iteration limit, 2 line search failed
+  int max_iter;
+};
+
 struct InstEntry {
   int NN;  // 0 = mono-exponential
   cudaError_t (*launch_nuts)(int mod, int grid, int block, size_t smem, cudaStream_t st, const SamplerParams& K);
   cudaError_t (*launch_logp)(int mod, int grid, int block, size_t smem, cudaStream_t st, const LogpParams& K);
   cudaError_t (*nuts_occupancy)(int mod, int block, size_t smem, int* blocks_per_sm, int* regs);
+  cudaError_t (*launch_map)(int mod, int grid, size_t smem, cudaStream_t st, const MapParams& K);
 };
 
 #define FOCT_DECL_INST(NN) const InstEntry* foct_inst_##NN();

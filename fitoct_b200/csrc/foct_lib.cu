@@ -846,6 +846,46 @@ extern "C" int foct_monoexp_map(const foct_problem* P, int n, const foct_model_s
   return rc;
 }
 
+
+// ------------------------------------------------------------------ ABI: ExpGP MAP (method = 'optim')
+extern "C" int foct_expgp_map(const foct_problem* P, int n, const foct_model_spec* spec, const double* init,
+                              double* par, double* hessian, int* status) {
+  if (int rc = check_device()) return rc;
+  if (!par) return fail(FOCT_EINVAL, "NULL par output");
+  int dev = 0, NN, npad;
+  size_t stride;
+  double* d_blobs;
+  DevProblem* d_probs;
+  CU(cudaGetDevice(&dev));
+  if (int rc = build_device_batch(FOCT_EXPGP, P, n, spec, dev, 0, &NN, &npad, &stride, &d_blobs, &d_probs)) return rc;
+  const int D = NN + 5, P_out = NN + 7;
+  double *d_init = nullptr, *d_par = nullptr, *d_H = nullptr;
+  int* d_st = nullptr;
+  int rc = 0;
+  do {
+#define CUB(call) if ((call) != cudaSuccess) { rc = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); break; }
+    CUB(cudaMalloc(&d_par, (size_t)n * P_out * sizeof(double)));
+    CUB(cudaMalloc(&d_st, (size_t)n * sizeof(int)));
+    if (hessian) CUB(cudaMalloc(&d_H, (size_t)n * D * D * sizeof(double)));
+    if (init) {
+      CUB(cudaMalloc(&d_init, (size_t)n * D * sizeof(double)));
+      CUB(cudaMemcpy(d_init, init, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    MapParams K;
+    K.blobs = d_blobs; K.blob_stride = stride; K.npad = npad; K.probs = d_probs; K.n_problems = n;
+    K.spec = dev_spec(*spec); K.init = d_init; K.par = d_par; K.hessian = d_H; K.status = d_st; K.max_iter = 1000;
+    const InstEntry* inst = inst_for(NN);
+    CUB(inst->launch_map(spec->modulation, std::min(n, 148 * 4), stride * sizeof(double), 0, K));
+    CUB(cudaDeviceSynchronize());
+    CUB(cudaMemcpy(par, d_par, (size_t)n * P_out * sizeof(double), cudaMemcpyDeviceToHost));
+    if (hessian) CUB(cudaMemcpy(hessian, d_H, (size_t)n * D * D * sizeof(double), cudaMemcpyDeviceToHost));
+    if (status) CUB(cudaMemcpy(status, d_st, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+#undef CUB
+  } while (0);
+  cudaFree(d_init); cudaFree(d_par); cudaFree(d_H); cudaFree(d_st); cudaFree(d_blobs); cudaFree(d_probs);
+  return rc;
+}
+
 // ------------------------------------------------------------------ ABI: fp64 peak
 extern "C" int foct_fp64_peak(int device, double* tflops, double* sm_mhz) {
   if (int rc = check_device()) return rc;

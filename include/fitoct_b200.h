@@ -147,6 +147,15 @@ int foct_monoexp_map(const foct_problem* P, int n_problems, const foct_model_spe
                      const double* init /*[n][3] or NULL*/, double* theta, double* hessian, double* br,
                      int* status);
 
+/* MAP of fitExpGP: `method = 'optim'`, the Shiny default (ShinyInterface/ui.R:107-114; FitOCT.R:42; consumers
+ * plotExpGP.R:13-17 read fit$par$theta / yGP / lambda / sigma / br, server.R:164-173 reads fit$hessian).  BFGS on
+ * the unconstrained space without Jacobian terms (rstan::optimizing's default), then a finite-difference Hessian
+ * of lp.  par: [n][P_out] constrained optimum in the MODEL_SPEC §6 column order (last column: lp at the optimum);
+ * hessian: [n][D][D] (may be NULL); init: [n][D] unconstrained or NULL; status: 0 converged, 1 iteration limit,
+ * 2 line search failed. */
+int foct_expgp_map(const foct_problem* P, int n_problems, const foct_model_spec* spec, const double* init,
+                   double* par, double* hessian, int* status);
+
 /* Generated quantities for selected draws (SURVEY a-6): m, resid, dL at every depth.
  * draws: [n_draws][P_out] constrained rows of one problem; outputs [n_draws][N] (any may be NULL). */
 int foct_predict(int kind, const foct_problem* P, const foct_model_spec* spec, const double* draws,

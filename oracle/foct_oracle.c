@@ -1011,6 +1011,96 @@ int foct_oracle_summary(const double* draws, int n, int C, int P, double* out) {
   return 0;
 }
 
+
+/* ------------------------------------------------------------------ ExpGP MAP (MODEL_SPEC §10)
+ * BFGS on the unconstrained space without Jacobian terms (rstan::optimizing default, jacobian = FALSE), Armijo
+ * backtracking, then a central finite-difference Hessian of the gradient.  Consumers: plotExpGP.R:13-17,
+ * ShinyInterface/server.R:164-173. */
+static double map_obj(const model_t* M, const double* q, double* g, double* chi2) {
+  double lp = model_lpg(M, q, g, chi2, NULL);
+  double jl = 0.0;
+  if (M->kind == FOCT_EXPGP) {
+    jl = q[3 + M->Nn] + q[4 + M->Nn];
+    g[3 + M->Nn] -= 1.0; g[4 + M->Nn] -= 1.0;
+  }
+  for (int d = 0; d < M->D; ++d) g[d] = -g[d];
+  return -(lp - jl);
+}
+
+int foct_oracle_expgp_map(const foct_problem* P, int n_problems, const foct_model_spec* spec, const double* init,
+                          double* par, double* hessian, int* status) {
+  for (int j = 0; j < n_problems; ++j) {
+    model_t M;
+    int rc = model_init(&M, FOCT_EXPGP, &P[j], spec, NULL);
+    if (rc) return rc;
+    const int D = M.D, Nn = M.Nn, P_out = Nn + 7;
+    double q[MAXD], g[MAXD], h0[MAXD], H[MAXD][MAXD], chi2;
+    for (int d = 0; d < D; ++d) {
+      if (init) q[d] = init[(size_t)j * D + d];
+      else if (d < 3) q[d] = P[j].theta0[d];
+      else if (d < 3 + Nn) q[d] = 0.0;
+      else if (d == 3 + Nn) q[d] = log(0.1);
+      else q[d] = 0.0;
+      if (d < 3) h0[d] = spec->theta_prior == 0 ? 1.0 / M.Pinv[d * 4] : (d == 2 ? 100.0 : 1.0e4);
+      else if (d < 3 + Nn) h0[d] = 2.5e-3;
+      else if (d == 3 + Nn) h0[d] = 0.25;
+      else h0[d] = 0.01;
+    }
+    for (int a = 0; a < D; ++a) for (int b = 0; b < D; ++b) H[a][b] = a == b ? h0[a] : 0.0;
+    double f = map_obj(&M, q, g, &chi2);
+    int st = 1;
+    for (int it = 0; it < 1000; ++it) {
+      double dv[MAXD], slope = 0.0;
+      for (int a = 0; a < D; ++a) { double s = 0.0; for (int b = 0; b < D; ++b) s += H[a][b] * g[b]; dv[a] = -s; }
+      for (int a = 0; a < D; ++a) slope += g[a] * dv[a];
+      if (!(slope < 0.0)) {
+        for (int a = 0; a < D; ++a) for (int b = 0; b < D; ++b) H[a][b] = a == b ? h0[a] : 0.0;
+        slope = 0.0;
+        for (int a = 0; a < D; ++a) { dv[a] = -h0[a] * g[a]; slope += g[a] * dv[a]; }
+        if (!(slope < 0.0)) { st = 0; break; }
+      }
+      double step = 1.0, fn = 0.0, gn[MAXD], qn[MAXD], c2n = 0.0;
+      int ok = 0;
+      for (int ls = 0; ls < 40; ++ls) {
+        for (int a = 0; a < D; ++a) qn[a] = q[a] + step * dv[a];
+        fn = map_obj(&M, qn, gn, &c2n);
+        if (isfinite(fn) && fn <= f + 1e-4 * step * slope) { ok = 1; break; }
+        step *= 0.5;
+      }
+      if (!ok) { st = 2; break; }
+      double s[MAXD], y[MAXD], sy = 0.0, ss = 0.0, yy = 0.0;
+      for (int a = 0; a < D; ++a) { s[a] = qn[a] - q[a]; y[a] = gn[a] - g[a]; sy += s[a] * y[a]; ss += s[a] * s[a]; yy += y[a] * y[a]; }
+      double df = f - fn, fold = f;
+      memcpy(q, qn, sizeof(double) * D); memcpy(g, gn, sizeof(double) * D); chi2 = c2n; f = fn;
+      if (df <= 1e-13 * (fabs(fold) + 1.0)) { st = 0; break; }
+      if (sy > 1e-12 * sqrt(ss * yy)) {
+        double Hy[MAXD], yHy = 0.0;
+        for (int a = 0; a < D; ++a) { double t = 0.0; for (int b = 0; b < D; ++b) t += H[a][b] * y[b]; Hy[a] = t; }
+        for (int a = 0; a < D; ++a) yHy += y[a] * Hy[a];
+        double c1 = (sy + yHy) / (sy * sy), isy = 1.0 / sy;
+        for (int a = 0; a < D; ++a) for (int b = 0; b < D; ++b) H[a][b] = H[a][b] + c1 * s[a] * s[b] - (Hy[a] * s[b] + s[a] * Hy[b]) * isy;
+      }
+    }
+    double* row = par + (size_t)j * P_out;
+    for (int d = 0; d < 3 + Nn; ++d) row[d] = q[d];
+    row[3 + Nn] = exp(q[3 + Nn]); row[4 + Nn] = exp(q[4 + Nn]);
+    row[5 + Nn] = M.prior_PD ? NAN : chi2 / br_ndf(&M);
+    row[6 + Nn] = -f;
+    if (status) status[j] = st;
+    if (hessian) {
+      for (int c = 0; c < D; ++c) {
+        double h = 1e-5 * (fabs(q[c]) > 1.0 ? fabs(q[c]) : 1.0), qp[MAXD], qm[MAXD], gp[MAXD], gm[MAXD], cc;
+        memcpy(qp, q, sizeof(double) * D); memcpy(qm, q, sizeof(double) * D);
+        qp[c] += h; qm[c] -= h;
+        map_obj(&M, qp, gp, &cc); map_obj(&M, qm, gm, &cc);
+        for (int a = 0; a < D; ++a) hessian[((size_t)j * D + a) * D + c] = -(gp[a] - gm[a]) / (2.0 * h);
+      }
+    }
+    model_free(&M);
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------ MonoExp MAP (SURVEY a-12) */
 
 /* -lp, gradient and exact Hessian of -lp for the mono-exponential (sigma == 1). */

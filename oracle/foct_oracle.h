@@ -54,6 +54,9 @@ int foct_oracle_summary(const double* draws, int n_saved, int chains, int P, dou
 int foct_oracle_monoexp_map(const foct_problem* P, int n_problems, const foct_model_spec* spec,
                             const double* init, double* theta, double* hessian, double* br, int* status);
 
+int foct_oracle_expgp_map(const foct_problem* P, int n_problems, const foct_model_spec* spec, const double* init,
+                          double* par, double* hessian, int* status);
+
 int foct_oracle_predict(int kind, const foct_problem* P, const foct_model_spec* spec, const double* draws,
                         int n_draws, double* m, double* resid, double* dL);
 

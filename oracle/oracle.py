@@ -44,6 +44,7 @@ def lib():
         L.foct_oracle_summary.argtypes = [dp, C.c_int, C.c_int, C.c_int, dp]
         L.foct_oracle_monoexp_map.argtypes = [C.POINTER(abi.Problem), C.c_int, C.POINTER(abi.ModelSpec), dp, dp, dp,
                                               dp, ip]
+        L.foct_oracle_expgp_map.argtypes = [C.POINTER(abi.Problem), C.c_int, C.POINTER(abi.ModelSpec), dp, dp, dp, ip]
         L.foct_oracle_predict.argtypes = [C.c_int, C.POINTER(abi.Problem), C.POINTER(abi.ModelSpec), dp, C.c_int,
                                           dp, dp, dp]
         L.foct_oracle_normal.argtypes = [C.POINTER(C.c_uint32)]
@@ -150,6 +151,18 @@ def monoexp_map(batch: abi.ProblemBatch, n_problems, spec, init=None):
     _check(lib().foct_oracle_monoexp_map(batch.array, n_problems, C.byref(spec), ip, abi.as_ptr(theta), abi.as_ptr(H),
                                          abi.as_ptr(br), st.ctypes.data_as(C.POINTER(C.c_int))), "monoexp_map")
     return theta, H, br, st
+
+
+def expgp_map(batch: abi.ProblemBatch, n_problems, spec, init=None, hessian=True):
+    Nn = batch.array[0].Nn
+    D, P_out = abi.dims(abi.FOCT_EXPGP, Nn)
+    par = np.empty((n_problems, P_out))
+    H = np.empty((n_problems, D, D)) if hessian else None
+    st = np.empty(n_problems, dtype=np.int32)
+    ip = abi.as_ptr(np.ascontiguousarray(init, dtype=np.float64)) if init is not None else abi.c_double_p()
+    _check(lib().foct_oracle_expgp_map(batch.array, n_problems, C.byref(spec), ip, abi.as_ptr(par), abi.as_ptr(H),
+                                       st.ctypes.data_as(C.POINTER(C.c_int))), "expgp_map")
+    return par, H, st
 
 
 def predict(kind, batch, j, spec, draws):

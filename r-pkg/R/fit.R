@@ -38,7 +38,10 @@ fitExpGP <- function(x, y, uy, dataType = 2, Nn = 10, gridType = "internal", met
                      theta0 = NULL, Sigma0 = NULL, lambda_rate = 0.1, rho_scale = 0.1,
                      nb_warmup = 500, nb_iter = 1500, prior_PD = 0, open_progress = FALSE,
                      chains = 4, seed = sample.int(.Machine$integer.max, 1)) {
-  stopifnot(method == "sample")   # optim / vb: SURVEY 8(f) N1 / N4
+  stopifnot(method %in% c("sample", "optim"))   # vb: SURVEY 8(f) N4
+  if (method == "optim") {   # MAP + Hessian: foct_expgp_map (MODEL_SPEC 10); shim entry foct_R_expgp_map is analogous
+    stop("method='optim' is available through the C ABI (foct_expgp_map) and the Python mirror; add the 10-line shim foct_R_expgp_map when building the R package")
+  }
   ctl <- list(dataType = dataType, Nn = Nn, gridType = as.integer(gridType == "extremal"),
               rho = ifelse(rho_scale == 0, 1 / Nn, rho_scale), lambda_rate = lambda_rate,
               theta0 = as.numeric(theta0), Sigma0 = as.numeric(Sigma0), prior_PD = prior_PD,

@@ -280,3 +280,30 @@ def test_api_mirror_fitExpGP_and_fitMonoExp(L):
     assert sf.as_matrix(["theta", "yGP", "lambda", "sigma", "br", "lp__"]).shape == (400, 17)
     mono_s = api.fitMonoExp(x, S["Y"][0], S["UY"][0], method="sample", nb_warmup=100, nb_iter=200)
     assert mono_s["fit"].draws.shape == (200, 4, 5)
+
+
+def test_expgp_map_vs_oracle(L, O):
+    # method = 'optim' (SURVEY 8f N1): same BFGS iteration on both sides => same optimum, same Hessian
+    S = synth.make_profiles(6, modulated_only=True)
+    for Nn, mod in ((10, 0), (5, 1), (15, 0)):
+        b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=Nn)
+        spec = abi.default_spec(); spec.modulation = mod
+        par, H, st = L.expgp_map(b, 6, spec)
+        paro, Ho, sto = O.expgp_map(b, 6, spec)
+        assert np.all(st == 0) and np.all(sto == 0)
+        # the optimum is defined to ~sqrt(eps) of the curvature scale; compare in units of the Laplace sd
+        for j in range(6):
+            sd = np.sqrt(np.diag(np.linalg.inv(-0.5 * (Ho[j] + Ho[j].T))))
+            qg = np.concatenate([par[j, :3 + Nn], np.log(par[j, 3 + Nn:5 + Nn])])
+            qo = np.concatenate([paro[j, :3 + Nn], np.log(paro[j, 3 + Nn:5 + Nn])])
+            assert np.all(np.abs(qg - qo) < 1e-3 * sd), (Nn, j)
+            assert abs(par[j, 6 + Nn] - paro[j, 6 + Nn]) < 1e-8 * abs(paro[j, 6 + Nn])
+            np.testing.assert_allclose(par[j, 5 + Nn], paro[j, 5 + Nn], rtol=1e-5)
+            scale = np.sqrt(np.outer(np.abs(np.diag(Ho[j])), np.abs(np.diag(Ho[j]))))
+            assert np.all(np.abs(H[j] - Ho[j]) < 2e-3 * scale)   # basis built independently + finite differences
+    from fitoct_b200 import api
+    fit = api.fitExpGP(S["x"], S["Y"][0], S["UY"][0], Nn=10, method="optim", theta0=S["theta0"][0], Sigma0=S["Sigma0"][0],
+                       rho_scale=0)
+    assert fit["method"] == "optim" and fit["fit"]["return_code"] == 0
+    assert fit["fit"]["par"]["m"].shape == (481,) and fit["fit"]["par"]["yGP"].shape == (10,)   # plotExpGP.R:13-17
+    assert fit["fit"]["hessian"].shape == (15, 15)                                                # server.R:164-173

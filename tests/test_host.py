@@ -99,7 +99,7 @@ def test_fitExpGP_argument_errors():
     with pytest.raises(ValueError):
         api.fitExpGP(x, x, x, theta0=[1, 1, 1], Sigma0=np.eye(3), method="bogus")
     with pytest.raises(NotImplementedError):
-        api.fitExpGP(x, x, x, theta0=[1, 1, 1], Sigma0=np.eye(3), method="vb")
+        api.fitExpGP(x, x + 1, x, theta0=[1, 1, 1], Sigma0=np.eye(3), method="vb")
 
 
 def test_shard_ranges_partition_the_batch():

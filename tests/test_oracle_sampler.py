@@ -169,3 +169,27 @@ def test_expgp_parameter_recovery_and_rhat(O):
         # posterior-mean modulation tracks the sinc curve of synthData.R:21 within a loose band
         assert np.abs(dl.mean(axis=0) - truth)[40:].max() < 0.08
     assert out["n_divergent"].sum() <= 2
+
+
+def test_expgp_map_is_a_stationary_point(O):
+    # MODEL_SPEC §10: BFGS optimum of lp - Jacobian; gradient vanishes, Hessian negative definite and symmetric,
+    # and the mode sits inside the bulk of the NUTS posterior of the same profile
+    S = synth.make_profiles(3, modulated_only=True)
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=10)
+    spec = abi.default_spec()
+    par, H, st = O.expgp_map(b, 3, spec)
+    assert np.all(st == 0)
+    for j in range(3):
+        q = np.concatenate([par[j, :13], np.log(par[j, 13:15])])[None]
+        lp, g, c2 = O.logp_grad(0, b, j, spec, q)
+        gj = g[0].copy(); gj[13] -= 1; gj[14] -= 1
+        scale = np.sqrt(np.abs(np.diag(H[j])))            # natural gradient scale of each coordinate
+        assert np.all(np.abs(gj) / scale < 1e-3)
+        assert np.isclose(par[j, 16], lp[0] - q[0, 13] - q[0, 14], rtol=1e-14)
+        assert np.isclose(par[j, 15], c2[0] / (481 - 13), rtol=1e-12)
+        Hs = 0.5 * (H[j] + H[j].T)
+        assert np.abs(H[j] - H[j].T).max() < 1e-6 * np.abs(H[j]).max()
+        assert np.linalg.eigvalsh(Hs).max() < 0
+    out = O.sample(0, b, 1, spec, abi.default_cfg(n_warmup=300, n_iter=600, seed=8), n_threads=4)
+    s = out["summary"][0]
+    assert np.all(np.abs(par[0, :13] - s[:13, 0]) < 4 * s[:13, 2])
