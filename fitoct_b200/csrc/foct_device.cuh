@@ -15,14 +15,6 @@
 #include "../../include/fitoct_b200.h"
 
 #define FOCT_FULL 0xffffffffu
-// FOCT_SPLIT = 1 runs the basis-transpose accumulation as a second streaming loop over a per-warp scratch row
-// (lets ptxas interleave the dependency chains at 168 registers).  Measured SLOWER on B200 (1.67e8 vs 2.14e8
-// gradients/s: the doubled LDS traffic turns 'wait' stalls into short-scoreboard stalls,
-// profiles/r1_ncu_nuts_v3_split.txt), so it is off; kept as a documented experiment.
-#ifndef FOCT_SPLIT
-#define FOCT_SPLIT 0
-#endif
-#define FOCT_SCRATCH_ROWS (FOCT_SPLIT ? 4 : 0)  // per-warp scratch rows of npad doubles behind the blob
 #define FOCT_STACK_LEVELS 12  // subtree depth <= max_treedepth - 1 <= 12
 
 namespace foct {
@@ -229,12 +221,11 @@ struct Dims {
 // flight; two inlined copies of a one-point body were scheduled back to back — profiles/r1_ncu_nuts_v2).
 // Lane-private loads at compile-time offsets from pp, ~52 fp64 instructions per point, no branches.
 // Raw sums go to acc[] (theta2 / theta3 factors are applied once, after the reduction).
-template <int NN, int MOD, int KP, int ZI, int U, bool SPLIT>
-__device__ __forceinline__ void sweep_points(const double* __restrict__ pp, double* __restrict__ sq, double th1, double th2,
-                                             double th3, double r3, double isig, const double (&yg)[NN > 0 ? NN : 1],
-                                             double (&acc)[KP]) {
+template <int NN, int MOD, int KP, int ZI, int U>
+__device__ __forceinline__ void sweep_points(const double* __restrict__ pp, double th1, double th2, double th3, double r3,
+                                             double isig, const double (&yg)[NN > 0 ? NN : 1], double (&acc)[KP]) {
   constexpr int STRIDE = (3 + NN) * 32;
-  double b[SPLIT ? 1 : U][NN > 0 ? NN : 1];  // SPLIT: basis values are consumed by the dot product and not kept
+  double b[U][NN > 0 ? NN : 1];
   double dl0[U], dl1[U], s[U], cx[U], y[U], ws[U], r[U], t[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) { dl0[u] = 0.0; dl1[u] = 0.0; }
@@ -242,9 +233,8 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
   for (int k = 0; k < NN; ++k) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const double bv = pp[u * STRIDE + (3 + k) * 32];
-      if (!SPLIT) b[u][k] = bv;
-      if (k & 1) dl1[u] = fma(bv, yg[k], dl1[u]); else dl0[u] = fma(bv, yg[k], dl0[u]);
+      b[u][k] = pp[u * STRIDE + (3 + k) * 32];
+      if (k & 1) dl1[u] = fma(b[u][k], yg[k], dl1[u]); else dl0[u] = fma(b[u][k], yg[k], dl0[u]);
     }
   }
 #pragma unroll
@@ -338,15 +328,10 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
       acc[1] += ge[u];
       acc[2] = fma(qq[u], s[u], acc[2]);
     }
-    if (SPLIT) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) sq[u * 32] = qq[u];
-    } else {
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int k = 0; k < NN; ++k) acc[3 + k] = fma(qq[u], b[u][k], acc[3 + k]);
-    }
+      for (int k = 0; k < NN; ++k) acc[3 + k] = fma(qq[u], b[u][k], acc[3 + k]);
   } else {
     double es[U], m[U], z[U], gi[U], ge[U], ges[U];
 #pragma unroll
@@ -366,15 +351,10 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
       acc[1] += ges[u];
       acc[2] = fma(ges[u], t[u], acc[2]);
     }
-    if (SPLIT) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) sq[u * 32] = ge[u];
-    } else {
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int k = 0; k < NN; ++k) acc[3 + k] = fma(ge[u], b[u][k], acc[3 + k]);
-    }
+      for (int k = 0; k < NN; ++k) acc[3 + k] = fma(ge[u], b[u][k], acc[3 + k]);
   }
 }
 
@@ -383,8 +363,8 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
 // processes two passes (64 points per warp) per iteration so that two independent dependency chains are
 // in flight per warp (the fp64 pipe was latency-, not throughput-bound with one: profiles/r1_*v1*).
 template <int NN, int MOD>
-__device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, double* __restrict__ scratch,
-                                               const DevProblem& P, const DevSpec& S, double qd, int lane) {
+__device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, const DevProblem& P, const DevSpec& S,
+                                               double qd, int lane) {
   FOCT_T(t_g0);
   using DM = Dims<NN>;
   constexpr int D = DM::D;
@@ -393,10 +373,6 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
 #define FOCT_UNROLL 2
 #endif
   constexpr int UNROLL = NN <= 16 ? FOCT_UNROLL : 1;
-  // SPLIT: the basis-transpose accumulation (d/d yGP) runs as a second, register-light streaming loop over the
-  // per-point factor parked in a per-warp shared-memory scratch row; the first loop then no longer holds the
-  // basis row across exp(), which is what kept ptxas from interleaving the U dependency chains at 168 registers.
-  constexpr bool SPLIT = NN > 0 && FOCT_SPLIT != 0;
   const double th1 = bcast(qd, 0), th2 = bcast(qd, 1), th3 = bcast(qd, 2);
   double yg[NN > 0 ? NN : 1];
 #pragma unroll
@@ -469,27 +445,13 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
     FOCT_T(t_l0);
     FOCT_TADD(3, t_g0, t_l0);
     int pass = 0;
-    double* sq = scratch + lane;
     if (UNROLL >= 2) {
 #pragma unroll 1
-      for (; pass + UNROLL <= P.npass; pass += UNROLL, pp += UNROLL * ROWS * 32, sq += UNROLL * 32)
-        sweep_points<NN, MOD, KP, ZI, UNROLL, SPLIT>(pp, sq, th1, th2, th3, r3, isig, yg, acc);
+      for (; pass + UNROLL <= P.npass; pass += UNROLL, pp += UNROLL * ROWS * 32)
+        sweep_points<NN, MOD, KP, ZI, UNROLL>(pp, th1, th2, th3, r3, isig, yg, acc);
     }
 #pragma unroll 1
-    for (; pass < P.npass; ++pass, pp += ROWS * 32, sq += 32)
-      sweep_points<NN, MOD, KP, ZI, 1, SPLIT>(pp, sq, th1, th2, th3, r3, isig, yg, acc);
-    if (SPLIT) {
-      // every lane re-reads only what it wrote itself: no synchronisation needed
-      const double* pb = blob + lane + 3 * 32;
-      const double* sr = scratch + lane;
-#pragma unroll 2
-      for (int ps = 0; ps < P.npass; ++ps, pb += ROWS * 32, sr += 32) {
-        const double w = *sr;
-#pragma unroll
-        for (int k = 0; k < NN; ++k) acc[3 + k] = fma(w, pb[k * 32], acc[3 + k]);
-      }
-    }
-    // sum z^2 travels in slot ZI: the log-sigma gradient slot for GP models, the last slot otherwise
+    for (; pass < P.npass; ++pass, pp += ROWS * 32) sweep_points<NN, MOD, KP, ZI, 1>(pp, th1, th2, th3, r3, isig, yg, acc);
     FOCT_T(t_l1);
     FOCT_TADD(1, t_l0, t_l1);
     const double red = warp_reduce_scatter<KP>(acc, lane);

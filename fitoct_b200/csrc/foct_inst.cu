@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(128) logp_kernel(const LogpParams K) {
     for (int iq = warp; iq < K.n_q; iq += nwarp) {
       const size_t r = (size_t)j * K.n_q + iq;
       const double qd = lane < D ? K.q[r * D + lane] : 0.0;
-      const Eval ev = warp_logp_grad<NN, MOD>(smem, smem + K.blob_stride + (size_t)warp * K.npad, s_prob, K.spec, qd, lane);
+      const Eval ev = warp_logp_grad<NN, MOD>(smem, s_prob, K.spec, qd, lane);
       if (lane < D) K.grad[r * D + lane] = ev.g;
       if (lane == 0) {
         K.lp[r] = ev.lp;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(32) map_bfgs_kernel(const MapParams K) {
     // objective f = -(lp - Jacobian); jac_d = 1 on the log-lambda / log-sigma lanes
     const double jac = (DM::GP && (lane == 3 + NN || lane == 4 + NN)) ? 1.0 : 0.0;
     auto eval = [&](double qd, double& f, double& gd, double& chi2) {
-      const Eval ev = warp_logp_grad<NN, MOD>(smem, smem, P, K.spec, qd, lane);
+      const Eval ev = warp_logp_grad<NN, MOD>(smem, P, K.spec, qd, lane);
       const double jl = DM::GP ? bcast(qd, 3 + NN) + bcast(qd, 4 + NN) : 0.0;
       f = -(ev.lp - jl);
       gd = act ? -(ev.g - jac) : 0.0;

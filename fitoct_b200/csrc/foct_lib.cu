@@ -401,7 +401,7 @@ static int build_device_batch(int kind, const foct_problem* P, int n, const foct
   }
   const int npad = (maxN + 31) / 32 * 32;
   const size_t stride = (size_t)(3 + NN) * npad;
-  if ((stride + FOCT_SCRATCH_ROWS * (size_t)npad) * sizeof(double) > 220 * 1024) return fail(FOCT_EINVAL, "profile of %d points x %d control points does not fit shared memory", maxN, NN);
+  if (stride * sizeof(double) > 220 * 1024) return fail(FOCT_EINVAL, "profile of %d points x %d control points does not fit shared memory", maxN, NN);
 
   double* h_up = nullptr;
   HostMeta* h_meta = nullptr;
@@ -541,7 +541,7 @@ extern "C" int foct_logp_grad(int kind, const foct_problem* P, int n, const foct
     K.blobs = d_blobs; K.blob_stride = stride; K.npad = npad; K.probs = d_probs; K.n_problems = n;
     K.spec = dev_spec(*spec); K.q = d_q; K.n_q = n_q; K.lp = d_lp; K.grad = d_g; K.chi2 = d_c2;
     const InstEntry* inst = inst_for(NN);
-    CUB(inst->launch_logp(spec->modulation, std::min(n, 148 * 4), 128, (stride + FOCT_SCRATCH_ROWS * (size_t)npad) * sizeof(double), 0, K));
+    CUB(inst->launch_logp(spec->modulation, std::min(n, 148 * 4), 128, stride * sizeof(double), 0, K));
     CUB(cudaDeviceSynchronize());
     CUB(cudaMemcpy(lp, d_lp, nq * sizeof(double), cudaMemcpyDeviceToHost));
     CUB(cudaMemcpy(grad, d_g, nq * D * sizeof(double), cudaMemcpyDeviceToHost));
@@ -636,7 +636,7 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
   }
   p->inst = inst_for(p->NN);
   p->block = 32 * std::min(cfg->chains, FOCT_CTA_CHAINS);
-  p->smem = (p->blob_stride + (size_t)FOCT_SCRATCH_ROWS * p->npad) * sizeof(double);  // blob (+ scratch rows if FOCT_SPLIT)
+  p->smem = p->blob_stride * sizeof(double);
   CUP(p->inst->nuts_occupancy(spec->modulation, p->block, p->smem, &p->blocks_per_sm, &p->regs));
   if (p->blocks_per_sm < 1) { plan_free(p); return fail(FOCT_EINVAL, "sampling kernel does not fit an SM (smem %zu B)", p->smem); }
   cudaDeviceProp prop;

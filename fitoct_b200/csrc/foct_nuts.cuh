@@ -64,19 +64,19 @@ __device__ __forceinline__ bool merge_persists(double invM, double i_rho, double
 #define FOCT_LEAPFROG_INLINE __forceinline__
 #endif
 template <int NN, int MOD>
-__device__ FOCT_LEAPFROG_INLINE void leapfrog(const double* __restrict__ blob, double* __restrict__ scr, const DevProblem* P, const DevSpec* S,
+__device__ FOCT_LEAPFROG_INLINE void leapfrog(const double* __restrict__ blob, const DevProblem* P, const DevSpec* S,
                                       double eps, double invM, double* zq, double* zp, double* zg, double* zV,
                                       double* zc2, int lane) {
   double p = fma(0.5 * eps, *zg, *zp);
   double q = fma(eps * invM, p, *zq);
-  const Eval ev = warp_logp_grad<NN, MOD>(blob, scr, *P, *S, q, lane);
+  const Eval ev = warp_logp_grad<NN, MOD>(blob, *P, *S, q, lane);
   p = fma(0.5 * eps, ev.g, p);
   *zq = q; *zp = p; *zg = ev.g; *zV = -ev.lp; *zc2 = ev.chi2;
 }
 
 template <int NN, int MOD>
-__device__ void run_chain(const SamplerParams& K, const DevProblem& P, const double* __restrict__ blob,
-                          double* __restrict__ scr, int prob, int chain, int lane) {
+__device__ void run_chain(const SamplerParams& K, const DevProblem& P, const double* __restrict__ blob, int prob,
+                          int chain, int lane) {
   using DM = Dims<NN>;
   constexpr int D = DM::D;
   constexpr int P_OUT = DM::P_OUT;
@@ -100,7 +100,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       else q = 0.0;
     }
   }
-  Eval ev = warp_logp_grad<NN, MOD>(blob, scr, P, K.spec, q, lane);
+  Eval ev = warp_logp_grad<NN, MOD>(blob, P, K.spec, q, lane);
   double g = ev.g, V = -ev.lp, c2 = ev.chi2;
   const double invM0 = 1.0;
   double invM = invM0;
@@ -143,7 +143,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       }
       ++attempt;
       const double H0 = zV + 0.5 * warp_sum(invM * zp * zp);
-      leapfrog<NN, MOD>(blob, scr, &P, &K.spec, eps, invM, &zq, &zp, &zg, &zV, &zc2, lane);
+      leapfrog<NN, MOD>(blob, &P, &K.spec, eps, invM, &zq, &zp, &zg, &zV, &zc2, lane);
       double h = zV + 0.5 * warp_sum(invM * zp * zp);
       if (isnan(h)) h = CUDART_INF;
       const double dH = H0 - h;
@@ -192,7 +192,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       const uint32_t n_leaves = 1u << depth;
       for (uint32_t n = 0; n < n_leaves; ++n) {
         FOCT_T(t_f0);
-        leapfrog<NN, MOD>(blob, scr, &P, &K.spec, eps_s, invM, &zq, &zp, &zg, &zV, &zc2, lane);
+        leapfrog<NN, MOD>(blob, &P, &K.spec, eps_s, invM, &zq, &zp, &zg, &zV, &zc2, lane);
         ++n_leap;
         double h = zV + 0.5 * warp_sum(invM * zp * zp);
         if (isnan(h)) h = CUDART_INF;
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(32 * FOCT_CTA_CHAINS, NutsBounds<NN>::MINB) nu
     if (threadIdx.x == 0) s_prob = K.probs[j];
     stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase);
     __syncthreads();
-    if (chain < K.chains) run_chain<NN, MOD>(K, s_prob, smem, smem + K.blob_stride + (size_t)warp * K.npad, j, chain, lane);
+    if (chain < K.chains) run_chain<NN, MOD>(K, s_prob, smem, j, chain, lane);
     __syncthreads();
   }
 }
