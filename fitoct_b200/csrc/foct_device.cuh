@@ -223,7 +223,7 @@ struct Dims {
 // Raw sums go to acc[] (theta2 / theta3 factors are applied once, after the reduction).
 template <int NN, int MOD, int KP, int ZI, int U>
 __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, double th1, double th2, double th3, double r3,
-                                             double isig, const double (&yg)[NN > 0 ? NN : 1], double (&acc)[KP]) {
+                                             const double (&yg)[NN > 0 ? NN : 1], double (&acc)[KP]) {
   constexpr int STRIDE = (3 + NN) * 32;
   double b[U][NN > 0 ? NN : 1];
   double dl0[U], dl1[U], s[U], cx[U], y[U], ws[U], r[U], t[U];
@@ -242,7 +242,7 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
     s[u] = 1.0 + (dl0[u] + dl1[u]);
     cx[u] = pp[u * STRIDE];
     y[u] = pp[u * STRIDE + 32];
-    ws[u] = pp[u * STRIDE + 64] * isig;
+    ws[u] = pp[u * STRIDE + 64];  // 1/uy; the 1/sigma^2 common to every sum is applied once after the reduction
   }
   // reciprocal of the local decay length (length modulation with a GP); otherwise r3 is hoisted
   if (MOD == 0 && NN > 0) {
@@ -283,6 +283,17 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
   for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXP_NLN2HI, x[u]);
 #pragma unroll
   for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXP_NLN2LO, rr[u]);
+#ifdef FOCT_HORNER
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    double p = FEXP_C9;
+    p = fma(p, rr[u], FEXP_C8); p = fma(p, rr[u], FEXP_C7); p = fma(p, rr[u], FEXP_C6); p = fma(p, rr[u], FEXP_C5);
+    p = fma(p, rr[u], FEXP_C4); p = fma(p, rr[u], FEXP_C3); p = fma(p, rr[u], FEXP_C2); p = fma(p, rr[u], FEXP_C1);
+    p = fma(p, rr[u], FEXP_C0); p = fma(p, rr[u], 1.0);
+    q0[u] = fma(p, rr[u], 1.0);
+    q4[u] = 0.0; r8[u] = 0.0; (void)q1; (void)q2; (void)q3; (void)q5; (void)r2; (void)r4;
+  }
+#else
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     r2[u] = rr[u] * rr[u];
@@ -302,6 +313,7 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
   }
 #pragma unroll
   for (int u = 0; u < U; ++u) { r8[u] = r4[u] * r4[u]; q0[u] = fma(q2[u], r4[u], q0[u]); }
+#endif
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const double p = fma(q4[u], r8[u], q0[u]);
@@ -381,7 +393,8 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
   const double qsig = DM::GP ? bcast(qd, 4 + NN) : 0.0;
   const double lam = DM::GP ? fexp(qlam) : 1.0;
   const double sig = DM::GP ? fexp(qsig) : 1.0;
-  const double isig = DM::GP ? fexp(-qsig) : 1.0;
+  const double isig = DM::GP ? frcp(sig) : 1.0;
+  const double isig2 = isig * isig;
 
   // priors + Jacobians (O(D), evaluated redundantly by every lane; each lane keeps its own component).  Done BEFORE
   // the sweep, while q is fresh in registers: only two doubles stay live across the loop (computed after it, this
@@ -400,14 +413,15 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
   if (DM::GP) {
     double sy = 0.0;
     if (S.ygp_prior == 0) {
-      const double il2 = fexp(-2.0 * qlam);
+      const double il1 = frcp(lam);
+      const double il2 = il1 * il1;
 #pragma unroll
       for (int k = 0; k < NN; ++k) sy = fma(yg[k], yg[k], sy);
       pr_lp += -(double)NN * qlam - 0.5 * sy * il2;
       if (lane >= 3 && lane < 3 + NN) pr_g -= qd * il2;
       if (lane == 3 + NN) pr_g += sy * il2 - (double)NN;
     } else {
-      const double il = fexp(-qlam);
+      const double il = frcp(lam);
 #pragma unroll
       for (int k = 0; k < NN; ++k) sy += fabs(yg[k]);
       pr_lp += -(double)NN * qlam - sy * il;
@@ -448,13 +462,13 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
     if (UNROLL >= 2) {
 #pragma unroll 1
       for (; pass + UNROLL <= P.npass; pass += UNROLL, pp += UNROLL * ROWS * 32)
-        sweep_points<NN, MOD, KP, ZI, UNROLL>(pp, th1, th2, th3, r3, isig, yg, acc);
+        sweep_points<NN, MOD, KP, ZI, UNROLL>(pp, th1, th2, th3, r3, yg, acc);
     }
 #pragma unroll 1
-    for (; pass < P.npass; ++pass, pp += ROWS * 32) sweep_points<NN, MOD, KP, ZI, 1>(pp, th1, th2, th3, r3, isig, yg, acc);
+    for (; pass < P.npass; ++pass, pp += ROWS * 32) sweep_points<NN, MOD, KP, ZI, 1>(pp, th1, th2, th3, r3, yg, acc);
     FOCT_T(t_l1);
     FOCT_TADD(1, t_l0, t_l1);
-    const double red = warp_reduce_scatter<KP>(acc, lane);
+    const double red = warp_reduce_scatter<KP>(acc, lane) * isig2;  // every sum carries the factor 1/sigma^2
     zz = bcast(red, ZI);
     FOCT_T(t_l2);
     FOCT_TADD(2, t_l1, t_l2);
@@ -471,7 +485,7 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
     if (DM::GP && lane == 4 + NN) out.g = zz - (double)P.N;
     if (lane >= D) out.g = 0.0;
     out.lp = -0.5 * zz - (double)P.N * qsig - P.sum_log_uy;
-    out.chi2 = zz * sig * sig;
+    out.chi2 = zz * sig * sig;  // = sum ((y-m)/uy)^2
   } else {
     out.g = 0.0;
     out.lp = 0.0;
