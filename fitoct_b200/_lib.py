@@ -108,8 +108,8 @@ def logp_grad(kind: int, batch: abi.ProblemBatch, n_problems: int, spec: abi.Mod
 
 def alloc_result(kind, n_problems, Nn, cfg: abi.SamplerCfg, draws=True, summary=True):
     D, P_out = abi.dims(kind, Nn)
-    n_saved = cfg.n_iter if cfg.save_warmup else cfg.n_iter - cfg.n_warmup
-    Cn = cfg.chains
+    n_saved = max(0, cfg.n_iter if cfg.save_warmup else cfg.n_iter - cfg.n_warmup)  # the library validates the cfg
+    Cn = max(0, cfg.chains)
     out = dict(
         draws=np.full((n_problems, n_saved, Cn, P_out), np.nan) if draws else None,
         sampler_params=np.full((n_problems, n_saved, Cn, 6), np.nan) if draws else None,

@@ -677,7 +677,7 @@ extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
   CU(cudaEventRecord(p->ev0, p->stream));
   CU(p->inst->launch_nuts(p->spec.modulation, p->grid, p->block, p->smem, p->stream, K));
   CU(cudaEventRecord(p->ev1, p->stream));
-  if (p->want_summary) {
+  if (p->want_summary && p->n_post >= 2) {
     const int off = c.save_warmup ? c.n_warmup : 0;
     CU(launch_summary(p->d_draws, p->n, p->n_saved, off, p->n_post, c.chains, p->P_out, p->d_summary, p->stream));
   }
@@ -720,17 +720,19 @@ extern "C" int foct_plan_fetch(foct_plan* p, foct_result* R) {
   CU(cudaSetDevice(p->device));
   CU(cudaStreamSynchronize(p->stream));
   const size_t pc = (size_t)p->n * p->cfg.chains;
-  if (R->draws) {
+  if (R->draws && p->n_saved > 0) {
     if (!p->want_draws) return fail(FOCT_EINVAL, "plan was created without draws");
     CU(cudaMemcpy(R->draws, p->d_draws, pc * p->n_saved * p->P_out * sizeof(double), cudaMemcpyDeviceToHost));
   }
-  if (R->sampler_params) {
-    if (!p->d_sparams) return fail(FOCT_EINVAL, "plan was created without draws");
+  if (R->sampler_params && p->n_saved > 0) {
+    if (!p->want_draws) return fail(FOCT_EINVAL, "plan was created without draws");
     CU(cudaMemcpy(R->sampler_params, p->d_sparams, pc * p->n_saved * 6 * sizeof(double), cudaMemcpyDeviceToHost));
   }
   if (R->summary) {
     if (!p->want_summary) return fail(FOCT_EINVAL, "plan was created without summary");
-    CU(cudaMemcpy(R->summary, p->d_summary, (size_t)p->n * p->P_out * FOCT_N_SUMMARY_COLS * sizeof(double), cudaMemcpyDeviceToHost));
+    const size_t ns = (size_t)p->n * p->P_out * FOCT_N_SUMMARY_COLS;
+    if (p->n_post >= 2) CU(cudaMemcpy(R->summary, p->d_summary, ns * sizeof(double), cudaMemcpyDeviceToHost));
+    else for (size_t i = 0; i < ns; ++i) R->summary[i] = std::nan("");  // fewer than two post-warm-up draws: nothing to summarise
   }
   if (R->stepsize) CU(cudaMemcpy(R->stepsize, p->d_stepsize, pc * sizeof(double), cudaMemcpyDeviceToHost));
   if (R->inv_metric) CU(cudaMemcpy(R->inv_metric, p->d_invm, pc * p->D * sizeof(double), cudaMemcpyDeviceToHost));

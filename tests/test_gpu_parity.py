@@ -307,3 +307,60 @@ def test_expgp_map_vs_oracle(L, O):
     assert fit["method"] == "optim" and fit["fit"]["return_code"] == 0
     assert fit["fit"]["par"]["m"].shape == (481,) and fit["fit"]["par"]["yGP"].shape == (10,)   # plotExpGP.R:13-17
     assert fit["fit"]["hessian"].shape == (15, 15)                                                # server.R:164-173
+
+
+def test_size_edges(L, O):
+    rng = np.random.default_rng(11)
+    # long profile (N = 1500 > 32 * 46), few control points; tiny profile at the N >= Nn + 4 limit; widest model Nn = 25
+    x = np.linspace(5.0, 900.0, 1500)
+    y = 900 + 1800 * np.exp(-2 * x / 280.0) + rng.standard_normal(1500) * 3
+    uy = np.full(1500, 3.0)
+    th0 = np.array([900.0, 1800.0, 280.0]); S0 = np.diag((0.05 * th0) ** 2)
+    cases = [dict(x=x, y=y, uy=uy, Nn=5, rho=0.2, theta0=th0, Sigma0=S0, id=0),
+             dict(x=x[:9], y=y[:9], uy=uy[:9], Nn=5, rho=0.2, theta0=th0, Sigma0=S0, id=1),
+             dict(x=x[:200], y=y[:200], uy=uy[:200], Nn=25, rho=0.05, theta0=th0, Sigma0=S0, id=2)]
+    for c in cases:
+        b = abi.make_problems([c])
+        Nn = c["Nn"]
+        q = rand_q(rng, th0, Nn, 3)[None]
+        lp, g, chi2 = L.logp_grad(0, b, 1, abi.default_spec(), q)
+        lpo, go, c2o, at = O.logp_grad(0, b, 0, abi.default_spec(), q[0], B=L.basis(b, 0, abi.default_spec()), want_abs=True)
+        assert np.all(np.abs(lp[0] - lpo) <= RTOL * np.abs(lpo))
+        assert grad_tol_ok(g[0], go, at, RTOL)
+        cfg = abi.default_cfg(n_warmup=20, n_iter=30, seed=4, save_warmup=1, chains=2)
+        out = L.sample(0, b, 1, abi.default_spec(), cfg)
+        ref = O.sample(0, b, 1, abi.default_spec(), cfg)
+        np.testing.assert_array_equal(out["sampler_params"][:, :4, :, 2:5], ref["sampler_params"][:, :4, :, 2:5])
+    # too large for shared memory, too few points for the parameter count: refused, not truncated
+    big = dict(x=np.linspace(1, 2, 5000), y=np.ones(5000), uy=np.ones(5000), Nn=10, theta0=th0, Sigma0=S0)
+    with pytest.raises(L.FitOCTError, match="shared memory"):
+        L.logp_grad(0, abi.make_problems([big]), 1, abi.default_spec(), np.zeros((1, 1, 15)))
+    few = dict(x=x[:8], y=y[:8], uy=uy[:8], Nn=5, theta0=th0, Sigma0=S0)
+    with pytest.raises(L.FitOCTError, match="too small"):
+        L.logp_grad(0, abi.make_problems([few]), 1, abi.default_spec(), np.zeros((1, 1, 10)))
+
+
+def test_sampler_cfg_edges(L, O):
+    S = synth.make_profiles(1, modulated_only=True)
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=10)
+    spec = abi.default_spec()
+    # no warm-up at all: fixed step size, unit metric, same trees as the oracle
+    cfg = abi.default_cfg(n_warmup=0, n_iter=12, seed=3, stepsize0=0.01)
+    out = L.sample(0, b, 1, spec, cfg); ref = O.sample(0, b, 1, spec, cfg)
+    assert np.all(out["inv_metric"] == 1.0) and np.all(out["stepsize"] == 0.01)
+    np.testing.assert_array_equal(out["sampler_params"][..., 2:5][:, :6], ref["sampler_params"][..., 2:5][:, :6])
+    # only warm-up iterations requested: no draws, summary is NaN, nothing crashes
+    cfg = abi.default_cfg(n_warmup=25, n_iter=25, seed=3)
+    out = L.sample(0, b, 1, spec, cfg)
+    assert out["draws"].shape[1] == 0 and np.all(np.isnan(out["summary"]))
+    assert np.all(out["n_leapfrog"][..., 0] > 0) and np.all(out["n_leapfrog"][..., 1] == 0)
+    # max_treedepth is honoured and validated
+    cfg = abi.default_cfg(n_warmup=10, n_iter=20, seed=3, max_treedepth=3, save_warmup=1)
+    out = L.sample(0, b, 1, spec, cfg)
+    assert out["sampler_params"][..., 2].max() <= 3 and out["sampler_params"][..., 3].max() <= 15
+    for bad in (dict(chains=9), dict(chains=0), dict(n_warmup=30, n_iter=20), dict(max_treedepth=14), dict(init_mode=2)):
+        with pytest.raises(L.FitOCTError):
+            L.sample(0, b, 1, spec, abi.default_cfg(**{**dict(n_warmup=5, n_iter=10), **bad}))
+    # Stan's default random inits U(-2,2) are representable too (init_mode = 1): the chain must not produce NaN draws
+    out = L.sample(0, b, 1, spec, abi.default_cfg(n_warmup=30, n_iter=40, seed=3, init_mode=1))
+    assert np.isfinite(out["draws"][..., :15]).all()
