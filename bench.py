@@ -55,6 +55,29 @@ def min_ess_sum(summary, Nn):
     return float(np.nansum(np.nanmin(be, axis=1)))
 
 
+def host_cores() -> int:
+    """Cores this process may really use: affinity mask capped by the cgroup CPU quota (torchrun also exports
+    OMP_NUM_THREADS=1, so the thread count is always passed to the oracle explicitly)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p_ = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, int(q / p_ + 0.5)))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 class ClockSampler:
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -99,9 +122,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import oracle as O
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     chains = 4
-    n = max(1, min(args.profiles, (cores // chains) * args.cpu_waves))
+    n = max(1, min(args.profiles, max(1, cores // chains) * args.cpu_waves))
     _, b = make_batch(n, 0, args.nn)
     spec = abi.default_spec()
     cfg = abi.default_cfg(n_warmup=args.n_warmup, n_iter=args.n_iter, seed=args.seed, chains=chains)
@@ -109,7 +132,7 @@ def run_reference(args, rank, world):
     for s in range(args.warmup + args.steps):
         cfg.seed = args.seed + s
         t0 = time.perf_counter()
-        out = O.sample(abi.FOCT_EXPGP, b, n, spec, cfg, draws=True, summary=True)
+        out = O.sample(abi.FOCT_EXPGP, b, n, spec, cfg, draws=True, summary=True, n_threads=cores)
         dt = time.perf_counter() - t0
         threads = out["threads"]
         if s >= args.warmup:
@@ -124,7 +147,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic (synthData.R-shaped)", "draws_per_s": dps,
-        "config": workload_config(args, n),
+        "config": dict(workload_config(args, args.profiles), cpu_sample_profiles=n),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "draws_per_s": dps,
                          "note": "CPU restatement (Stan algorithm, analytic gradient) - not rstan (R absent, BASELINE.md s3)"},
@@ -152,7 +175,7 @@ def main():
     ap.add_argument("--n-warmup", type=int, default=500)
     ap.add_argument("--n-iter", type=int, default=1500)
     ap.add_argument("--seed", type=int, default=1234)
-    ap.add_argument("--cpu-waves", type=int, default=4, help="CPU sample = cores/4 * waves profiles")
+    ap.add_argument("--cpu-waves", type=int, default=2, help="CPU sample = cores/4 * waves profiles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -270,11 +293,11 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
-        cores = os.cpu_count() or 1
-        nc = max(1, min(n, (cores // chains) * args.cpu_waves))
+        cores = host_cores()
+        nc = max(1, min(n, max(1, cores // chains) * args.cpu_waves))
         _, bc = make_batch(nc, 0, args.nn)
         t0 = time.perf_counter()
-        oc = O.sample(abi.FOCT_EXPGP, bc, nc, spec, cfg, draws=True, summary=True)
+        oc = O.sample(abi.FOCT_EXPGP, bc, nc, spec, cfg, draws=True, summary=True, n_threads=cores)
         dt = time.perf_counter() - t0
         cpu = {"value": min_ess_sum(oc["summary"], args.nn) / dt, "unit": UNIT, "cores": oc["threads"], "kind": "port",
                "sample": f"{nc} of {n} profiles x {chains} chains, full {args.n_warmup}/{n_post} iterations, {dt:.1f} s",
