@@ -744,7 +744,7 @@ extern "C" int foct_plan_fetch(foct_plan* p, foct_result* R) {
 extern "C" void foct_plan_destroy(foct_plan* p) { plan_free(p); }
 
 // ------------------------------------------------------------------ ABI: one-shot sampling, sharded over devices
-static int sample_shard(int device, int kind, const foct_problem* P, int first, int n, const foct_model_spec* spec,
+static int sample_chunk(int device, int kind, const foct_problem* P, int first, int n, const foct_model_spec* spec,
                         const foct_sampler_cfg* cfg, foct_result* R, int D, int P_out) {
   const int C = cfg->chains;
   const int n_saved = cfg->save_warmup ? cfg->n_iter : cfg->n_iter - cfg->n_warmup;
@@ -763,11 +763,30 @@ static int sample_shard(int device, int kind, const foct_problem* P, int first, 
     if (S.inv_metric) S.inv_metric += pc0 * D;
     if (S.n_leapfrog) S.n_leapfrog += pc0 * 2;
     if (S.n_divergent) S.n_divergent += pc0;
-    if (S.sampler_params && !S.draws) { /* plan allocated both; fetch copes */ }
     rc = foct_plan_fetch(p, &S);
   }
   plan_free(p);
   return rc;
+}
+
+// One device's shard, processed in chunks so that the device-resident draws (needed by the summary kernel even
+// when the caller wants summaries only: n x chains x n_saved x P_out doubles) stay below a memory budget —
+// 1e5 profiles are 54 GB of draws; 1e6 would not fit 180 GB.  Chunks are whole multiples of the
+// resident CTA count where possible, so chunking does not add partial waves.
+static int sample_shard(int device, int kind, const foct_problem* P, int first, int n, const foct_model_spec* spec,
+                        const foct_sampler_cfg* cfg, foct_result* R, int D, int P_out) {
+  const int n_saved = cfg->save_warmup ? cfg->n_iter : cfg->n_iter - cfg->n_warmup;
+  const double per_profile = (double)cfg->chains * std::max(1, n_saved) * (P_out + 6) * sizeof(double);
+  double budget = 48.0 * 1024 * 1024 * 1024;
+  if (const char* env = std::getenv("FOCT_DRAW_BUDGET_MB")) budget = std::atof(env) * 1024 * 1024;
+  long long chunk = (long long)(budget / per_profile);
+  if (chunk >= 444 * 2) chunk -= chunk % 444;
+  chunk = std::max<long long>(1, std::min<long long>(chunk, n));
+  for (int off = 0; off < n; off += (int)chunk) {
+    const int m = (int)std::min<long long>(chunk, n - off);
+    if (int rc = sample_chunk(device, kind, P, first + off, m, spec, cfg, R, D, P_out)) return rc;
+  }
+  return 0;
 }
 
 extern "C" int foct_sample(int kind, const foct_problem* P, int n, const foct_model_spec* spec,

@@ -232,6 +232,15 @@ def test_shard_invariance_and_determinism(L):
     np.testing.assert_array_equal(part["draws"][0], full["draws"][4])
     np.testing.assert_array_equal(part["draws"][1], full["draws"][1])
     np.testing.assert_array_equal(part["summary"][1], full["summary"][1])
+    # chunked processing under a tiny device-memory budget for the draws gives the same bits
+    import os
+    os.environ["FOCT_DRAW_BUDGET_MB"] = "0.06"   # 2 profiles (40 draws x 4 chains x 23 doubles each) per chunk
+    try:
+        chunked = L.sample(0, b, 6, abi.default_spec(), cfg)
+    finally:
+        del os.environ["FOCT_DRAW_BUDGET_MB"]
+    np.testing.assert_array_equal(chunked["draws"], full["draws"])
+    np.testing.assert_array_equal(chunked["summary"], full["summary"])
     if L.device_count() >= 2:
         two = L.sample(0, b, 6, abi.default_spec(), cfg, devices=[0, 1])
         np.testing.assert_array_equal(two["draws"], full["draws"])
