@@ -354,6 +354,16 @@ static double analytic_lpg(const analytic_t* A, const double* q, double* g) {
     }
     return lp;
   }
+  if (A->target == 2) { /* zero-mean multivariate normal with dense precision matrix par[D*D] */
+    double lp = 0.0;
+    for (int a = 0; a < A->D; ++a) {
+      double s = 0.0;
+      for (int b = 0; b < A->D; ++b) s += A->par[a * A->D + b] * q[b];
+      g[a] = -s;
+      lp += -0.5 * q[a] * s;
+    }
+    return lp;
+  }
   /* Exponential(rate) on lambda = exp(q): lp = -rate*lambda + q  (Tests/testGamma.R:19-30) */
   double lam = exp(q[0]);
   g[0] = -A->par[0] * lam + 1.0;

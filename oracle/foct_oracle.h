@@ -44,7 +44,9 @@ int foct_oracle_sample(int kind, const foct_problem* P, int n_problems, const fo
 
 /* Sampler on a user-supplied diagonal-normal / exponential analytic target (tests of the NUTS logic):
  * target 0: independent normal, sd[d] given; target 1: Exponential(rate) on lambda>0 sampled on
- * q = log(lambda) with Jacobian (Tests/testGamma.R:19-30).  draws [n_saved][chains][D]. */
+ * q = log(lambda) with Jacobian (Tests/testGamma.R:19-30); target 2: zero-mean multivariate normal with dense
+ * precision matrix par[D*D] (correlated: exercises the U-turn logic under a diagonal metric).
+ * draws [n_saved][chains][D]. */
 int foct_oracle_sample_analytic(int target, int D, const double* par, const foct_sampler_cfg* cfg,
                                 double* draws, double* sampler_params);
 

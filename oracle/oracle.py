@@ -124,7 +124,7 @@ def sample(kind, batch: abi.ProblemBatch, n_problems, spec, cfg, draws=True, sum
 
 def sample_analytic(target, par, cfg):
     par = np.ascontiguousarray(par, dtype=np.float64)
-    D = par.size if target == 0 else 1
+    D = par.size if target == 0 else (int(round(par.size ** 0.5)) if target == 2 else 1)
     n_saved = cfg.n_iter if cfg.save_warmup else cfg.n_iter - cfg.n_warmup
     draws = np.empty((n_saved, cfg.chains, D))
     sp = np.empty((n_saved, cfg.chains, 6))

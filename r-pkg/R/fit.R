@@ -39,16 +39,21 @@ fitExpGP <- function(x, y, uy, dataType = 2, Nn = 10, gridType = "internal", met
                      nb_warmup = 500, nb_iter = 1500, prior_PD = 0, open_progress = FALSE,
                      chains = 4, seed = sample.int(.Machine$integer.max, 1)) {
   stopifnot(method %in% c("sample", "optim"))   # vb: SURVEY 8(f) N4
-  if (method == "optim") {   # MAP + Hessian: foct_expgp_map (MODEL_SPEC 10); shim entry foct_R_expgp_map is analogous
-    stop("method='optim' is available through the C ABI (foct_expgp_map) and the Python mirror; add the 10-line shim foct_R_expgp_map when building the R package")
-  }
   ctl <- list(dataType = dataType, Nn = Nn, gridType = as.integer(gridType == "extremal"),
               rho = ifelse(rho_scale == 0, 1 / Nn, rho_scale), lambda_rate = lambda_rate,
               theta0 = as.numeric(theta0), Sigma0 = as.numeric(Sigma0), prior_PD = prior_PD,
               chains = chains, nb_warmup = nb_warmup, nb_iter = nb_iter, seed = seed)
-  res <- .Call("foct_R_sample", 0L, as.numeric(x), as.numeric(y), as.numeric(uy), ctl, PACKAGE = "FitOCTb200")
   dx  <- 1 / (Nn + 1)
   xGP <- if (gridType == "internal") seq(dx / 2, 1 - dx / 2, length.out = Nn) else seq(0, 1, length.out = Nn)
+  if (method == "optim") {   # MAP + Hessian (MODEL_SPEC 10); fit$par$... as plotExpGP.R:13-17 reads it
+    r <- .Call("foct_R_expgp_map", as.numeric(x), as.numeric(y), as.numeric(uy), ctl, PACKAGE = "FitOCTb200")
+    p <- r$par
+    fit <- list(par = list(theta = p[1:3], yGP = p[3 + seq_len(Nn)], lambda = p[Nn + 4], sigma = p[Nn + 5], br = p[Nn + 6],
+                           m = r$m, resid = r$resid, dL = r$dL),
+                value = p[Nn + 7], hessian = r$hessian, return_code = r$status)
+    return(list(fit = fit, method = method, xGP = xGP, prior_PD = prior_PD))
+  }
+  res <- .Call("foct_R_sample", 0L, as.numeric(x), as.numeric(y), as.numeric(uy), ctl, PACKAGE = "FitOCTb200")
   list(fit = .as_stanfit(res, 0L, Nn, chains, nb_warmup, nb_iter), method = method, xGP = xGP, prior_PD = prior_PD)
 }
 

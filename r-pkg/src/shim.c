@@ -115,9 +115,45 @@ SEXP foct_R_monoexp_map(SEXP x, SEXP y, SEXP uy, SEXP dataType) {
   return out;
 }
 
+/* .Call("foct_R_expgp_map", x, y, uy, ctl) -> list(par, hessian, status, m, resid, dL): fitExpGP(method = 'optim') */
+SEXP foct_R_expgp_map(SEXP x, SEXP y, SEXP uy, SEXP ctl) {
+  foct_problem P;
+  memset(&P, 0, sizeof(P));
+  P.N = (int)XLENGTH(x);
+  P.x = REAL(x); P.y = REAL(y); P.uy = REAL(uy);
+  P.dataType = (int)get_num(ctl, "dataType", 2);
+  P.Nn = (int)get_num(ctl, "Nn", 10);
+  P.gridType = (int)get_num(ctl, "gridType", 0);
+  P.rho = get_num(ctl, "rho", 0.1);
+  P.lambda_rate = get_num(ctl, "lambda_rate", 0.1);
+  P.prior_PD = (int)get_num(ctl, "prior_PD", 0);
+  SEXP th0 = get_elt(ctl, "theta0"), S0 = get_elt(ctl, "Sigma0");
+  if (th0 != R_NilValue) memcpy(P.theta0, REAL(th0), 3 * sizeof(double));
+  if (S0 != R_NilValue) memcpy(P.Sigma0, REAL(S0), 9 * sizeof(double));
+  foct_model_spec spec;
+  foct_model_spec_default(&spec, FOCT_EXPGP);
+  const int D = P.Nn + 5, P_out = P.Nn + 7;
+  SEXP par = PROTECT(Rf_allocVector(REALSXP, P_out)), H = PROTECT(Rf_allocMatrix(REALSXP, D, D));
+  SEXP st = PROTECT(Rf_allocVector(INTSXP, 1));
+  SEXP m = PROTECT(Rf_allocVector(REALSXP, P.N)), resid = PROTECT(Rf_allocVector(REALSXP, P.N)), dL = PROTECT(Rf_allocVector(REALSXP, P.N));
+  int rc = foct_expgp_map(&P, 1, &spec, NULL, REAL(par), REAL(H), INTEGER(st));
+  if (!rc) rc = foct_predict(FOCT_EXPGP, &P, &spec, REAL(par), 1, REAL(m), REAL(resid), REAL(dL));
+  if (rc) {
+    UNPROTECT(6);
+    Rf_error("fitoct_b200 error %d: %s", rc, foct_last_error());
+  }
+  const char* nm[] = {"par", "hessian", "status", "m", "resid", "dL", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
+  SET_VECTOR_ELT(out, 0, par); SET_VECTOR_ELT(out, 1, H); SET_VECTOR_ELT(out, 2, st);
+  SET_VECTOR_ELT(out, 3, m); SET_VECTOR_ELT(out, 4, resid); SET_VECTOR_ELT(out, 5, dL);
+  UNPROTECT(7);
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"foct_R_sample", (DL_FUNC)&foct_R_sample, 5},
     {"foct_R_monoexp_map", (DL_FUNC)&foct_R_monoexp_map, 4},
+    {"foct_R_expgp_map", (DL_FUNC)&foct_R_expgp_map, 4},
     {NULL, NULL, 0}};
 
 void R_init_FitOCTb200(DllInfo* dll) {

@@ -193,3 +193,31 @@ def test_expgp_map_is_a_stationary_point(O):
     out = O.sample(0, b, 1, spec, abi.default_cfg(n_warmup=300, n_iter=600, seed=8), n_threads=4)
     s = out["summary"][0]
     assert np.all(np.abs(par[0, :13] - s[:13, 0]) < 4 * s[:13, 2])
+
+
+def test_correlated_normal_moments(O):
+    # dense precision matrix, correlations up to 0.95: the diagonal metric cannot decorrelate, so this exercises
+    # long trees, the three U-turn checks per merge and the multinomial sampling; known covariance = inv(A)
+    rng = np.random.default_rng(5)
+    D = 6
+    sd = np.array([1.0, 5.0, 0.2, 2.0, 1.0, 0.5])
+    R = np.full((D, D), 0.3) + 0.7 * np.eye(D)
+    R[0, 1] = R[1, 0] = 0.95
+    R[2, 3] = R[3, 2] = -0.9
+    w, V = np.linalg.eigh(R)
+    R = (V * np.maximum(w, 0.02)) @ V.T
+    d = np.sqrt(np.diag(R)); R = R / np.outer(d, d)
+    cov = R * np.outer(sd, sd)
+    A = np.linalg.inv(cov)
+    cfg = abi.default_cfg(n_warmup=500, n_iter=3000, seed=21)
+    dr, sp = O.sample_analytic(2, A.reshape(-1), cfg)
+    S = O.summary(dr)
+    flat = dr.reshape(-1, D)
+    assert np.all(S[:, 9] < 1.01)
+    assert np.all(np.abs(S[:, 0]) < 4 * sd / np.sqrt(S[:, 8]))               # means within 4 MCSE
+    assert np.all(np.abs(S[:, 2] / sd - 1) < 0.08)                           # marginal sds
+    C = np.corrcoef(flat.T)
+    assert abs(C[0, 1] - R[0, 1]) < 0.02 and abs(C[2, 3] - R[2, 3]) < 0.03   # strong correlations recovered
+    assert np.abs(C - R).max() < 0.06
+    assert sp[..., 4].sum() == 0 and sp[..., 2].max() <= 10
+    assert sp[..., 2].mean() > 2.5                                            # correlation => deeper trees than iid
