@@ -54,6 +54,10 @@ fitExpGP <- function(x, y, uy, dataType = 2, Nn = 10, gridType = "internal", met
     return(list(fit = fit, method = method, xGP = xGP, prior_PD = prior_PD))
   }
   res <- .Call("foct_R_sample", 0L, as.numeric(x), as.numeric(y), as.numeric(uy), ctl, PACKAGE = "FitOCTb200")
+  # rstan-style progress lines so that the Shiny log scraper (ShinyInterface/server.R:457-472) reaches 100 %:
+  # the whole fit is one kernel launch (~1.5 s), so only the final state of each chain is reported
+  for (k in seq_len(chains))
+    cat(sprintf("Chain %d: Iteration: %d / %d [100%%]  (Sampling)\n", k, nb_iter, nb_iter))
   list(fit = .as_stanfit(res, 0L, Nn, chains, nb_warmup, nb_iter), method = method, xGP = xGP, prior_PD = prior_PD)
 }
 
