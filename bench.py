@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--n-warmup", type=int, default=500)
     ap.add_argument("--n-iter", type=int, default=1500)
     ap.add_argument("--seed", type=int, default=1234)
-    ap.add_argument("--cpu-waves", type=int, default=2, help="CPU sample = cores/4 * waves profiles")
+    ap.add_argument("--cpu-waves", type=int, default=3, help="CPU sample = cores/4 * waves profiles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
