@@ -93,29 +93,13 @@ __host__ __device__ __forceinline__ size_t blob_index(int i, int r, int NN) {
 }
 
 // ---------------------------------------------------------------- fp64 exp
-// exp(x) = 2^n (1 + r + r^2 P(r)), n = rint(x log2 e), |r| <= ln2/2, P of degree 9 (Chebyshev interpolant,
-// 0.14 ulp approximation error; coefficients derived with mpmath).  Coefficients live in
-// constant memory so every DFMA takes its addend from the constant bank: no per-call constant
-// materialisation in the issue stream, which is what made the libdevice exp cost ~50 issue slots here.
-// Coefficients are compile-time literals on purpose: ptxas then feeds them to DFMA as uniform/immediate operands
-// instead of parking them in 28 vector registers for the whole sweep (which is what a __constant__ array led to).
-#define FEXP_C0 0x1.0000000000001p-1
-#define FEXP_C1 0x1.5555555555556p-3
-#define FEXP_C2 0x1.5555555553d63p-5
-#define FEXP_C3 0x1.11111111109b3p-7
-#define FEXP_C4 0x1.6c16c1788bd90p-10
-#define FEXP_C5 0x1.a01a01a7c41d5p-13
-#define FEXP_C6 0x1.a019b90d2ae7ap-16
-#define FEXP_C7 0x1.71de0dae63bb3p-19
-#define FEXP_C8 0x1.289185613a3d6p-22
-#define FEXP_C9 0x1.af38a9b0ec855p-26
-#define FEXP_L2E 0x1.71547652b82fep+0     /* log2 e */
+// exp(x) = 2^m T[j] E(r): n = rint(32 x / ln 2) = 32 m + j by the magic-number trick, |r| <= ln2/64, E the degree-6
+// Taylor polynomial (0.03 ulp truncation error), T = 2^(j/32) from a 256-byte table read through L1 with a
+// lane-dependent index (at most two cache lines); 12 fp64 instructions and 9 constants.  (Round 1 went through the
+// libdevice exp - ~50 issue slots with its per-call constant materialisation - and a table-free degree-11 Estrin
+// variant with 18 instructions and 14 constants; the table version won by 3-4 % because fewer constants stay in
+// registers across the sweep.)  Constants are literals so that ptxas may feed them as immediate / uniform operands.
 #define FEXP_MAGIC 6755399441055744.0     /* 1.5 * 2^52 */
-#define FEXP_NLN2HI (-0x1.62e42fefa39efp-1)
-#define FEXP_NLN2LO (-0x1.abc9e3b39803fp-56)
-// Table-driven variant used by the sweep: exp(x) = 2^m T[j] E(r), n = rint(32 x / ln 2) = 32 m + j, |r| <= ln2/64,
-// E of degree 6 (Taylor, 0.03 ulp truncation error): 12 fp64 instructions and 9 constants instead of 18 and 14; the
-// 256-byte table 2^(j/32) is read through L1 with a lane-dependent index (at most two cache lines).
 #define FEXPT_L2E32 0x1.71547652b82fep+5
 #define FEXPT_NHI (-0x1.62e42fefa39efp-6)
 #define FEXPT_NLO (-0x1.abc9e3b39803fp-61)
@@ -133,28 +117,20 @@ static __device__ const double FEXP_TAB[32] = {
 // a positive argument that large only arises from a negative decay length, i.e. a state that is non-finite
 // anyway), NaN propagates.  Being branch-free lets ptxas interleave two points of the sweep.
 __device__ __forceinline__ double fexp(double x) {
-  const double t = fma(x, FEXP_L2E, FEXP_MAGIC);
+  const double t = fma(x, FEXPT_L2E32, FEXP_MAGIC);
   const double nd = t - FEXP_MAGIC;
   const int n = __double2loint(t);
-  double r = fma(nd, FEXP_NLN2HI, x);
-  r = fma(nd, FEXP_NLN2LO, r);
-  // Estrin evaluation of 1 + r + r^2 (c0 + c1 r + ... + c9 r^9): depth 4 instead of 11 dependent DFMAs for
-  // 3 extra multiplies (the sweep is latency-bound, not pipe-bound: profiles/r1_ncu_nuts_v2_summary.txt)
+  const double tj = __ldg(&FEXP_TAB[n & 31]);
+  double r = fma(nd, FEXPT_NHI, x);
+  r = fma(nd, FEXPT_NLO, r);
   const double r2 = r * r;
-  const double q0 = 1.0 + r;
-  const double q1 = fma(FEXP_C1, r, FEXP_C0);
-  const double q2 = fma(FEXP_C3, r, FEXP_C2);
-  const double q3 = fma(FEXP_C5, r, FEXP_C4);
-  const double q4 = fma(FEXP_C7, r, FEXP_C6);
-  const double q5 = fma(FEXP_C9, r, FEXP_C8);
-  const double r4 = r2 * r2;
-  const double s0 = fma(q1, r2, q0);
-  const double s1 = fma(q3, r2, q2);
-  const double s2 = fma(q5, r2, q4);
-  const double r8 = r4 * r4;
-  const double t0 = fma(s1, r4, s0);
-  const double p = fma(s2, r8, t0);
-  double res = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+  double pa = fma(0x1.5555555555555p-3, r, 0.5);
+  double pb = fma(0x1.1111111111111p-7, r, 0x1.5555555555555p-5);
+  pb = fma(0x1.6c16c16c16c17p-10, r2, pb);
+  pa = fma(pb, r2, pa);
+  pa = fma(pa, r2, 1.0 + r);
+  const double p = pa * tj;
+  double res = __hiloint2double(__double2hiint(p) + ((n >> 5) << 20), __double2loint(p));
   res = x < -700.0 ? 0.0 : res;
   res = x > 700.0 ? CUDART_INF : res;
   return res;
