@@ -10,6 +10,10 @@
 
 namespace foct {
 
+#ifndef FOCT_PARK
+#define FOCT_PARK volatile
+#endif
+
 struct SamplerParams {
   const double* blobs;      // [n_problems][blob_stride] staged profile blobs
   size_t blob_stride;       // doubles per blob = (3 + NN) * npad
@@ -118,16 +122,19 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       a_num_warmup = nw; a_init_buffer = ib; a_term_buffer = tb; a_base_window = bw;
     }
   }
-  int a_counter = 0, a_wsize = a_base_window, a_next = a_init_buffer + a_base_window - 1;
-  double w_n = 0.0, w_mean = 0.0, w_m2 = 0.0;
+  // State that is touched once per iteration or per doubling, never per leaf, is declared volatile: it then lives in
+  // (L1-resident) local memory instead of occupying registers across the sweep, where register pressure decides whether
+  // ptxas keeps the two points of an iteration interleaved (profiles/r1_microbench.txt, in-situ ablations).
+  FOCT_PARK int a_counter = 0, a_wsize = a_base_window, a_next = a_init_buffer + a_base_window - 1;
+  FOCT_PARK double w_n = 0.0, w_mean = 0.0, w_m2 = 0.0;
   const double da_delta = K.adapt_delta > 0.0 ? K.adapt_delta : 0.8;
   const double da_gamma = K.gamma > 0.0 ? K.gamma : 0.05, da_kappa = K.kappa > 0.0 ? K.kappa : 0.75;
   const double da_t0 = K.t0 > 0.0 ? K.t0 : 10.0;
-  double da_mu = log(10.0 * eps), da_counter = 0.0, da_sbar = 0.0, da_xbar = 0.0;
+  FOCT_PARK double da_mu = log(10.0 * eps), da_counter = 0.0, da_sbar = 0.0, da_xbar = 0.0;
   const int max_depth = K.max_depth > 0 ? (K.max_depth <= FOCT_STACK_LEVELS + 1 ? K.max_depth : FOCT_STACK_LEVELS + 1) : 10;
   const double log08 = log(0.8);
 
-  double nlf_warm = 0.0, nlf_samp = 0.0, ndiv = 0.0;
+  FOCT_PARK double nlf_warm = 0.0, nlf_samp = 0.0, ndiv = 0.0;
   const int n_saved = K.save_warmup ? K.n_iter : K.n_iter - K.n_warmup;
 
   // Stan's init_stepsize heuristic; `it_site` tags the RNG sites of this call.
@@ -171,9 +178,10 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
     }
     const double H0 = V + 0.5 * warp_sum(invM * p * p);
     // trajectory ends (q, p, g) and the running sample
-    double fq = q, fp = p, fg = g, bq = q, bp = p, bg = g;
-    double sq = q, sg = g, sV = V, sc2 = c2, sH = H0;
-    double rho = p, lsw = 0.0, sum_metro = 0.0;
+    FOCT_PARK double fq = q, fp = p, fg = g, bq = q, bp = p, bg = g;
+    FOCT_PARK double sq = q, sg = g, sV = V, sc2 = c2, sH = H0;
+    FOCT_PARK double rho = p, lsw = 0.0;
+    double sum_metro = 0.0;
     int n_leap = 0, depth = 0;
     bool divergent = false;
 
@@ -183,7 +191,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       const double u_top = u53(rb[2], rb[3]);
       // integrator starts from the end being extended; the old trajectory is the "init" half of the top merge
       double zq = fwd ? fq : bq, zp = fwd ? fp : bp, zg = fwd ? fg : bg, zV = 0.0, zc2 = 0.0;
-      const double old_end_p = zp, other_end_p = fwd ? bp : fp;
+      FOCT_PARK double old_end_p = zp, other_end_p = fwd ? bp : fp;
       const double eps_s = fwd ? eps : -eps;
       // current (growing) subtree
       double c_lsw = -CUDART_INF, c_rho = 0.0, c_pbeg = 0.0, c_pend = 0.0, c_qp = 0.0, c_gp = 0.0;
