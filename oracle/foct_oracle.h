@@ -62,6 +62,20 @@ int foct_oracle_expgp_map(const foct_problem* P, int n_problems, const foct_mode
 int foct_oracle_predict(int kind, const foct_problem* P, const foct_model_spec* spec, const double* draws,
                         int n_draws, double* m, double* resid, double* dL);
 
+/* ---- steps either side of the path (foct_oracle_prep.c; MODEL_SPEC §11-13) ---- */
+int foct_oracle_nknots(int n);
+/* R-style penalised cubic regression spline.  info[4] = spar, lambda, df reached, evaluations.
+ * spar_fixed = NaN: solve df(spar) = df; all_knots != 0: every x is a knot (natural smoothing spline). */
+int foct_oracle_smooth_spline(int N, const double* x, const double* y, double df, int all_knots, double spar_fixed,
+                              double* ySmooth, double* info);
+int foct_oracle_noise_fit(int N, const double* x, const double* resid, double max_rate, double theta[2]);
+int foct_oracle_estimate_noise(const foct_problem* P, int n, double df, double max_rate, double* uy, double* ySmooth,
+                               double* theta, double* info);
+double foct_oracle_qchisq(double p, double ndf);
+int foct_oracle_print_br(const double* br, int n, double ndf, double ci[2], int* alert);
+int foct_oracle_exp_prior(const foct_problem* P, int n, int priorType, const double* theta_map, const double* hessian,
+                          double ru_theta, double* theta0, double* Sigma0, double* ru_out);
+
 #ifdef __cplusplus
 }
 #endif

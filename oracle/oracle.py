@@ -47,6 +47,14 @@ def lib():
         L.foct_oracle_expgp_map.argtypes = [C.POINTER(abi.Problem), C.c_int, C.POINTER(abi.ModelSpec), dp, dp, dp, ip]
         L.foct_oracle_predict.argtypes = [C.c_int, C.POINTER(abi.Problem), C.POINTER(abi.ModelSpec), dp, C.c_int,
                                           dp, dp, dp]
+        L.foct_oracle_nknots.argtypes = [C.c_int]
+        L.foct_oracle_smooth_spline.argtypes = [C.c_int, dp, dp, C.c_double, C.c_int, C.c_double, dp, dp]
+        L.foct_oracle_noise_fit.argtypes = [C.c_int, dp, dp, C.c_double, dp]
+        L.foct_oracle_estimate_noise.argtypes = [C.POINTER(abi.Problem), C.c_int, C.c_double, C.c_double, dp, dp, dp, dp]
+        L.foct_oracle_qchisq.argtypes = [C.c_double, C.c_double]
+        L.foct_oracle_qchisq.restype = C.c_double
+        L.foct_oracle_print_br.argtypes = [dp, C.c_int, C.c_double, dp, ip]
+        L.foct_oracle_exp_prior.argtypes = [C.POINTER(abi.Problem), C.c_int, C.c_int, dp, dp, C.c_double, dp, dp, dp]
         L.foct_oracle_normal.argtypes = [C.POINTER(C.c_uint32)]
         L.foct_oracle_normal.restype = C.c_double
         _LIB = L
@@ -173,3 +181,63 @@ def predict(kind, batch, j, spec, draws):
     _check(lib().foct_oracle_predict(kind, C.byref(batch.array[j]), C.byref(spec), abi.as_ptr(draws), n, abi.as_ptr(m),
                                      abi.as_ptr(r), abi.as_ptr(dl)), "predict")
     return m, r, dl
+
+
+# ---- steps either side of the path (MODEL_SPEC §11-13) ----
+def nknots(n):
+    return lib().foct_oracle_nknots(int(n))
+
+
+def smooth_spline(x, y, df=15.0, all_knots=False, spar=None):
+    """R-style smooth.spline(x, y, df) (or at a fixed spar).  Returns ySmooth, dict(spar, lambda, df, evals)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out = np.empty_like(x)
+    info = np.empty(4)
+    _check(lib().foct_oracle_smooth_spline(x.size, abi.as_ptr(x), abi.as_ptr(y), float(df), int(all_knots),
+                                           float("nan") if spar is None else float(spar), abi.as_ptr(out),
+                                           abi.as_ptr(info)), "smooth_spline")
+    return out, dict(spar=info[0], lam=info[1], df=info[2], evals=int(info[3]))
+
+
+def noise_fit(x, resid, max_rate=1e4):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    r = np.ascontiguousarray(resid, dtype=np.float64)
+    th = np.empty(2)
+    _check(lib().foct_oracle_noise_fit(x.size, abi.as_ptr(x), abi.as_ptr(r), float(max_rate), abi.as_ptr(th)), "noise_fit")
+    return th
+
+
+def estimate_noise(batch: abi.ProblemBatch, n, df=15.0, max_rate=1e4):
+    """Returns uy, ySmooth (lists of per-problem arrays), theta [n,2], info [n,4]."""
+    Ns = [batch.array[j].N for j in range(n)]
+    tot = int(np.sum(Ns))
+    uy, ys = np.empty(tot), np.empty(tot)
+    th, info = np.empty((n, 2)), np.empty((n, 4))
+    _check(lib().foct_oracle_estimate_noise(batch.array, n, float(df), float(max_rate), abi.as_ptr(uy), abi.as_ptr(ys),
+                                            abi.as_ptr(th), abi.as_ptr(info)), "estimate_noise")
+    offs = np.concatenate([[0], np.cumsum(Ns)])
+    return ([uy[offs[j]:offs[j + 1]] for j in range(n)], [ys[offs[j]:offs[j + 1]] for j in range(n)], th, info)
+
+
+def qchisq(p, ndf):
+    return lib().foct_oracle_qchisq(float(p), float(ndf))
+
+
+def print_br(br, ndf):
+    br = np.ascontiguousarray(br, dtype=np.float64)
+    ci = np.empty(2)
+    alert = np.empty(br.size, dtype=np.int32)
+    _check(lib().foct_oracle_print_br(abi.as_ptr(br), br.size, float(ndf), abi.as_ptr(ci),
+                                      alert.ctypes.data_as(C.POINTER(C.c_int))), "print_br")
+    return ci, alert
+
+
+def exp_prior(batch: abi.ProblemBatch, n, priorType, theta_map, hessian, ru_theta=0.05):
+    """priorType 'mono' | 'abc'.  Returns theta0 [n,3], Sigma0 [n,3,3], ru [n]."""
+    th = np.ascontiguousarray(theta_map, dtype=np.float64)
+    H = np.ascontiguousarray(hessian, dtype=np.float64)
+    t0, S0, ru = np.empty((n, 3)), np.empty((n, 3, 3)), np.empty(n)
+    _check(lib().foct_oracle_exp_prior(batch.array, n, {"mono": 0, "abc": 1}[priorType], abi.as_ptr(th), abi.as_ptr(H),
+                                       float(ru_theta), abi.as_ptr(t0), abi.as_ptr(S0), abi.as_ptr(ru)), "exp_prior")
+    return t0, S0, ru
