@@ -93,6 +93,45 @@ class Result(C.Structure):
     ]
 
 
+FOCT_PRIOR_MONO, FOCT_PRIOR_ABC = 0, 1
+c_int_p = C.POINTER(C.c_int)
+
+
+class PipelineCfg(C.Structure):
+    """foct_pipeline_cfg: the ctrlParams.yaml keys the batch pipeline needs (FitOCT.R:37-53)."""
+    _fields_ = [
+        ("smooth_df", C.c_double),
+        ("max_rate", C.c_double),
+        ("prior_type", C.c_int),
+        ("ru_theta", C.c_double),
+        ("Nn", C.c_int),
+        ("gridType", C.c_int),
+        ("rho_scale", C.c_double),
+        ("lambda_rate", C.c_double),
+        ("gate", C.c_int),
+    ]
+
+
+class PipelineOut(C.Structure):
+    _fields_ = [
+        ("uy", c_double_p),
+        ("ySmooth", c_double_p),
+        ("noise_theta", c_double_p),
+        ("mono_theta", c_double_p),
+        ("mono_hessian", c_double_p),
+        ("mono_br", c_double_p),
+        ("mono_status", c_int_p),
+        ("br_ci", c_double_p),
+        ("alert", c_int_p),
+        ("theta0", c_double_p),
+        ("Sigma0", c_double_p),
+        ("ru", c_double_p),
+        ("n_expgp", C.c_int),
+        ("expgp_index", c_int_p),
+        ("expgp", Result),
+    ]
+
+
 def dims(kind: int, Nn: int) -> tuple[int, int]:
     """(D unconstrained dims, P_out output columns) — MODEL_SPEC §2, §6."""
     if kind == FOCT_EXPGP:

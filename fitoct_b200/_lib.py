@@ -21,6 +21,8 @@ EXPORTS = (
     "foct_dims", "foct_expgp_grid", "foct_expgp_basis", "foct_logp_grad", "foct_sample", "foct_expgp_sample",
     "foct_monoexp_sample", "foct_monoexp_map", "foct_expgp_map", "foct_predict", "foct_plan_create", "foct_plan_run",
     "foct_plan_sync", "foct_plan_timing", "foct_plan_fetch", "foct_plan_destroy", "foct_fp64_peak",
+    "foct_estimate_noise", "foct_birge_ci", "foct_print_br", "foct_estimate_exp_prior", "foct_pipeline_cfg_default",
+    "foct_pipeline",
 )
 
 _LIB = None
@@ -67,6 +69,13 @@ def lib():
         L.foct_plan_destroy.argtypes = [C.c_void_p]
         L.foct_plan_destroy.restype = None
         L.foct_fp64_peak.argtypes = [C.c_int, dp, dp]
+        L.foct_estimate_noise.argtypes = [PP, C.c_int, C.c_double, C.c_double, dp, dp, dp, dp, ip]
+        L.foct_birge_ci.argtypes = [C.c_double, dp]
+        L.foct_print_br.argtypes = [C.c_int, PP, C.c_int, MS, dp, dp, ip]
+        L.foct_estimate_exp_prior.argtypes = [PP, C.c_int, C.c_int, dp, dp, C.c_double, dp, dp, dp]
+        L.foct_pipeline_cfg_default.argtypes = [C.POINTER(abi.PipelineCfg)]
+        L.foct_pipeline_cfg_default.restype = None
+        L.foct_pipeline.argtypes = [PP, C.c_int, C.POINTER(abi.PipelineCfg), MS, SC, C.POINTER(abi.PipelineOut)]
         _LIB = L
     return _LIB
 
@@ -225,3 +234,87 @@ def fp64_peak(device: int = 0):
     t, f = np.zeros(1), np.zeros(1)
     check(lib().foct_fp64_peak(device, abi.as_ptr(t), abi.as_ptr(f)))
     return float(t[0]), float(f[0])
+
+
+# ---- the steps either side of the sampling path (include/fitoct_b200.h, MODEL_SPEC §11-13) ----
+def _split(packed, Ns):
+    offs = np.concatenate([[0], np.cumsum(Ns)]).astype(np.int64)
+    return [packed[offs[j]:offs[j + 1]] for j in range(len(Ns))]
+
+
+def _int_ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def estimate_noise(batch: abi.ProblemBatch, n_problems: int, df: float = 15.0, max_rate: float = 1e4):
+    """Returns dict(uy, ySmooth: lists of per-problem arrays; theta [n,2]; info [n,4]; status [n])."""
+    Ns = [batch.array[j].N for j in range(n_problems)]
+    tot = int(np.sum(Ns))
+    uy, ys = np.empty(tot), np.empty(tot)
+    th, info = np.empty((n_problems, 2)), np.empty((n_problems, 4))
+    st = np.empty(n_problems, dtype=np.int32)
+    check(lib().foct_estimate_noise(batch.array, n_problems, float(df), float(max_rate), abi.as_ptr(uy), abi.as_ptr(ys),
+                                    abi.as_ptr(th), abi.as_ptr(info), _int_ptr(st)))
+    return dict(uy=_split(uy, Ns), ySmooth=_split(ys, Ns), theta=th, info=info, status=st)
+
+
+def birge_ci(ndf: float) -> np.ndarray:
+    ci = np.empty(2)
+    check(lib().foct_birge_ci(float(ndf), abi.as_ptr(ci)))
+    return ci
+
+
+def print_br(kind: int, batch: abi.ProblemBatch, n_problems: int, spec: abi.ModelSpec, br):
+    """Returns ci [n,2], alert [n] (1 = br outside the 95 % interval: the fit is not OK)."""
+    br = np.ascontiguousarray(br, dtype=np.float64)
+    ci = np.empty((n_problems, 2))
+    alert = np.empty(n_problems, dtype=np.int32)
+    check(lib().foct_print_br(kind, batch.array, n_problems, C.byref(spec), abi.as_ptr(br), abi.as_ptr(ci), _int_ptr(alert)))
+    return ci, alert
+
+
+def estimate_exp_prior(batch: abi.ProblemBatch, n_problems: int, priorType: str, theta_map, hessian, ru_theta: float = 0.05):
+    """priorType 'mono' | 'abc'.  Returns theta0 [n,3], Sigma0 [n,3,3], ru [n]."""
+    if priorType not in ("mono", "abc"):
+        raise ValueError("priorType must be 'mono' or 'abc'")
+    th = np.ascontiguousarray(theta_map, dtype=np.float64)
+    H = np.ascontiguousarray(hessian, dtype=np.float64)
+    t0, S0, ru = np.empty((n_problems, 3)), np.empty((n_problems, 3, 3)), np.empty(n_problems)
+    check(lib().foct_estimate_exp_prior(batch.array, n_problems, {"mono": 0, "abc": 1}[priorType], abi.as_ptr(th),
+                                        abi.as_ptr(H), float(ru_theta), abi.as_ptr(t0), abi.as_ptr(S0), abi.as_ptr(ru)))
+    return t0, S0, ru
+
+
+def pipeline_cfg(**kw) -> abi.PipelineCfg:
+    c = abi.PipelineCfg()
+    lib().foct_pipeline_cfg_default(C.byref(c))
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise TypeError(f"unknown pipeline key {k}")
+        setattr(c, k, v)
+    return c
+
+
+def pipeline(batch: abi.ProblemBatch, n_problems: int, pcfg: abi.PipelineCfg, cfg: abi.SamplerCfg, spec_gp=None, draws=False,
+             summary=True):
+    """foct_pipeline: noise -> MonoExp MAP -> gate -> prior -> fitExpGP on the gated profiles, one call."""
+    n = n_problems
+    Ns = [batch.array[j].N for j in range(n)]
+    tot = int(np.sum(Ns))
+    o = dict(uy=np.empty(tot), ySmooth=np.empty(tot), noise_theta=np.empty((n, 2)), mono_theta=np.empty((n, 3)),
+             mono_hessian=np.empty((n, 3, 3)), mono_br=np.empty(n), mono_status=np.empty(n, dtype=np.int32),
+             br_ci=np.empty((n, 2)), alert=np.empty(n, dtype=np.int32), theta0=np.empty((n, 3)), Sigma0=np.empty((n, 3, 3)),
+             ru=np.empty(n), expgp_index=np.full(n, -1, dtype=np.int32))
+    res, R = alloc_result(abi.FOCT_EXPGP, n, pcfg.Nn, cfg, draws, summary)
+    out = abi.PipelineOut()
+    for k, v in o.items():
+        setattr(out, k, _int_ptr(v) if v.dtype == np.int32 else abi.as_ptr(v))
+    out.expgp = R
+    check(lib().foct_pipeline(batch.array, n, C.byref(pcfg), C.byref(spec_gp) if spec_gp is not None else None, C.byref(cfg),
+                              C.byref(out)))
+    k = out.n_expgp
+    o["uy"], o["ySmooth"] = _split(o["uy"], Ns), _split(o["ySmooth"], Ns)
+    o["n_expgp"] = k
+    o["expgp_index"] = o["expgp_index"][:k]
+    o["expgp"] = {name: (v[:k] if v is not None else None) for name, v in res.items()}
+    return o

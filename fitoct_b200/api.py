@@ -212,3 +212,93 @@ def fitMonoExp(x, y, uy, dataType=2, method="optim", *, nb_warmup=500, nb_iter=1
     out = L.sample(abi.FOCT_MONOEXP, batch, 1, spec, cfg, draws=True, summary=True)
     fit = _stanfit_from(out, 0, abi.FOCT_MONOEXP, 0, cfg)
     return dict(best_theta=fit.summary_table[:3, 0], cor_theta=cor, fit=fit, method="sample")
+
+
+# ---- the steps either side of the path (MODEL_SPEC §11-13) ----
+def _xy_problem(x, y, dataType=2):
+    x = np.asarray(x, dtype=np.float64)
+    return dict(x=x, y=y, uy=np.ones_like(x), dataType=dataType, Nn=0, gridType=0, rho=1.0, lambda_rate=0.0,
+                theta0=(0.0, 0.0, 1.0), Sigma0=np.eye(3), prior_PD=0)
+
+
+def estimateNoise(x, y, df=15, maxRate=10000):
+    """Drop-in for FitOCTLib::estimateNoise (FitOCT.R:89-91, server.R:309-311): `uy`, `ySmooth`, `theta` (= a_1, a_2 of
+    uy = a_1 exp(-x/a_2), plotNoise.R:4-6), plus `fit` (spar, lambda, df of the smoother) and `method`."""
+    batch = abi.make_problems([_xy_problem(x, y)])
+    o = L.estimate_noise(batch, 1, df=float(df), max_rate=float(maxRate))
+    if o["status"][0] == 3:
+        raise ValueError("estimateNoise: x must be strictly increasing")
+    info = o["info"][0]
+    return dict(uy=o["uy"][0], ySmooth=o["ySmooth"][0], theta=o["theta"][0], method="optim",
+                fit=dict(spar=info[0], **{"lambda": info[1]}, df=info[2], iterations=int(info[3]), return_code=int(o["status"][0])))
+
+
+def printBr(fit, N=None, n_par=None, silent=False):
+    """Drop-in for FitOCTLib::printBr (plotMonoExp.R:10, plotExpGP.R:22, server.R:354,379,499,510).  `fit` is what
+    fitMonoExp / fitExpGP return in `$fit`: an optimizing-style dict (`par$br`, `par$resid`) or a StanFit (posterior mean
+    of `br`).  Returns dict(br, CI95, alert) with alert None when the fit is OK (the test at FitOCT.R:100)."""
+    if isinstance(fit, StanFit):
+        d = fit.extract(["br"])
+        br = float(np.mean(d["br"]))
+        n_par = n_par if n_par is not None else len([p for p in fit.par_names if p.startswith(("theta", "yGP"))])
+        if N is None:
+            raise ValueError("printBr on a sampled fit needs N (the stanfit does not carry the data)")
+    else:
+        br = float(fit["par"]["br"])
+        N = N if N is not None else len(fit["par"]["resid"])
+        n_par = n_par if n_par is not None else len(np.atleast_1d(fit["par"]["theta"])) + len(np.atleast_1d(fit["par"].get("yGP", [])))
+    ndf = N - n_par
+    ci = L.birge_ci(ndf)
+    ok = ci[0] <= br <= ci[1]
+    alert = None if ok else "!!! WARNING !!! br out of interval"
+    if not silent:
+        print(f"br   : {br:.3g}\nCI95 : [{ci[0]:.3g}, {ci[1]:.3g}]" + ("" if ok else f"\n{alert}"))
+    return dict(br=br, CI95=ci, alert=alert)
+
+
+def estimateExpPrior(x, uy, dataType, priorType="mono", out=None, ru_theta=0.05, eps=1e-3):
+    """Drop-in for FitOCTLib::estimateExpPrior (FitOCT.R:103-107, server.R:396-404).  `out` is fitMonoExp's result
+    (method 'optim'); returns dict(theta0, Sigma0[, ru]).  `eps` (the ABC tolerance) has no role in the closed-form
+    matching of MODEL_SPEC §13 and is accepted for signature compatibility."""
+    if out is None:
+        raise ValueError("out= (the fitMonoExp result) is required")
+    fit = out["fit"]
+    x = np.asarray(x, dtype=np.float64)
+    y = fit["par"]["m"] + fit["par"]["resid"]
+    p = _xy_problem(x, y, dataType)
+    p["uy"] = np.asarray(uy, dtype=np.float64)
+    batch = abi.make_problems([p])
+    t0, S0, ru = L.estimate_exp_prior(batch, 1, priorType, np.asarray(out["best_theta"])[None, :], np.asarray(fit["hessian"])[None],
+                                      ru_theta=float(ru_theta))
+    return dict(theta0=t0[0], Sigma0=S0[0], ru=float(ru[0]))
+
+
+def FitOCT_batch(x, Y, ctrl=None, *, chains=4, seed=1234, gate=True, keep_draws=False, spec=None):
+    """FitOCT.R:74-124 for a batch of profiles on a shared depth grid, in one library call: estimateNoise -> fitMonoExp ->
+    printBr gate -> estimateExpPrior -> fitExpGP(method='sample') on the profiles the gate lets through.  `ctrl` holds
+    ctrlParams.yaml keys (load_ctrl_params()).  NB the reference `break`s out of its dataset loop at the first profile
+    whose MonoExp fit is OK (FitOCT.R:100); a batch treats that as `next`."""
+    c = dict(CTRL_DEFAULTS)
+    c.update(ctrl or {})
+    from . import io as fio
+
+    Y = np.atleast_2d(np.asarray(Y, dtype=np.float64))
+    n = Y.shape[0]
+    xs, Ys = [], []
+    for j in range(n):
+        xj, yj = fio.selX(x, Y[j], c.get("depthSel"), c.get("subSample", 1))
+        xs.append(xj)
+        Ys.append(yj)
+    Ysel = np.stack(Ys)
+    batch = abi.make_problems_dense(xs[0], Ysel, np.ones_like(Ysel), np.tile([0.0, 0.0, 1.0], (n, 1)),
+                                    np.tile(np.eye(3), (n, 1, 1)), dataType=int(c["dataType"]), Nn=0)
+    pc = L.pipeline_cfg(smooth_df=float(c["smooth_df"]), prior_type={"mono": 0, "abc": 1}[c["priorType"]],
+                        ru_theta=float(c["ru_theta"]), Nn=int(c["Nn"]), gridType=_grid_code(c["gridType"]),
+                        rho_scale=float(c["rho_scale"]), lambda_rate=float(c["lambda_rate"]), gate=int(bool(gate)))
+    cfg = abi.default_cfg(chains=chains, n_warmup=int(c["nb_warmup"]), n_iter=int(c["nb_warmup"]) + int(c["nb_sample"]),
+                          seed=int(seed))
+    out = L.pipeline(batch, n, pc, cfg, spec_gp=spec, draws=keep_draws, summary=True)
+    out["x"] = xs[0]
+    out["par_names"] = abi.param_names(abi.FOCT_EXPGP, int(c["Nn"]))
+    out["xGP"] = L.grid(int(c["Nn"]), _grid_code(c["gridType"]))
+    return out

@@ -43,6 +43,10 @@ struct InstEntry {
   cudaError_t (*launch_map)(int mod, int grid, size_t smem, cudaStream_t st, const MapParams& K);
 };
 
+// shared by the host translation units (defined in foct_lib.cu)
+int fail(int code, const char* fmt, ...);  // records the thread-local message behind foct_last_error(), returns code
+int check_device();
+
 #define FOCT_DECL_INST(NN) const InstEntry* foct_inst_##NN();
 
 }  // namespace foct

@@ -36,7 +36,7 @@ static const InstEntry* inst_for(int NN) {
 
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
-static int fail(int code, const char* fmt, ...) {
+int fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -364,7 +364,7 @@ static void plan_free(foct_plan* p) {
   delete p;
 }
 
-static int check_device() {
+int foct::check_device() {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n < 1)

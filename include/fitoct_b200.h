@@ -175,6 +175,68 @@ int foct_plan_timing(foct_plan* plan, float* sample_ms, float* summary_ms, int* 
                      int* blocks_per_sm, int* regs, int* smem_bytes);
 void foct_plan_destroy(foct_plan* plan);
 
+/* ---- the steps either side of the sampling path (MODEL_SPEC §11-13) ---------------------------
+ * Per-point outputs of a batch are packed back to back in problem order (problem j starts at sum_{i<j} N_i). */
+
+/* FitOCTLib::estimateNoise(x, y, df) (FitOCT.R:89-91, server.R:309-311): R-style smooth.spline at `df` equivalent
+ * degrees of freedom, then the MLE of resid_i ~ N(0, a_1 exp(-x_i/a_2)).  P[j].uy is ignored.  theta: [n][2] = a_1, a_2
+ * (plotNoise.R:4-6); info: [n][4] = spar, lambda, df reached, spline evaluations (may be NULL); status: [n] 0 ok,
+ * 1 requested df not reachable on spar in [-1.5, 1.5], 3 x not strictly increasing (may be NULL). */
+int foct_estimate_noise(const foct_problem* P, int n_problems, double df, double max_rate, double* uy, double* ySmooth,
+                        double* theta, double* info, int* status);
+
+/* 95 % interval of the Birge ratio, qchisq((.025,.975), ndf)/ndf.  Scalar host arithmetic, no device needed. */
+int foct_birge_ci(double ndf, double* ci /*[2]*/);
+
+/* FitOCTLib::printBr (plotMonoExp.R:10, plotExpGP.R:22; the gate at FitOCT.R:100): alert[j] = 1 iff br[j] lies outside
+ * the interval for ndf = N_j - n_par (spec->br_ndf as in MODEL_SPEC §6).  ci: [n][2] (may be NULL). */
+int foct_print_br(int kind, const foct_problem* P, int n_problems, const foct_model_spec* spec, const double* br,
+                  double* ci, int* alert);
+
+/* FitOCTLib::estimateExpPrior(x, uy, dataType, priorType, out = fitMonoExp result, ru_theta, eps) (FitOCT.R:103-107,
+ * server.R:396-404).  theta_map: [n][3] and hessian: [n][9] as returned by foct_monoexp_map; outputs theta0 [n][3],
+ * Sigma0 [n][9], ru [n] (the relative uncertainty applied; may be NULL). */
+#define FOCT_PRIOR_MONO 0
+#define FOCT_PRIOR_ABC 1
+int foct_estimate_exp_prior(const foct_problem* P, int n_problems, int priorType, const double* theta_map,
+                            const double* hessian, double ru_theta, double* theta0, double* Sigma0, double* ru);
+
+/* The body of FitOCT.R's dataset loop (FitOCT.R:84-124) for a whole batch in one call: estimateNoise -> fitMonoExp
+ * (MAP) -> printBr gate -> estimateExpPrior -> fitExpGP(method = 'sample') on the profiles the gate lets through.
+ * The keys are ctrlParams.yaml's (FitOCT.R:37-53). */
+typedef struct foct_pipeline_cfg {
+  double smooth_df;   /* 15 */
+  double max_rate;    /* 1e4 */
+  int prior_type;     /* FOCT_PRIOR_ABC */
+  double ru_theta;    /* 0.05 */
+  int Nn;             /* 10 */
+  int gridType;       /* FOCT_GRID_INTERNAL */
+  double rho_scale;   /* 0 => 1/Nn (FitOCT.R:119) */
+  double lambda_rate; /* 0.1 */
+  int gate;           /* 1: only profiles with a Birge-ratio alert go on to fitExpGP (FitOCT.R:100); 0: all do */
+} foct_pipeline_cfg;
+void foct_pipeline_cfg_default(foct_pipeline_cfg* c);
+
+typedef struct foct_pipeline_out {
+  double* uy;            /* packed [sum N] */
+  double* ySmooth;       /* packed [sum N] */
+  double* noise_theta;   /* [n][2] */
+  double* mono_theta;    /* [n][3] */
+  double* mono_hessian;  /* [n][9] */
+  double* mono_br;       /* [n] */
+  int* mono_status;      /* [n] or NULL */
+  double* br_ci;         /* [n][2] or NULL */
+  int* alert;            /* [n] */
+  double* theta0;        /* [n][3] */
+  double* Sigma0;        /* [n][9] */
+  double* ru;            /* [n] or NULL */
+  int n_expgp;           /* out: number of profiles passed to fitExpGP */
+  int* expgp_index;      /* [n]: profile index of ExpGP fit k, k < n_expgp */
+  foct_result expgp;     /* buffers sized for n problems by the caller; the first n_expgp entries are filled */
+} foct_pipeline_out;
+int foct_pipeline(const foct_problem* P, int n_problems, const foct_pipeline_cfg* pc, const foct_model_spec* spec_gp,
+                  const foct_sampler_cfg* cfg, foct_pipeline_out* out);
+
 /* Measured fp64 FMA throughput of the device (DFMA-chain microbenchmark), the roofline denominator for
  * the sampling kernel (MEASURED_PEAKS.json has no fp64 figure). */
 int foct_fp64_peak(int device, double* tflops, double* sm_mhz);

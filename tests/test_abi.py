@@ -46,6 +46,8 @@ int main(void) {
   printf("%zu %zu %zu %zu\n", sizeof(foct_model_spec), sizeof(foct_problem), sizeof(foct_sampler_cfg), sizeof(foct_result));
   printf("%zu %zu %zu %zu\n", offsetof(foct_problem, theta0), offsetof(foct_problem, id), offsetof(foct_sampler_cfg, seed), offsetof(foct_sampler_cfg, devices));
   printf("%d %d %d %d\n", FOCT_MAX_NN, FOCT_MAX_CHAINS, FOCT_N_SUMMARY_COLS, FOCT_N_SAMPLER_PARAMS);
+  printf("%zu %zu %zu %zu %zu\n", sizeof(foct_pipeline_cfg), sizeof(foct_pipeline_out), offsetof(foct_pipeline_cfg, gate),
+         offsetof(foct_pipeline_out, n_expgp), offsetof(foct_pipeline_out, expgp));
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
@@ -59,7 +61,9 @@ int main(void) {
     assert vals[:4] == [C.sizeof(abi.ModelSpec), C.sizeof(abi.Problem), C.sizeof(abi.SamplerCfg), C.sizeof(abi.Result)]
     assert vals[4:8] == [abi.Problem.theta0.offset, abi.Problem.id.offset, abi.SamplerCfg.seed.offset,
                          abi.SamplerCfg.devices.offset]
-    assert vals[8:] == [abi.FOCT_MAX_NN, abi.FOCT_MAX_CHAINS, abi.FOCT_N_SUMMARY_COLS, abi.FOCT_N_SAMPLER_PARAMS]
+    assert vals[8:12] == [abi.FOCT_MAX_NN, abi.FOCT_MAX_CHAINS, abi.FOCT_N_SUMMARY_COLS, abi.FOCT_N_SAMPLER_PARAMS]
+    assert vals[12:] == [C.sizeof(abi.PipelineCfg), C.sizeof(abi.PipelineOut), abi.PipelineCfg.gate.offset,
+                         abi.PipelineOut.n_expgp.offset, abi.PipelineOut.expgp.offset]
 
 
 def test_defaults_and_dims_without_device():

@@ -1,0 +1,168 @@
+"""GPU parity of the steps either side of the sampling path (MODEL_SPEC §11-13) against the CPU
+oracle, through the C ABI: estimateNoise, the printBr gate, estimateExpPrior and the batch pipeline."""
+import numpy as np
+import pytest
+
+from fitoct_b200 import _abi as abi
+from fitoct_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL_SPLINE = 1e-9   # fp64 banded solves, summation order differs between warp and serial code
+RTOL_NOISE = 1e-8
+
+
+def _xy_batch(xs, ys, dataType=2):
+    return abi.make_problems([dict(x=x, y=y, uy=np.ones_like(x), dataType=dataType, Nn=0, gridType=0, rho=1.0,
+                                   lambda_rate=0.0, theta0=(0, 0, 1), Sigma0=np.eye(3), prior_PD=0, id=j)
+                              for j, (x, y) in enumerate(zip(xs, ys))])
+
+
+def _ragged_profiles():
+    rng = np.random.default_rng(7)
+    xs, ys = [], []
+    for N in (481, 481, 30, 60, 199, 200, 1000, 3300):
+        x = 20.0 + np.arange(N) * (480.0 / (N - 1)) + (rng.uniform(-0.2, 0.2, N) * (480.0 / (N - 1)) if N != 481 else 0.0)
+        y0 = 1000 + 2000 * np.exp(-x / 150)
+        sd = 0.5 * np.sqrt(y0 - 1000 + 1)
+        xs.append(x)
+        ys.append(y0 * (1 + 0.002 * np.sin(x / 25)) + sd * rng.standard_normal(N))
+    return xs, ys
+
+
+def test_estimate_noise_matches_oracle_on_ragged_batch(L, O):
+    xs, ys = _ragged_profiles()
+    batch = _xy_batch(xs, ys)
+    n = len(xs)
+    g = L.estimate_noise(batch, n, df=15.0)
+    uy_o, ys_o, th_o, info_o = O.estimate_noise(batch, n, df=15.0)
+    assert g["status"].tolist() == [0] * n
+    for j in range(n):
+        scale = np.max(np.abs(ys[j]))
+        assert np.max(np.abs(g["ySmooth"][j] - ys_o[j])) <= RTOL_SPLINE * scale, j
+        assert np.allclose(g["theta"][j], th_o[j], rtol=RTOL_NOISE), (j, g["theta"][j], th_o[j])
+        assert np.allclose(g["uy"][j], uy_o[j], rtol=RTOL_NOISE)
+        assert abs(g["info"][j, 2] - 15.0) <= 1e-9 and abs(g["info"][j, 0] - info_o[j, 0]) <= 1e-8
+    # the fitted noise law is close to the generating one (a1 = 0.5*sqrt(2000), a2 = 300) on the full-length profiles
+    assert abs(g["theta"][0, 0] - 22.4) < 4 and abs(g["theta"][0, 1] - 300) < 80
+
+
+@pytest.mark.parametrize("df", [4.0, 15.0, 30.0])
+def test_estimate_noise_df_sweep(L, O, df):
+    """Tests/statsSplineSmooth.R sweeps df 2..20 and looks at sd(residuals): the same statistic from both sides."""
+    S = synth.make_profiles(6, modulated_only=True)
+    batch = abi.make_problems_dense(S["x"], S["Y"], np.ones_like(S["Y"]), np.tile([0.0, 0.0, 1.0], (6, 1)),
+                                    np.tile(np.eye(3), (6, 1, 1)), Nn=0)
+    g = L.estimate_noise(batch, 6, df=df)
+    _, ys_o, th_o, _ = O.estimate_noise(batch, 6, df=df)
+    for j in range(6):
+        sd_g = np.std(S["Y"][j] - g["ySmooth"][j], ddof=1)
+        sd_o = np.std(S["Y"][j] - ys_o[j], ddof=1)
+        assert sd_g == pytest.approx(sd_o, rel=1e-9)
+        assert np.allclose(g["theta"][j], th_o[j], rtol=RTOL_NOISE)
+
+
+def test_estimate_noise_rejects_bad_input(L):
+    x = np.array([1.0, 2.0, 2.0, 3.0, 4.0, 5.0])
+    g = L.estimate_noise(_xy_batch([x], [np.ones(6)]), 1, df=3.0)
+    assert g["status"][0] == 3 and np.all(np.isnan(g["uy"][0]))
+    from fitoct_b200._lib import FitOCTError
+    with pytest.raises(FitOCTError):
+        L.estimate_noise(_xy_batch([np.arange(6.0)], [np.ones(6)]), 1, df=40.0)   # more df than coefficients
+    with pytest.raises(FitOCTError):
+        L.estimate_noise(_xy_batch([np.arange(3.0)], [np.ones(3)]), 1, df=2.0)    # N < 4
+
+
+def test_print_br_and_exp_prior_match_oracle(L, O):
+    n = 16
+    S = synth.make_profiles(n)
+    spec = abi.default_spec(abi.FOCT_MONOEXP)
+    batch = abi.make_problems_dense(S["x"], S["Y"], S["UY"], np.tile([0.0, 0.0, 1.0], (n, 1)), np.tile(np.eye(3), (n, 1, 1)), Nn=0)
+    th, H, br, st = L.monoexp_map(batch, n, spec)
+    ci_g, al_g = L.print_br(abi.FOCT_MONOEXP, batch, n, spec, br)
+    ci_o, al_o = O.print_br(br, S["x"].size - 3)
+    assert np.allclose(ci_g, ci_o[None, :], rtol=1e-12) and al_g.tolist() == al_o.tolist()
+    assert 0 < al_g.sum() < n   # the synthetic family mixes unmodulated (OK) and modulated (alert) profiles
+    for pt in ("mono", "abc"):
+        t0g, S0g, rug = L.estimate_exp_prior(batch, n, pt, th, H, ru_theta=0.07)
+        t0o, S0o, ruo = O.exp_prior(batch, n, pt, th, H, ru_theta=0.07)
+        assert np.array_equal(t0g, th) and np.allclose(t0g, t0o, rtol=0, atol=0)
+        assert np.allclose(rug, ruo, rtol=1e-11), pt
+        assert np.allclose(S0g, S0o, rtol=1e-10, atol=0), pt
+
+
+def test_pipeline_equals_the_step_by_step_calls(L):
+    n = 12
+    S = synth.make_profiles(n)
+    xy = abi.make_problems_dense(S["x"], S["Y"], np.ones_like(S["Y"]), np.tile([0.0, 0.0, 1.0], (n, 1)),
+                                 np.tile(np.eye(3), (n, 1, 1)), Nn=0)
+    pc = L.pipeline_cfg(Nn=8, prior_type=abi.FOCT_PRIOR_ABC, smooth_df=15.0)
+    cfg = abi.default_cfg(chains=2, n_warmup=60, n_iter=120, seed=99)
+    out = L.pipeline(xy, n, pc, cfg, draws=True, summary=True)
+    # the same thing by hand, as FitOCT.R:89-124 spells it
+    nz = L.estimate_noise(xy, n, df=15.0)
+    UY = np.stack(nz["uy"])
+    assert np.array_equal(np.stack(out["uy"]), UY) and np.array_equal(out["noise_theta"], nz["theta"])
+    spec_m = abi.default_spec(abi.FOCT_MONOEXP)
+    mono = abi.make_problems_dense(S["x"], S["Y"], UY, np.tile([0.0, 0.0, 1.0], (n, 1)), np.tile(np.eye(3), (n, 1, 1)), Nn=0)
+    th, H, br, st = L.monoexp_map(mono, n, spec_m)
+    assert np.array_equal(out["mono_theta"], th) and np.array_equal(out["mono_br"], br)
+    ci, alert = L.print_br(abi.FOCT_MONOEXP, mono, n, spec_m, br)
+    assert out["alert"].tolist() == alert.tolist()
+    t0, S0, ru = L.estimate_exp_prior(mono, n, "abc", th, H)
+    assert np.array_equal(out["theta0"], t0) and np.array_equal(out["Sigma0"], S0)
+    idx = np.flatnonzero(alert)
+    assert out["n_expgp"] == idx.size and out["expgp_index"].tolist() == idx.tolist() and 0 < idx.size < n
+    gp = abi.make_problems_dense(S["x"], S["Y"][idx], UY[idx], t0[idx], S0[idx], Nn=8, gridType=0, rho=1.0 / 8,
+                                 lambda_rate=0.1, ids=idx)
+    ref = L.sample(abi.FOCT_EXPGP, gp, idx.size, abi.default_spec(abi.FOCT_EXPGP), cfg, draws=True, summary=True)
+    assert np.array_equal(out["expgp"]["draws"], ref["draws"])
+    assert np.array_equal(out["expgp"]["summary"], ref["summary"], equal_nan=True)
+    # gate = 0 sends every profile on
+    pc.gate = 0
+    out_all = L.pipeline(xy, n, pc, cfg, draws=False, summary=True)
+    assert out_all["n_expgp"] == n
+
+
+def test_reference_script_flow_through_the_api():
+    """FitOCT.R:84-124 written with the mirrored operator names."""
+    from fitoct_b200 import api
+    S = synth.make_profiles(2, modulated_only=True)
+    from fitoct_b200.io import selX
+    x, y = selX(S["x"], S["Y"][0], depthSel=None, subSample=1)
+    fits = api.estimateNoise(x, y, df=15)
+    uy = fits["uy"]
+    assert uy.shape == x.shape and np.all(uy > 0) and fits["fit"]["df"] == pytest.approx(15.0, abs=1e-8)
+    fitm = api.fitMonoExp(x, y, uy, dataType=2)
+    br = api.printBr(fitm["fit"], silent=True)
+    assert br["alert"] is not None            # a modulated profile fails the mono-exponential fit
+    for pt in ("mono", "abc"):
+        pri = api.estimateExpPrior(x, uy, 2, pt, out=fitm, ru_theta=0.05, eps=1e-3)
+        assert np.allclose(pri["theta0"], fitm["best_theta"]) and np.all(np.linalg.eigvalsh(pri["Sigma0"]) > 0)
+    fitGP = api.fitExpGP(x, y, uy, dataType=2, Nn=10, gridType="internal", method="sample", theta0=pri["theta0"],
+                         Sigma0=pri["Sigma0"], lambda_rate=0.1, rho_scale=0, nb_warmup=150, nb_iter=300, prior_PD=0)
+    brGP = api.printBr(fitGP["fit"], N=x.size, silent=True)
+    assert brGP["br"] < br["br"] and brGP["alert"] is None   # the GP-modulated model repairs the fit
+
+
+def test_fitoct_batch_driver_and_scale(L):
+    from fitoct_b200 import api
+    import time
+    n = 1000
+    S = synth.make_profiles(n)
+    xy = abi.make_problems_dense(S["x"], S["Y"], np.ones_like(S["Y"]), np.tile([0.0, 0.0, 1.0], (n, 1)),
+                                 np.tile(np.eye(3), (n, 1, 1)), Nn=0)
+    t0 = time.perf_counter()
+    g = L.estimate_noise(xy, n, df=15.0)
+    dt = time.perf_counter() - t0
+    assert np.all(g["status"] == 0) and np.max(np.abs(g["info"][:, 2] - 15.0)) < 1e-9
+    a = g["theta"]
+    assert abs(np.median(a[:, 0]) - 22.4) < 2.5 and abs(np.median(a[:, 1]) - 300) < 40
+    print(f"estimate_noise: {n} profiles in {dt * 1e3:.1f} ms end to end")
+    out = api.FitOCT_batch(S["x"], S["Y"][:40], dict(nb_warmup=100, nb_sample=100, Nn=10, priorType="abc"), chains=4)
+    kinds = S["mod_kind"][:40]
+    # the gate passes (nearly) every unmodulated profile and stops the strongly modulated ones
+    assert np.mean(out["alert"][kinds == 0]) <= 0.25 and np.mean(out["alert"][kinds == 1]) >= 0.75
+    k = out["n_expgp"]
+    assert k == int(out["alert"].sum()) and out["expgp"]["summary"].shape[0] == k
+    assert np.all(np.isfinite(out["expgp"]["summary"][:, :, 0]))
