@@ -5,7 +5,10 @@
 // and foct_pipeline(), the body of FitOCT.R's dataset loop for a whole batch (noise -> MonoExp MAP -> gate -> prior ->
 // fitExpGP on the gated profiles).  One warp per profile; the banded spline algebra lives in shared memory.
 // No CPU compute path: every entry point but foct_birge_ci (a scalar function of ndf) needs a CUDA device.
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -89,58 +92,76 @@ __device__ __forceinline__ double wsum(double v) {
   return v;
 }
 
-// Banded symmetric storage M[d*nk + j] = M_{j,j+d}, d = 0..3.  Lane 0: LDL^T of XtX + lam*Om, solve for the
-// coefficients, band of the inverse (Takahashi recurrence), df = tr[(XtX + lam Om)^-1 XtX].  Returned to all lanes.
-__device__ double spl_fit(int nk, const double* XtX, const double* Om, const double* Xty, double* L, double* Z, double* c,
+// Banded symmetric storage M[d*nk + j] = M_{j,j+d}, d = 0..3.  Lane 0 factors XtX + lam*Om = L D L^T, solves for the
+// coefficients and accumulates df = tr[(XtX + lam Om)^-1 XtX] from the band of the inverse (Takahashi recurrence).
+// Two sweeps with every recurrence carried in registers (a window of three columns), so the dependent chain per column
+// is a few FMAs and one division instead of ~40 shared-memory round trips:
+//   up:   column j of L and d, fused with the forward substitution;   stores l1,l2,l3,d,w=z/d per column
+//   down: back substitution fused with the inverse band (6-value window) and the trace
+// Ls: [5*nk] = l1 | l2 | l3 | d | w.  Returns df to all lanes; the coefficients are left in c.
+__device__ double spl_fit(int nk, const double* XtX, const double* Om, const double* Xty, double* Ls, double* c,
                           double lam, int lane) {
   double df = 0.0;
   if (lane == 0) {
-#define AB(d, j) (XtX[(d) * nk + (j)] + lam * Om[(d) * nk + (j)])
+    double* l1 = Ls; double* l2 = Ls + nk; double* l3 = Ls + 2 * nk; double* dd = Ls + 3 * nk; double* w = Ls + 4 * nk;
+    // window: columns j-1 (a), j-2 (b), j-3 (e)
+    double a1 = 0, a2 = 0, a3 = 0, ad = 0, b2 = 0, b3 = 0, bd = 0, e3 = 0, ed = 0;
+    double za = 0, zb = 0, ze = 0;  // z_{j-1}, z_{j-2}, z_{j-3}
     for (int j = 0; j < nk; ++j) {
-      double dj = AB(0, j);
-      for (int k = (j - 3 > 0 ? j - 3 : 0); k < j; ++k) {
-        const double ljk = L[(j - k) * nk + k];
-        dj -= ljk * ljk * L[k];
-      }
-      L[j] = dj;
-      for (int i = j + 1; i <= j + 3 && i < nk; ++i) {
-        double s = AB(i - j, j);
-        for (int k = (i - 3 > 0 ? i - 3 : 0); k < j; ++k) s -= L[(i - k) * nk + k] * L[(j - k) * nk + k] * L[k];
-        L[(i - j) * nk + j] = s / dj;
-      }
+      const double A0 = XtX[j] + lam * Om[j];
+      const double A1 = XtX[nk + j] + lam * Om[nk + j];
+      const double A2 = XtX[2 * nk + j] + lam * Om[2 * nk + j];
+      const double A3 = XtX[3 * nk + j] + lam * Om[3 * nk + j];
+      double dj = A0;
+      dj -= e3 * e3 * ed;
+      dj -= b2 * b2 * bd;
+      dj -= a1 * a1 * ad;
+      double s1 = A1;
+      s1 -= b3 * b2 * bd;
+      s1 -= a2 * a1 * ad;
+      double s2 = A2;
+      s2 -= a3 * a1 * ad;
+      const double n1 = j + 1 < nk ? s1 / dj : 0.0;
+      const double n2 = j + 2 < nk ? s2 / dj : 0.0;
+      const double n3 = j + 3 < nk ? A3 / dj : 0.0;
+      double z = Xty[j];
+      z -= e3 * ze;
+      z -= b2 * zb;
+      z -= a1 * za;
+      l1[j] = n1; l2[j] = n2; l3[j] = n3; dd[j] = dj; w[j] = z / dj;
+      e3 = b3; ed = bd; b2 = a2; b3 = a3; bd = ad; a1 = n1; a2 = n2; a3 = n3; ad = dj;
+      ze = zb; zb = za; za = z;
     }
-#undef AB
-    for (int i = 0; i < nk; ++i) {
-      double s = Xty[i];
-      for (int k = (i - 3 > 0 ? i - 3 : 0); k < i; ++k) s -= L[(i - k) * nk + k] * c[k];
-      c[i] = s;
-    }
-    for (int i = 0; i < nk; ++i) c[i] /= L[i];
+    // window of the inverse band on rows/cols i+1..i+3, and of the coefficients
+    double z11 = 0, z12 = 0, z13 = 0, z22 = 0, z23 = 0, z33 = 0, c1 = 0, c2 = 0, c3 = 0;
     for (int i = nk - 1; i >= 0; --i) {
-      double s = c[i];
-      for (int k = i + 1; k <= i + 3 && k < nk; ++k) s -= L[(k - i) * nk + i] * c[k];
-      c[i] = s;
+      const double m1 = l1[i], m2 = l2[i], m3 = l3[i];
+      double ci = w[i];
+      ci -= m1 * c1;
+      ci -= m2 * c2;
+      ci -= m3 * c3;
+      c[i] = ci;
+      double y3 = 0.0;  // Z_{i,i+3}
+      y3 -= m1 * z13; y3 -= m2 * z23; y3 -= m3 * z33;
+      double y2 = 0.0;  // Z_{i,i+2}
+      y2 -= m1 * z12; y2 -= m2 * z22; y2 -= m3 * z23;
+      double y1 = 0.0;  // Z_{i,i+1}
+      y1 -= m1 * z11; y1 -= m2 * z12; y1 -= m3 * z13;
+      double y0 = 1.0 / dd[i];  // Z_{i,i}
+      y0 -= m1 * y1; y0 -= m2 * y2; y0 -= m3 * y3;
+      df += y0 * XtX[i];
+      if (i + 1 < nk) df += 2.0 * y1 * XtX[nk + i];
+      if (i + 2 < nk) df += 2.0 * y2 * XtX[2 * nk + i];
+      if (i + 3 < nk) df += 2.0 * y3 * XtX[3 * nk + i];
+      z33 = z22; z23 = z12; z22 = z11; z13 = y2; z12 = y1; z11 = y0;
+      c3 = c2; c2 = c1; c1 = ci;
     }
-    for (int i = nk - 1; i >= 0; --i) {
-      const int jmax = i + 3 < nk - 1 ? i + 3 : nk - 1;
-      for (int j = jmax; j >= i; --j) {
-        double s = (i == j) ? 1.0 / L[i] : 0.0;
-        for (int k = i + 1; k <= jmax; ++k) {
-          const double zkj = k <= j ? Z[(j - k) * nk + k] : Z[(k - j) * nk + j];
-          s -= L[(k - i) * nk + i] * zkj;
-        }
-        Z[(j - i) * nk + i] = s;
-      }
-    }
-    for (int j = 0; j < nk; ++j) df += Z[j] * XtX[j];
-    for (int d = 1; d <= 3; ++d)
-      for (int j = 0; j + d < nk; ++j) df += 2.0 * Z[d * nk + j] * XtX[d * nk + j];
   }
   __syncwarp();
   return __shfl_sync(PREP_FULL, df, 0);
 }
 
-// One warp per profile.  Shared memory per CTA: (19*nkmax + 4) doubles.
+// One warp per profile.  Shared memory per CTA: (16*nkmax + 4) doubles: T | XtX 4 | Om 4 | Xty | L 5 | c.
 __global__ void __launch_bounds__(32) noise_kernel(const double* __restrict__ up, const PrepMeta* __restrict__ meta, int n,
                                                    int nkmax, double df_target, double max_rate, double* __restrict__ uy,
                                                    double* __restrict__ ys, double* __restrict__ theta,
@@ -151,9 +172,8 @@ __global__ void __launch_bounds__(32) noise_kernel(const double* __restrict__ up
   double* XtX = T + nkmax + 4;
   double* Om = XtX + 4 * nkmax;
   double* Xty = Om + 4 * nkmax;
-  double* L = Xty + nkmax;
-  double* Z = L + 4 * nkmax;
-  double* c = Z + 4 * nkmax;
+  double* L = Xty + nkmax;   // l1 | l2 | l3 | d | w per column
+  double* c = L + 5 * nkmax;
   for (int j = blockIdx.x; j < n; j += gridDim.x) {
     const PrepMeta M = meta[j];
     const int N = M.N, nkn = M.nknots, nk = nkn + 2;
@@ -240,19 +260,19 @@ __global__ void __launch_bounds__(32) noise_kernel(const double* __restrict__ up
     int evals = 0;
     {
       double sa = -1.5, sb = 1.5;
-      double fa = spl_fit(nk, XtX, Om, Xty, L, Z, c, r * pow(256.0, 3.0 * sa - 1.0), lane) - df_target;
+      double fa = spl_fit(nk, XtX, Om, Xty, L, c, r * pow(256.0, 3.0 * sa - 1.0), lane) - df_target;
       ++evals;
       if (fa <= 0.0) {
         spar = sa; dfv = fa + df_target;
       } else {
-        double fb = spl_fit(nk, XtX, Om, Xty, L, Z, c, r * pow(256.0, 3.0 * sb - 1.0), lane) - df_target;
+        double fb = spl_fit(nk, XtX, Om, Xty, L, c, r * pow(256.0, 3.0 * sb - 1.0), lane) - df_target;
         ++evals;
         spar = sb; dfv = fb + df_target;
         if (fb < 0.0) {
           int side = 0;
           for (int it = 0; it < 100; ++it) {
             const double sc = (sa * fb - sb * fa) / (fb - fa);
-            const double fc = spl_fit(nk, XtX, Om, Xty, L, Z, c, r * pow(256.0, 3.0 * sc - 1.0), lane) - df_target;
+            const double fc = spl_fit(nk, XtX, Om, Xty, L, c, r * pow(256.0, 3.0 * sc - 1.0), lane) - df_target;
             ++evals;
             spar = sc; dfv = fc + df_target;
             if (fabs(fc) <= 1e-10) break;
@@ -438,6 +458,20 @@ static double chisq_quantile(double p, double ndf) {
   return x;
 }
 
+// FOCT_TRACE=1: host-phase wall times of the prep entry points on stderr
+struct Trace {
+  bool on;
+  const char* what;
+  std::chrono::steady_clock::time_point t0;
+  explicit Trace(const char* w) : on(std::getenv("FOCT_TRACE") != nullptr), what(w), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* phase) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[foct trace] %s: %s %.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 struct PrepUpload {
   std::vector<double> up;
   std::vector<PrepMeta> meta;
@@ -556,15 +590,17 @@ extern "C" int foct_estimate_noise(const foct_problem* P, int n, double df, doub
   if (!uy || !ySmooth || !theta) return fail(FOCT_EINVAL, "NULL output");
   if (!(df > 1.0)) return fail(FOCT_EINVAL, "df=%g must exceed 1", df);
   if (!(max_rate > 0.0)) max_rate = 1e4;
+  Trace tr("foct_estimate_noise");
   PrepUpload U;
   if (int rc = prep_upload(P, n, U)) return rc;
+  tr.mark("pack + upload");
   for (int j = 0; j < n; ++j)
     if (df > (double)(U.meta[j].nknots + 2)) return fail(FOCT_EINVAL, "problem %d: df=%g exceeds the %d spline coefficients", j, df, U.meta[j].nknots + 2);
   DevBuf d_uy, d_ys, d_th, d_info, d_st;
 #define CUP(call) if ((call) != cudaSuccess) return fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError()))
   CUP(d_uy.alloc(U.total * 8)); CUP(d_ys.alloc(U.total * 8)); CUP(d_th.alloc(2 * (size_t)n * 8));
   CUP(d_info.alloc(4 * (size_t)n * 8)); CUP(d_st.alloc((size_t)n * sizeof(int)));
-  const size_t smem = (19 * (size_t)U.nkmax + 4) * sizeof(double);
+  const size_t smem = (16 * (size_t)U.nkmax + 4) * sizeof(double);
   if (smem > 200 * 1024) return fail(FOCT_EINVAL, "profile too long: %d spline coefficients do not fit in shared memory", U.nkmax);
   CUP(cudaFuncSetAttribute(noise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
@@ -573,13 +609,16 @@ extern "C" int foct_estimate_noise(const foct_problem* P, int n, double df, doub
   const int grid = std::min(n, sms * 16);
   noise_kernel<<<grid, 32, smem>>>(U.d_up, U.d_meta, n, U.nkmax, df, max_rate, d_uy.as<double>(), d_ys.as<double>(),
                                    d_th.as<double>(), d_info.as<double>(), d_st.as<int>());
+  tr.mark("alloc + launch");
   CUP(cudaGetLastError());
   CUP(cudaDeviceSynchronize());
+  tr.mark("kernel");
   CUP(cudaMemcpy(uy, d_uy.p, U.total * 8, cudaMemcpyDeviceToHost));
   CUP(cudaMemcpy(ySmooth, d_ys.p, U.total * 8, cudaMemcpyDeviceToHost));
   CUP(cudaMemcpy(theta, d_th.p, 2 * (size_t)n * 8, cudaMemcpyDeviceToHost));
   if (info) CUP(cudaMemcpy(info, d_info.p, 4 * (size_t)n * 8, cudaMemcpyDeviceToHost));
   if (status) CUP(cudaMemcpy(status, d_st.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  tr.mark("download");
 #undef CUP
   return 0;
 }
