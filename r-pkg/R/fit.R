@@ -70,3 +70,38 @@ fitMonoExp <- function(x, y, uy, dataType = 2) {
                   return_code = r$status),
        method = "optim")
 }
+
+# FitOCTLib::estimateNoise (FitOCT.R:89-91): smooth.spline at `df`, then uy = a_1 exp(-x/a_2) fitted to the residuals
+estimateNoise <- function(x, y, df = 15, maxRate = 10000) {
+  r <- .Call("foct_R_estimate_noise", as.numeric(x), as.numeric(y), as.numeric(df), as.numeric(maxRate),
+             PACKAGE = "FitOCTb200")
+  list(fit = list(par = list(theta = r$theta), spar = r$info[1], lambda = r$info[2], df = r$info[3], return_code = r$status),
+       theta = r$theta, uy = r$uy, ySmooth = r$ySmooth, method = "optim")
+}
+
+# FitOCTLib::printBr (plotMonoExp.R:10, plotExpGP.R:22): NULL alert <=> fit OK (the gate at FitOCT.R:100)
+printBr <- function(fit, silent = FALSE) {
+  if (inherits(fit, "stanfit")) {
+    br  <- mean(rstan::extract(fit, "br")[[1]])
+    N   <- length(grep("^resid\\[", names(fit)))   # not saved by this back-end: pass the data length via attr(fit, "N")
+    if (N == 0) N <- attr(fit, "N")
+    np  <- length(grep("^(theta|yGP)\\[", names(fit)))
+  } else {
+    br <- fit$par$br; N <- length(fit$par$resid); np <- length(fit$par$theta) + length(fit$par$yGP)
+  }
+  ci    <- .Call("foct_R_birge_ci", as.numeric(N - np), PACKAGE = "FitOCTb200")
+  alert <- if (br < ci[1] || br > ci[2]) "!!! WARNING !!! br out of interval" else NULL
+  if (!silent) {
+    cat("br   :", signif(br, 2), "\n"); cat("CI95 :", paste0(signif(ci, 2), collapse = "-"), "\n")
+    if (!is.null(alert)) cat(alert, "\n")
+  }
+  list(br = br, CI95 = ci, alert = alert)
+}
+
+# FitOCTLib::estimateExpPrior (FitOCT.R:103-107)
+estimateExpPrior <- function(x, uy, dataType, priorType = "mono", out, ru_theta = 0.05, eps = 1e-3) {
+  fit <- out$fit
+  .Call("foct_R_exp_prior", as.numeric(x), as.numeric(fit$par$m + fit$par$resid), as.numeric(uy), as.integer(dataType),
+        as.integer(priorType == "abc"), as.numeric(out$best.theta), as.numeric(fit$hessian), as.numeric(ru_theta),
+        PACKAGE = "FitOCTb200")
+}

@@ -150,10 +150,72 @@ SEXP foct_R_expgp_map(SEXP x, SEXP y, SEXP uy, SEXP ctl) {
   return out;
 }
 
+/* .Call("foct_R_estimate_noise", x, y, df, maxRate) -> list(uy, ySmooth, theta, info, status): FitOCTLib::estimateNoise
+ * (FitOCT.R:89-91) */
+SEXP foct_R_estimate_noise(SEXP x, SEXP y, SEXP df, SEXP maxRate) {
+  foct_problem P;
+  memset(&P, 0, sizeof(P));
+  P.N = (int)XLENGTH(x);
+  P.x = REAL(x); P.y = REAL(y); P.uy = NULL;
+  P.dataType = 2;
+  SEXP uy = PROTECT(Rf_allocVector(REALSXP, P.N)), ys = PROTECT(Rf_allocVector(REALSXP, P.N));
+  SEXP th = PROTECT(Rf_allocVector(REALSXP, 2)), info = PROTECT(Rf_allocVector(REALSXP, 4));
+  SEXP st = PROTECT(Rf_allocVector(INTSXP, 1));
+  int rc = foct_estimate_noise(&P, 1, Rf_asReal(df), Rf_asReal(maxRate), REAL(uy), REAL(ys), REAL(th), REAL(info), INTEGER(st));
+  if (rc) {
+    UNPROTECT(5);
+    Rf_error("fitoct_b200 error %d: %s", rc, foct_last_error());
+  }
+  const char* nm[] = {"uy", "ySmooth", "theta", "info", "status", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
+  SET_VECTOR_ELT(out, 0, uy); SET_VECTOR_ELT(out, 1, ys); SET_VECTOR_ELT(out, 2, th);
+  SET_VECTOR_ELT(out, 3, info); SET_VECTOR_ELT(out, 4, st);
+  UNPROTECT(6);
+  return out;
+}
+
+/* .Call("foct_R_birge_ci", ndf) -> c(lo, hi): the interval FitOCTLib::printBr compares br with (plotMonoExp.R:10) */
+SEXP foct_R_birge_ci(SEXP ndf) {
+  SEXP ci = PROTECT(Rf_allocVector(REALSXP, 2));
+  int rc = foct_birge_ci(Rf_asReal(ndf), REAL(ci));
+  if (rc) {
+    UNPROTECT(1);
+    Rf_error("fitoct_b200 error %d: %s", rc, foct_last_error());
+  }
+  UNPROTECT(1);
+  return ci;
+}
+
+/* .Call("foct_R_exp_prior", x, y, uy, dataType, priorType, theta, hessian, ru_theta) -> list(theta0, Sigma0, ru):
+ * FitOCTLib::estimateExpPrior (FitOCT.R:103-107); y = m + resid of the MonoExp fit */
+SEXP foct_R_exp_prior(SEXP x, SEXP y, SEXP uy, SEXP dataType, SEXP priorType, SEXP theta, SEXP hessian, SEXP ru_theta) {
+  foct_problem P;
+  memset(&P, 0, sizeof(P));
+  P.N = (int)XLENGTH(x);
+  P.x = REAL(x); P.y = REAL(y); P.uy = REAL(uy);
+  P.dataType = Rf_asInteger(dataType);
+  SEXP t0 = PROTECT(Rf_allocVector(REALSXP, 3)), S0 = PROTECT(Rf_allocMatrix(REALSXP, 3, 3));
+  SEXP ru = PROTECT(Rf_allocVector(REALSXP, 1));
+  int rc = foct_estimate_exp_prior(&P, 1, Rf_asInteger(priorType), REAL(theta), REAL(hessian), Rf_asReal(ru_theta),
+                                   REAL(t0), REAL(S0), REAL(ru));
+  if (rc) {
+    UNPROTECT(3);
+    Rf_error("fitoct_b200 error %d: %s", rc, foct_last_error());
+  }
+  const char* nm[] = {"theta0", "Sigma0", "ru", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
+  SET_VECTOR_ELT(out, 0, t0); SET_VECTOR_ELT(out, 1, S0); SET_VECTOR_ELT(out, 2, ru);
+  UNPROTECT(4);
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"foct_R_sample", (DL_FUNC)&foct_R_sample, 5},
     {"foct_R_monoexp_map", (DL_FUNC)&foct_R_monoexp_map, 4},
     {"foct_R_expgp_map", (DL_FUNC)&foct_R_expgp_map, 4},
+    {"foct_R_estimate_noise", (DL_FUNC)&foct_R_estimate_noise, 4},
+    {"foct_R_birge_ci", (DL_FUNC)&foct_R_birge_ci, 1},
+    {"foct_R_exp_prior", (DL_FUNC)&foct_R_exp_prior, 8},
     {NULL, NULL, 0}};
 
 void R_init_FitOCTb200(DllInfo* dll) {
