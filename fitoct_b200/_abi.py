@@ -132,6 +132,62 @@ class PipelineOut(C.Structure):
     ]
 
 
+class VbCfg(C.Structure):
+    """foct_vb_cfg: rstan::vb's arguments (MODEL_SPEC §14)."""
+    _fields_ = [
+        ("iter", C.c_int),
+        ("grad_samples", C.c_int),
+        ("elbo_samples", C.c_int),
+        ("eval_elbo", C.c_int),
+        ("output_samples", C.c_int),
+        ("adapt_engaged", C.c_int),
+        ("adapt_iter", C.c_int),
+        ("eta", C.c_double),
+        ("tol_rel_obj", C.c_double),
+        ("seed", C.c_ulonglong),
+        ("init_mode", C.c_int),
+        ("init", c_double_p),
+        ("omega0", C.c_double),
+    ]
+
+
+class VbResult(C.Structure):
+    _fields_ = [
+        ("mean", c_double_p),
+        ("draws", c_double_p),
+        ("mu", c_double_p),
+        ("omega", c_double_p),
+        ("elbo", c_double_p),
+        ("eta", c_double_p),
+        ("iters", c_int_p),
+        ("status", c_int_p),
+    ]
+
+
+def default_vb_cfg(**kw) -> VbCfg:
+    """rstan::vb defaults; kept in step with foct_vb_cfg_default (tests/test_abi.py)."""
+    c = VbCfg(iter=10000, grad_samples=1, elbo_samples=100, eval_elbo=100, output_samples=1000, adapt_engaged=1,
+              adapt_iter=50, eta=1.0, tol_rel_obj=0.01, seed=1234, init_mode=0, omega0=0.0)
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise TypeError(f"unknown vb key {k}")
+        setattr(c, k, v)
+    return c
+
+
+def alloc_vb_result(kind: int, n: int, Nn: int, cfg: VbCfg, draws=True):
+    D, P_out = dims(kind, Nn)
+    out = dict(mean=np.full((n, P_out), np.nan), draws=np.full((n, cfg.output_samples, P_out), np.nan) if draws else None,
+               mu=np.full((n, D), np.nan), omega=np.full((n, D), np.nan), elbo=np.full(n, np.nan), eta=np.full(n, np.nan),
+               iters=np.zeros(n, dtype=np.int32), status=np.full(n, -1, dtype=np.int32))
+    R = VbResult()
+    for k, v in out.items():
+        if v is None:
+            continue
+        setattr(R, k, v.ctypes.data_as(c_int_p) if v.dtype == np.int32 else as_ptr(v))
+    return out, R
+
+
 def dims(kind: int, Nn: int) -> tuple[int, int]:
     """(D unconstrained dims, P_out output columns) — MODEL_SPEC §2, §6."""
     if kind == FOCT_EXPGP:

@@ -22,7 +22,7 @@ EXPORTS = (
     "foct_monoexp_sample", "foct_monoexp_map", "foct_expgp_map", "foct_predict", "foct_plan_create", "foct_plan_run",
     "foct_plan_sync", "foct_plan_timing", "foct_plan_fetch", "foct_plan_destroy", "foct_fp64_peak",
     "foct_estimate_noise", "foct_birge_ci", "foct_print_br", "foct_estimate_exp_prior", "foct_pipeline_cfg_default",
-    "foct_pipeline",
+    "foct_pipeline", "foct_vb_cfg_default", "foct_vb",
 )
 
 _LIB = None
@@ -75,6 +75,9 @@ def lib():
         L.foct_estimate_exp_prior.argtypes = [PP, C.c_int, C.c_int, dp, dp, C.c_double, dp, dp, dp]
         L.foct_pipeline_cfg_default.argtypes = [C.POINTER(abi.PipelineCfg)]
         L.foct_pipeline_cfg_default.restype = None
+        L.foct_vb_cfg_default.argtypes = [C.POINTER(abi.VbCfg)]
+        L.foct_vb_cfg_default.restype = None
+        L.foct_vb.argtypes = [C.c_int, PP, C.c_int, MS, C.POINTER(abi.VbCfg), C.POINTER(abi.VbResult)]
         L.foct_pipeline.argtypes = [PP, C.c_int, C.POINTER(abi.PipelineCfg), MS, SC, C.POINTER(abi.PipelineOut)]
         _LIB = L
     return _LIB
@@ -318,3 +321,13 @@ def pipeline(batch: abi.ProblemBatch, n_problems: int, pcfg: abi.PipelineCfg, cf
     o["expgp_index"] = o["expgp_index"][:k]
     o["expgp"] = {name: (v[:k] if v is not None else None) for name, v in res.items()}
     return o
+
+
+# ---- method = 'vb' (MODEL_SPEC §14) ----
+def vb(kind: int, batch: abi.ProblemBatch, n_problems: int, spec: abi.ModelSpec, cfg: abi.VbCfg, draws=True):
+    """Mean-field ADVI for a batch.  Returns dict(mean [n,P_out], draws [n,output_samples,P_out], mu, omega [n,D], elbo, eta,
+    iters, status [n])."""
+    Nn = batch.array[0].Nn if kind == abi.FOCT_EXPGP else 0
+    out, R = abi.alloc_vb_result(kind, n_problems, Nn, cfg, draws)
+    check(lib().foct_vb(kind, batch.array, n_problems, C.byref(spec), C.byref(cfg), C.byref(R)))
+    return out

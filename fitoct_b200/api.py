@@ -139,10 +139,39 @@ def fitExpGP(x, y, uy, dataType=2, Nn=10, gridType="internal", method="sample", 
         raise ValueError("theta0 and Sigma0 are required (estimateExpPrior output, FitOCT.R:103-107)")
     if method not in ("sample", "optim", "vb"):
         raise ValueError("method must be one of 'sample', 'optim', 'vb' (FitOCT.R:42)")
-    if method == "vb":
-        raise NotImplementedError("method='vb': SURVEY §8(f) row N4 ('next'); 'sample' and 'optim' are implemented")
     spec = spec or abi.default_spec(abi.FOCT_EXPGP)
     control = control or {}
+    if method == "vb":
+        # Stan's mean-field ADVI (MODEL_SPEC §14).  rstan::vb's arguments pass through `control`.  omega0: Stan starts the
+        # approximation at unit standard deviations (omega = 0), where this model's draws have 1 + dL <= 0 and ADVI stops with
+        # "dropped evaluations"; the mirror starts narrower unless told otherwise (control = dict(omega0 = 0) is Stan's).
+        vcfg = abi.default_vb_cfg(seed=int(seed), omega0=float(control.get("omega0", -3.0)),
+                                  **{k: control[k] for k in ("iter", "grad_samples", "elbo_samples", "eval_elbo", "output_samples",
+                                                             "adapt_engaged", "adapt_iter", "eta", "tol_rel_obj") if k in control})
+        keep = None
+        if init is not None:
+            keep = np.ascontiguousarray(init, dtype=np.float64).reshape(1, Nn + 5)
+            vcfg.init_mode = 2
+            vcfg.init = abi.as_ptr(keep)
+        batch = abi.make_problems([_one_problem(x, y, uy, dataType, Nn, gridType, theta0, Sigma0, lambda_rate,
+                                                resolve_rho(rho_scale, Nn), prior_PD)])
+        o = L.vb(abi.FOCT_EXPGP, batch, 1, spec, vcfg, draws=True)
+        if o["status"][0] == 2:
+            raise RuntimeError("fitExpGP(method='vb'): ADVI failed (non-finite gradient / ELBO, or all proposed step sizes "
+                               "failed) — Stan reports the same as 'dropped evaluations'")
+        ns = vcfg.output_samples
+        d = o["draws"][0]
+        # rstan's table for a vb fit: independent draws, so se_mean = sd/sqrt(n), n_eff = n, no Rhat
+        tab = np.column_stack([d.mean(0), d.std(0, ddof=1) / np.sqrt(ns), d.std(0, ddof=1),
+                               *np.quantile(d, [0.025, 0.25, 0.5, 0.75, 0.975], axis=0), np.full(d.shape[1], float(ns)),
+                               np.full(d.shape[1], np.nan), np.full(d.shape[1], float(ns))])
+        fit = StanFit(par_names=abi.param_names(abi.FOCT_EXPGP, Nn), draws=o["draws"][0][:, None, :],
+                      sampler_params=np.zeros((ns, 1, 6)), n_warmup=0, n_iter=ns, save_warmup=False,
+                      summary_table=tab, stepsize=np.array([o["eta"][0]]), inv_metric=np.exp(2 * o["omega"][0])[None, :],
+                      n_divergent=np.zeros(1))
+        fit.vb = dict(mean=o["mean"][0], mu=o["mu"][0], omega=o["omega"][0], elbo=float(o["elbo"][0]), eta=float(o["eta"][0]),
+                      iterations=int(o["iters"][0]), converged=bool(o["status"][0] == 0))
+        return dict(fit=fit, method=method, xGP=L.grid(Nn, _grid_code(gridType)), prior_PD=prior_PD)
     if method == "optim":
         # MAP + Hessian (MODEL_SPEC §10): the Shiny default (ui.R:107-114); consumers plotExpGP.R:13-17, server.R:164-173
         batch = abi.make_problems([_one_problem(x, y, uy, dataType, Nn, gridType, theta0, Sigma0, lambda_rate,

@@ -156,6 +156,187 @@ __global__ void __launch_bounds__(32) map_bfgs_kernel(const MapParams K) {
   }
 }
 
+// method = 'vb': Stan's mean-field ADVI (MODEL_SPEC §14; FitOCT.R:42), one warp per profile, lane d owns component d of
+// mu / omega and of the step-size history.  Every Monte-Carlo draw costs one fused log-density + gradient sweep; the
+// draws come from per-site Philox counters, so the CPU checker consumes the same variates.
+template <int NN, int MOD>
+__global__ void __launch_bounds__(32) vb_kernel(const VbParams K) {
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t mbar;
+  __shared__ DevProblem s_prob;
+  using DM = Dims<NN>;
+  constexpr int D = DM::D;
+  constexpr int P_OUT = DM::P_OUT;
+  constexpr uint32_t SITE_VB_GRAD = 5, SITE_VB_ELBO = 6, SITE_VB_OUT = 7;
+  const int lane = threadIdx.x;
+  const bool act = lane < D;
+  mbar_init(&mbar);
+  uint32_t phase_bit = 0;
+  for (int j = blockIdx.x; j < K.n_problems; j += gridDim.x) {
+    if (lane == 0) s_prob = K.probs[j];
+    stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase_bit);
+    __syncthreads();
+    const DevProblem& P = s_prob;
+    Rng rng;
+    rng.seed(K.seed, P.id, 0);
+    uint32_t rb[4];
+    auto draw = [&](double mu, double om, uint32_t it, uint32_t kind, uint32_t a, uint32_t ph, double& eta) -> double {
+      eta = 0.0;
+      if (!act) return 0.0;
+      rng.block(it, kind, a, (uint32_t)lane, ph, rb);
+      eta = normal_from(rb);
+      return mu + exp(om) * eta;
+    };
+    // gradient estimate; returns true when a draw was non-finite
+    auto grad = [&](double mu, double om, uint32_t it, uint32_t ph, double& gmu, double& gom) -> bool {
+      gmu = 0.0; gom = 0.0;
+      bool bad = false;
+      for (int s = 0; s < K.grad_samples; ++s) {
+        double eta;
+        const double zeta = draw(mu, om, it, SITE_VB_GRAD, (uint32_t)s, ph, eta);
+        const Eval ev = warp_logp_grad<NN, MOD>(smem, P, K.spec, zeta, lane);
+        bad |= !isfinite(ev.lp) || __any_sync(FOCT_FULL, act && !isfinite(ev.g));
+        if (act) { gmu += ev.g; gom += ev.g * eta; }
+      }
+      gmu /= K.grad_samples; gom /= K.grad_samples;
+      gom = act ? gom * exp(om) + 1.0 : 0.0;
+      return bad;
+    };
+    auto elbo_est = [&](double mu, double om, uint32_t it, uint32_t ph) -> double {
+      double sum = 0.0;
+      int ok = 0, dropped = 0;
+      for (uint32_t a = 0; ok < K.elbo_samples; ++a) {
+        double eta;
+        const double zeta = draw(mu, om, it, SITE_VB_ELBO, a, ph, eta);
+        const Eval ev = warp_logp_grad<NN, MOD>(smem, P, K.spec, zeta, lane);
+        if (isfinite(ev.lp)) { sum += ev.lp; ++ok; }
+        else if (++dropped >= K.elbo_samples) return CUDART_NAN;
+      }
+      const double ent = 0.5 * D * (1.0 + 1.8378770664093454836) + warp_sum(act ? om : 0.0);
+      return sum / K.elbo_samples + ent;
+    };
+    auto step = [&](double& mu, double& om, double& hmu, double& hom, double gmu, double gom, int k, double eta_s) {
+      const double sc = eta_s / sqrt((double)k);
+      hmu = k == 1 ? gmu * gmu : 0.9 * hmu + 0.1 * gmu * gmu;
+      hom = k == 1 ? gom * gom : 0.9 * hom + 0.1 * gom * gom;
+      if (act) {
+        mu += sc * gmu / (1.0 + sqrt(hmu));
+        om += sc * gom / (1.0 + sqrt(hom));
+      }
+    };
+    // start (init_mode as the sampler's, MODEL_SPEC §7)
+    double q0 = 0.0;
+    if (act) {
+      rng.block(0, SITE_INIT, 0, (uint32_t)lane, 0, rb);
+      if (K.init_mode == 2 && K.init) q0 = K.init[(size_t)j * D + lane];
+      else if (K.init_mode == 1) q0 = -2.0 + 4.0 * u53(rb[0], rb[1]);
+      else if (lane < 3) q0 = P.theta0[lane];
+      else if (lane < 3 + NN) q0 = 0.01 * normal_from(rb);
+      else if (lane == 3 + NN) q0 = log(0.1);
+      else q0 = 0.0;
+    }
+    double mu = q0, om = act ? K.omega0 : 0.0, hmu = 0.0, hom = 0.0, gmu, gom;
+    double eta_s = K.eta, elbo = CUDART_NAN;
+    int status = 1, iters = 0;
+    bool failed = false;
+    if (K.adapt_engaged) {
+      const double elbo_init = elbo_est(mu, om, 0, 1);
+      if (isnan(elbo_init)) failed = true;
+      double elbo_best = -CUDART_INF, eta_best = 0.0;
+      bool found = false;
+      for (int e = 0; e < 5 && !failed; ++e) {
+        const double eta_e = e == 0 ? 100.0 : e == 1 ? 10.0 : e == 2 ? 1.0 : e == 3 ? 0.1 : 0.01;
+        mu = q0; om = act ? K.omega0 : 0.0; hmu = 0.0; hom = 0.0;
+        for (int k = 1; k <= K.adapt_iter; ++k) {
+          if (grad(mu, om, (uint32_t)k, (uint32_t)(1 + e), gmu, gom)) { gmu = 0.0; gom = 0.0; }
+          step(mu, om, hmu, hom, gmu, gom, k, eta_e);
+        }
+        double el = elbo_est(mu, om, (uint32_t)K.adapt_iter, (uint32_t)(1 + e));
+        if (isnan(el)) el = -CUDART_INF;
+        if (el < elbo_best && elbo_best > elbo_init) { found = true; break; }
+        if (e < 4) { elbo_best = el; eta_best = eta_e; }
+        else if (el > elbo_init) { eta_best = eta_e; found = true; }
+      }
+      if (!found) failed = true;
+      eta_s = eta_best;
+    }
+    if (failed) {
+      status = 2; eta_s = CUDART_NAN;
+    } else {
+      mu = q0; om = act ? K.omega0 : 0.0; hmu = 0.0; hom = 0.0;
+      int cap = (int)(0.1 * K.iter / K.eval_elbo);
+      cap = cap < 2 ? 2 : (cap > 32 ? 32 : cap);
+      double cbv = 0.0;  // lane i holds entry i of the circular buffer of relative ELBO changes
+      int cbn = 0, cbpos = 0;
+      double elbo_prev;
+      elbo = 0.0;
+      int k = 1;
+      for (; k <= K.iter; ++k) {
+        if (grad(mu, om, (uint32_t)k, 0, gmu, gom)) { status = 2; break; }
+        step(mu, om, hmu, hom, gmu, gom, k, eta_s);
+        if (k % K.eval_elbo == 0) {
+          elbo_prev = elbo;
+          elbo = elbo_est(mu, om, (uint32_t)k, 0);
+          if (isnan(elbo)) { status = 2; break; }
+          const double delta = fabs((elbo_prev - elbo) / elbo);
+          if (lane == cbpos) cbv = delta;
+          cbpos = (cbpos + 1) % cap;
+          if (cbn < cap) ++cbn;
+          const bool in = lane < cbn;
+          const double mean = warp_sum(in ? cbv : 0.0) / cbn;
+          int rank = 0;  // upper median = the entry with cbn/2 entries ordered before it
+          for (int i = 0; i < cbn; ++i) {
+            const double vi = bcast(cbv, i);
+            rank += (vi < cbv) || (vi == cbv && i < lane);
+          }
+          const unsigned who = __ballot_sync(FOCT_FULL, in && rank == cbn / 2);
+          const double med = bcast(cbv, __ffs(who) - 1);
+          if (mean < K.tol_rel_obj || med < K.tol_rel_obj) { status = 0; break; }
+        }
+      }
+      iters = k > K.iter ? K.iter : k;
+    }
+    if (act) { K.mu[(size_t)j * D + lane] = mu; K.omega[(size_t)j * D + lane] = om; }
+    if (lane == 0) {
+      if (K.elbo) K.elbo[j] = elbo;
+      if (K.eta_out) K.eta_out[j] = eta_s;
+      if (K.iters) K.iters[j] = iters;
+      if (K.status) K.status[j] = status;
+    }
+    auto write_row = [&](double q, double* row) {
+      const Eval ev = warp_logp_grad<NN, MOD>(smem, P, K.spec, q, lane);
+      double v = q;
+      if (DM::GP && (lane == 3 + NN || lane == 4 + NN)) v = exp(q);
+      if (lane == D) v = P.prior_PD ? CUDART_NAN : ev.chi2 / P.br_ndf;
+      if (lane == D + 1) v = 0.0;  // lp__ = 0 in ADVI output, as Stan writes it
+      if (lane < P_OUT) row[lane] = v;
+    };
+    write_row(mu, K.mean + (size_t)j * P_OUT);
+    if (K.draws)
+      for (int i = 0; i < K.output_samples; ++i) {
+        double eta;
+        const double zeta = draw(mu, om, 0, SITE_VB_OUT, (uint32_t)i, 0, eta);
+        write_row(zeta, K.draws + ((size_t)j * K.output_samples + i) * P_OUT);
+      }
+    __syncthreads();
+  }
+}
+
+template <int NN>
+static cudaError_t launch_vb(int mod, int grid, size_t smem, cudaStream_t st, const VbParams& K) {
+  cudaError_t e;
+  if (mod == 0) {
+    e = cudaFuncSetAttribute(vb_kernel<NN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    vb_kernel<NN, 0><<<grid, 32, smem, st>>>(K);
+  } else {
+    e = cudaFuncSetAttribute(vb_kernel<NN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    vb_kernel<NN, 1><<<grid, 32, smem, st>>>(K);
+  }
+  return cudaGetLastError();
+}
+
 template <int NN>
 static cudaError_t launch_map(int mod, int grid, size_t smem, cudaStream_t st, const MapParams& K) {
   cudaError_t e;
@@ -227,7 +408,7 @@ static cudaError_t nuts_occupancy(int mod, int block, size_t smem, int* blocks_p
 
 const InstEntry* FOCT_CAT(foct_inst_, FOCT_INST_NN)() {
   static const InstEntry e = {FOCT_INST_NN, &launch_nuts<FOCT_INST_NN>, &launch_logp<FOCT_INST_NN>,
-                              &nuts_occupancy<FOCT_INST_NN>, &launch_map<FOCT_INST_NN>};
+                              &nuts_occupancy<FOCT_INST_NN>, &launch_map<FOCT_INST_NN>, &launch_vb<FOCT_INST_NN>};
   return &e;
 }
 

@@ -35,12 +35,28 @@ struct MapParams {
   int max_iter;
 };
 
+struct VbParams {  // method = 'vb' (MODEL_SPEC §14)
+  const double* blobs;
+  size_t blob_stride;
+  int npad;
+  const DevProblem* probs;
+  int n_problems;
+  DevSpec spec;
+  int iter, grad_samples, elbo_samples, eval_elbo, output_samples, adapt_engaged, adapt_iter, init_mode;
+  double eta, tol_rel_obj, omega0;
+  unsigned long long seed;
+  const double* init;  // [n_problems][D] or nullptr
+  double *mean, *draws, *mu, *omega, *elbo, *eta_out;
+  int *iters, *status;
+};
+
 struct InstEntry {
   int NN;  // 0 = mono-exponential
   cudaError_t (*launch_nuts)(int mod, int grid, int block, size_t smem, cudaStream_t st, const SamplerParams& K);
   cudaError_t (*launch_logp)(int mod, int grid, int block, size_t smem, cudaStream_t st, const LogpParams& K);
   cudaError_t (*nuts_occupancy)(int mod, int block, size_t smem, int* blocks_per_sm, int* regs);
   cudaError_t (*launch_map)(int mod, int grid, size_t smem, cudaStream_t st, const MapParams& K);
+  cudaError_t (*launch_vb)(int mod, int grid, size_t smem, cudaStream_t st, const VbParams& K);
 };
 
 // shared by the host translation units (defined in foct_lib.cu)

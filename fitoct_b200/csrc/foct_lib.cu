@@ -907,6 +907,73 @@ extern "C" int foct_expgp_map(const foct_problem* P, int n, const foct_model_spe
   return rc;
 }
 
+// ------------------------------------------------------------------ ABI: method = 'vb' (ADVI, MODEL_SPEC §14)
+extern "C" void foct_vb_cfg_default(foct_vb_cfg* c) {
+  if (!c) return;
+  std::memset(c, 0, sizeof(*c));
+  c->iter = 10000; c->grad_samples = 1; c->elbo_samples = 100; c->eval_elbo = 100; c->output_samples = 1000;
+  c->adapt_engaged = 1; c->adapt_iter = 50; c->eta = 1.0; c->tol_rel_obj = 0.01; c->seed = 1234ull; c->init_mode = 0;
+  c->init = nullptr; c->omega0 = 0.0;
+}
+
+extern "C" int foct_vb(int kind, const foct_problem* P, int n, const foct_model_spec* spec, const foct_vb_cfg* cfg,
+                       foct_vb_result* R) {
+  if (int rc = check_device()) return rc;
+  if (!cfg || !R || !R->mean || !R->mu || !R->omega) return fail(FOCT_EINVAL, "NULL cfg / result (mean, mu, omega are required)");
+  if (cfg->iter < 1 || cfg->grad_samples < 1 || cfg->elbo_samples < 1 || cfg->eval_elbo < 1 || cfg->output_samples < 0 ||
+      (cfg->adapt_engaged && cfg->adapt_iter < 1) || !(cfg->tol_rel_obj > 0.0) || (!cfg->adapt_engaged && !(cfg->eta > 0.0)))
+    return fail(FOCT_EINVAL, "vb: iter, grad_samples, elbo_samples, eval_elbo, adapt_iter >= 1; eta, tol_rel_obj > 0");
+  if (cfg->init_mode < 0 || cfg->init_mode > 2 || (cfg->init_mode == 2 && !cfg->init)) return fail(FOCT_EINVAL, "vb: bad init_mode / init");
+  int dev = 0, NN, npad;
+  size_t stride;
+  double* d_blobs;
+  DevProblem* d_probs;
+  CU(cudaGetDevice(&dev));
+  if (int rc = build_device_batch(kind, P, n, spec, dev, 0, &NN, &npad, &stride, &d_blobs, &d_probs)) return rc;
+  const int D = kind == FOCT_EXPGP ? NN + 5 : 3, P_out = kind == FOCT_EXPGP ? NN + 7 : 5;
+  const size_t nd = (size_t)n * cfg->output_samples * P_out;
+  double *d_init = nullptr, *d_mean = nullptr, *d_draws = nullptr, *d_mu = nullptr, *d_om = nullptr, *d_elbo = nullptr, *d_eta = nullptr;
+  int *d_it = nullptr, *d_st = nullptr;
+  int rc = 0;
+  do {
+#define CUB(call) if ((call) != cudaSuccess) { rc = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); break; }
+    CUB(cudaMalloc(&d_mean, (size_t)n * P_out * sizeof(double)));
+    CUB(cudaMalloc(&d_mu, (size_t)n * D * sizeof(double)));
+    CUB(cudaMalloc(&d_om, (size_t)n * D * sizeof(double)));
+    CUB(cudaMalloc(&d_elbo, (size_t)n * sizeof(double)));
+    CUB(cudaMalloc(&d_eta, (size_t)n * sizeof(double)));
+    CUB(cudaMalloc(&d_it, (size_t)n * sizeof(int)));
+    CUB(cudaMalloc(&d_st, (size_t)n * sizeof(int)));
+    if (R->draws && nd) CUB(cudaMalloc(&d_draws, nd * sizeof(double)));
+    if (cfg->init_mode == 2) {
+      CUB(cudaMalloc(&d_init, (size_t)n * D * sizeof(double)));
+      CUB(cudaMemcpy(d_init, cfg->init, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    VbParams K;
+    K.blobs = d_blobs; K.blob_stride = stride; K.npad = npad; K.probs = d_probs; K.n_problems = n; K.spec = dev_spec(*spec);
+    K.iter = cfg->iter; K.grad_samples = cfg->grad_samples; K.elbo_samples = cfg->elbo_samples; K.eval_elbo = cfg->eval_elbo;
+    K.output_samples = cfg->output_samples; K.adapt_engaged = cfg->adapt_engaged; K.adapt_iter = cfg->adapt_iter;
+    K.init_mode = cfg->init_mode; K.eta = cfg->eta; K.tol_rel_obj = cfg->tol_rel_obj; K.omega0 = cfg->omega0; K.seed = cfg->seed;
+    K.init = d_init; K.mean = d_mean; K.draws = d_draws; K.mu = d_mu; K.omega = d_om; K.elbo = d_elbo; K.eta_out = d_eta;
+    K.iters = d_it; K.status = d_st;
+    const InstEntry* inst = inst_for(NN);
+    CUB(inst->launch_vb(spec->modulation, std::min(n, 148 * 8), stride * sizeof(double), 0, K));
+    CUB(cudaDeviceSynchronize());
+    CUB(cudaMemcpy(R->mean, d_mean, (size_t)n * P_out * sizeof(double), cudaMemcpyDeviceToHost));
+    CUB(cudaMemcpy(R->mu, d_mu, (size_t)n * D * sizeof(double), cudaMemcpyDeviceToHost));
+    CUB(cudaMemcpy(R->omega, d_om, (size_t)n * D * sizeof(double), cudaMemcpyDeviceToHost));
+    if (d_draws) CUB(cudaMemcpy(R->draws, d_draws, nd * sizeof(double), cudaMemcpyDeviceToHost));
+    if (R->elbo) CUB(cudaMemcpy(R->elbo, d_elbo, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (R->eta) CUB(cudaMemcpy(R->eta, d_eta, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (R->iters) CUB(cudaMemcpy(R->iters, d_it, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (R->status) CUB(cudaMemcpy(R->status, d_st, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+#undef CUB
+  } while (0);
+  cudaFree(d_init); cudaFree(d_mean); cudaFree(d_draws); cudaFree(d_mu); cudaFree(d_om); cudaFree(d_elbo); cudaFree(d_eta);
+  cudaFree(d_it); cudaFree(d_st); cudaFree(d_blobs); cudaFree(d_probs);
+  return rc;
+}
+
 // ------------------------------------------------------------------ ABI: fp64 peak
 extern "C" int foct_fp64_peak(int device, double* tflops, double* sm_mhz) {
   if (int rc = check_device()) return rc;

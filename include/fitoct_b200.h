@@ -237,6 +237,37 @@ typedef struct foct_pipeline_out {
 int foct_pipeline(const foct_problem* P, int n_problems, const foct_pipeline_cfg* pc, const foct_model_spec* spec_gp,
                   const foct_sampler_cfg* cfg, foct_pipeline_out* out);
 
+/* ---- method = 'vb' (FitOCT.R:42; rstan::vb): Stan's mean-field ADVI, MODEL_SPEC §14 ------------------------------ */
+typedef struct foct_vb_cfg {
+  int iter;            /* 10000 */
+  int grad_samples;    /* 1 */
+  int elbo_samples;    /* 100 */
+  int eval_elbo;       /* 100 */
+  int output_samples;  /* 1000 */
+  int adapt_engaged;   /* 1 */
+  int adapt_iter;      /* 50 */
+  double eta;          /* 1.0; used as is when adapt_engaged = 0 */
+  double tol_rel_obj;  /* 0.01 */
+  unsigned long long seed;
+  int init_mode;       /* as foct_sampler_cfg.init_mode */
+  const double* init;  /* [n_problems][D] unconstrained, for init_mode 2 */
+  double omega0;       /* initial log standard deviation of every component; Stan: 0 (MODEL_SPEC §14) */
+} foct_vb_cfg;
+void foct_vb_cfg_default(foct_vb_cfg* cfg);
+
+typedef struct foct_vb_result { /* caller-allocated; mean, mu, omega required, the rest may be NULL */
+  double* mean;   /* [n][P_out] constrained mean of the approximation, br at the mean, lp__ = 0 (Stan's first CSV row) */
+  double* draws;  /* [n][output_samples][P_out] */
+  double* mu;     /* [n][D] */
+  double* omega;  /* [n][D] log standard deviations */
+  double* elbo;   /* [n] last ELBO estimate */
+  double* eta;    /* [n] step-size scale used */
+  int* iters;     /* [n] main-loop iterations done */
+  int* status;    /* [n] 0 converged, 1 iteration limit, 2 failed (non-finite gradient / ELBO, or no usable step size) */
+} foct_vb_result;
+int foct_vb(int kind, const foct_problem* P, int n_problems, const foct_model_spec* spec, const foct_vb_cfg* cfg,
+            foct_vb_result* R);
+
 /* Measured fp64 FMA throughput of the device (DFMA-chain microbenchmark), the roofline denominator for
  * the sampling kernel (MEASURED_PEAKS.json has no fp64 figure). */
 int foct_fp64_peak(int device, double* tflops, double* sm_mhz);

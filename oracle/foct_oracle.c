@@ -1207,3 +1207,4 @@ int foct_oracle_monoexp_map(const foct_problem* P, int n_problems, const foct_mo
   }
   return 0;
 }
+#include "foct_oracle_vb.c"

@@ -76,6 +76,12 @@ int foct_oracle_print_br(const double* br, int n, double ndf, double ci[2], int*
 int foct_oracle_exp_prior(const foct_problem* P, int n, int priorType, const double* theta_map, const double* hessian,
                           double ru_theta, double* theta0, double* Sigma0, double* ru_out);
 
+/* ---- method = 'vb': Stan's mean-field ADVI (foct_oracle_vb.c; MODEL_SPEC §14) ---- */
+int foct_oracle_vb(int kind, const foct_problem* P, int n_problems, const foct_model_spec* spec, const foct_vb_cfg* cfg,
+                   foct_vb_result* R);
+int foct_oracle_vb_analytic(int target, int D, const double* par, const foct_vb_cfg* cfg, const double* q0, double* mu,
+                            double* omega, double* info);
+
 #ifdef __cplusplus
 }
 #endif

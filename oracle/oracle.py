@@ -55,6 +55,9 @@ def lib():
         L.foct_oracle_qchisq.restype = C.c_double
         L.foct_oracle_print_br.argtypes = [dp, C.c_int, C.c_double, dp, ip]
         L.foct_oracle_exp_prior.argtypes = [C.POINTER(abi.Problem), C.c_int, C.c_int, dp, dp, C.c_double, dp, dp, dp]
+        L.foct_oracle_vb.argtypes = [C.c_int, C.POINTER(abi.Problem), C.c_int, C.POINTER(abi.ModelSpec), C.POINTER(abi.VbCfg),
+                                     C.POINTER(abi.VbResult)]
+        L.foct_oracle_vb_analytic.argtypes = [C.c_int, C.c_int, dp, C.POINTER(abi.VbCfg), dp, dp, dp, dp]
         L.foct_oracle_normal.argtypes = [C.POINTER(C.c_uint32)]
         L.foct_oracle_normal.restype = C.c_double
         _LIB = L
@@ -241,3 +244,21 @@ def exp_prior(batch: abi.ProblemBatch, n, priorType, theta_map, hessian, ru_thet
     _check(lib().foct_oracle_exp_prior(batch.array, n, {"mono": 0, "abc": 1}[priorType], abi.as_ptr(th), abi.as_ptr(H),
                                        float(ru_theta), abi.as_ptr(t0), abi.as_ptr(S0), abi.as_ptr(ru)), "exp_prior")
     return t0, S0, ru
+
+
+# ---- method = 'vb' (MODEL_SPEC §14) ----
+def vb(kind, batch: abi.ProblemBatch, n, spec, cfg: abi.VbCfg, draws=True):
+    Nn = batch.array[0].Nn if kind == abi.FOCT_EXPGP else 0
+    out, R = abi.alloc_vb_result(kind, n, Nn, cfg, draws)
+    _check(lib().foct_oracle_vb(kind, batch.array, n, C.byref(spec), C.byref(cfg), C.byref(R)), "vb")
+    return out
+
+
+def vb_analytic(target, par, cfg: abi.VbCfg, q0):
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    q0 = np.ascontiguousarray(q0, dtype=np.float64)
+    D = q0.size
+    mu, om, info = np.empty(D), np.empty(D), np.empty(3)
+    st = lib().foct_oracle_vb_analytic(target, D, abi.as_ptr(par), C.byref(cfg), abi.as_ptr(q0), abi.as_ptr(mu), abi.as_ptr(om),
+                                       abi.as_ptr(info))
+    return dict(mu=mu, omega=om, elbo=info[0], eta=info[1], iters=int(info[2]), status=st)

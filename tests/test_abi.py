@@ -48,6 +48,7 @@ int main(void) {
   printf("%d %d %d %d\n", FOCT_MAX_NN, FOCT_MAX_CHAINS, FOCT_N_SUMMARY_COLS, FOCT_N_SAMPLER_PARAMS);
   printf("%zu %zu %zu %zu %zu\n", sizeof(foct_pipeline_cfg), sizeof(foct_pipeline_out), offsetof(foct_pipeline_cfg, gate),
          offsetof(foct_pipeline_out, n_expgp), offsetof(foct_pipeline_out, expgp));
+  printf("%zu %zu %zu %zu\n", sizeof(foct_vb_cfg), sizeof(foct_vb_result), offsetof(foct_vb_cfg, seed), offsetof(foct_vb_cfg, omega0));
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
@@ -62,14 +63,20 @@ int main(void) {
     assert vals[4:8] == [abi.Problem.theta0.offset, abi.Problem.id.offset, abi.SamplerCfg.seed.offset,
                          abi.SamplerCfg.devices.offset]
     assert vals[8:12] == [abi.FOCT_MAX_NN, abi.FOCT_MAX_CHAINS, abi.FOCT_N_SUMMARY_COLS, abi.FOCT_N_SAMPLER_PARAMS]
-    assert vals[12:] == [C.sizeof(abi.PipelineCfg), C.sizeof(abi.PipelineOut), abi.PipelineCfg.gate.offset,
-                         abi.PipelineOut.n_expgp.offset, abi.PipelineOut.expgp.offset]
+    assert vals[12:17] == [C.sizeof(abi.PipelineCfg), C.sizeof(abi.PipelineOut), abi.PipelineCfg.gate.offset,
+                           abi.PipelineOut.n_expgp.offset, abi.PipelineOut.expgp.offset]
+    assert vals[17:] == [C.sizeof(abi.VbCfg), C.sizeof(abi.VbResult), abi.VbCfg.seed.offset, abi.VbCfg.omega0.offset]
 
 
 def test_defaults_and_dims_without_device():
     from fitoct_b200 import _lib
 
     L = _lib.lib()
+    v, w = abi.VbCfg(), abi.default_vb_cfg()
+    L.foct_vb_cfg_default(C.byref(v))
+    for name, _ in abi.VbCfg._fields_:
+        if name != "init":
+            assert getattr(v, name) == getattr(w, name), name
     assert L.foct_version() == 1
     for kind in (abi.FOCT_EXPGP, abi.FOCT_MONOEXP):
         s = abi.ModelSpec()

@@ -98,8 +98,8 @@ def test_fitExpGP_argument_errors():
         api.fitExpGP(x, x, x, theta0=None, Sigma0=None)
     with pytest.raises(ValueError):
         api.fitExpGP(x, x, x, theta0=[1, 1, 1], Sigma0=np.eye(3), method="bogus")
-    with pytest.raises(NotImplementedError):
-        api.fitExpGP(x, x + 1, x, theta0=[1, 1, 1], Sigma0=np.eye(3), method="vb")
+    with pytest.raises(TypeError):
+        api.fitExpGP(x, x + 1, x, theta0=[1, 1, 1], Sigma0=np.eye(3), method="vb", control=dict(tol_rel_obj="tight"))
 
 
 def test_shard_ranges_partition_the_batch():
