@@ -38,7 +38,7 @@ fitExpGP <- function(x, y, uy, dataType = 2, Nn = 10, gridType = "internal", met
                      theta0 = NULL, Sigma0 = NULL, lambda_rate = 0.1, rho_scale = 0.1,
                      nb_warmup = 500, nb_iter = 1500, prior_PD = 0, open_progress = FALSE,
                      chains = 4, seed = sample.int(.Machine$integer.max, 1)) {
-  stopifnot(method %in% c("sample", "optim"))   # vb: SURVEY 8(f) N4
+  stopifnot(method %in% c("sample", "optim", "vb"))
   ctl <- list(dataType = dataType, Nn = Nn, gridType = as.integer(gridType == "extremal"),
               rho = ifelse(rho_scale == 0, 1 / Nn, rho_scale), lambda_rate = lambda_rate,
               theta0 = as.numeric(theta0), Sigma0 = as.numeric(Sigma0), prior_PD = prior_PD,
@@ -51,6 +51,15 @@ fitExpGP <- function(x, y, uy, dataType = 2, Nn = 10, gridType = "internal", met
     fit <- list(par = list(theta = p[1:3], yGP = p[3 + seq_len(Nn)], lambda = p[Nn + 4], sigma = p[Nn + 5], br = p[Nn + 6],
                            m = r$m, resid = r$resid, dL = r$dL),
                 value = p[Nn + 7], hessian = r$hessian, return_code = r$status)
+    return(list(fit = fit, method = method, xGP = xGP, prior_PD = prior_PD))
+  }
+  if (method == "vb") {      # Stan's mean-field ADVI (MODEL_SPEC 14); the draws go through read_stan_csv like a 1-chain fit
+    r <- .Call("foct_R_vb", as.numeric(x), as.numeric(y), as.numeric(uy), ctl, PACKAGE = "FitOCTb200")
+    if (r$status == 2L) stop("fitExpGP(method='vb'): ADVI failed (dropped evaluations / no usable step size)")
+    ns  <- length(r$draws) / (Nn + 7)
+    res <- list(draws = r$draws, sampler_params = numeric(6 * ns), stepsize = r$eta, inv_metric = exp(2 * r$omega))
+    fit <- .as_stanfit(res, 0L, Nn, 1L, 0L, ns)
+    attr(fit, "vb") <- r[c("mean", "mu", "omega", "elbo", "eta", "iters", "status")]
     return(list(fit = fit, method = method, xGP = xGP, prior_PD = prior_PD))
   }
   res <- .Call("foct_R_sample", 0L, as.numeric(x), as.numeric(y), as.numeric(uy), ctl, PACKAGE = "FitOCTb200")

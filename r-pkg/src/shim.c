@@ -209,6 +209,60 @@ SEXP foct_R_exp_prior(SEXP x, SEXP y, SEXP uy, SEXP dataType, SEXP priorType, SE
   return out;
 }
 
+/* .Call("foct_R_vb", x, y, uy, ctl) -> list(mean, draws, mu, omega, elbo, eta, iters, status): fitExpGP(method = 'vb')
+ * (FitOCT.R:42).  ctl as for foct_R_sample plus rstan::vb's iter, grad_samples, elbo_samples, eval_elbo, output_samples,
+ * adapt_engaged, adapt_iter, eta, tol_rel_obj and omega0. */
+SEXP foct_R_vb(SEXP x, SEXP y, SEXP uy, SEXP ctl) {
+  foct_problem P;
+  memset(&P, 0, sizeof(P));
+  P.N = (int)XLENGTH(x);
+  P.x = REAL(x); P.y = REAL(y); P.uy = REAL(uy);
+  P.dataType = (int)get_num(ctl, "dataType", 2);
+  P.Nn = (int)get_num(ctl, "Nn", 10);
+  P.gridType = (int)get_num(ctl, "gridType", 0);
+  P.rho = get_num(ctl, "rho", 0.1);
+  P.lambda_rate = get_num(ctl, "lambda_rate", 0.1);
+  P.prior_PD = (int)get_num(ctl, "prior_PD", 0);
+  SEXP th0 = get_elt(ctl, "theta0"), S0 = get_elt(ctl, "Sigma0");
+  if (th0 != R_NilValue) memcpy(P.theta0, REAL(th0), 3 * sizeof(double));
+  if (S0 != R_NilValue) memcpy(P.Sigma0, REAL(S0), 9 * sizeof(double));
+  foct_model_spec spec;
+  foct_model_spec_default(&spec, FOCT_EXPGP);
+  foct_vb_cfg cfg;
+  foct_vb_cfg_default(&cfg);
+  cfg.iter = (int)get_num(ctl, "iter", cfg.iter);
+  cfg.grad_samples = (int)get_num(ctl, "grad_samples", cfg.grad_samples);
+  cfg.elbo_samples = (int)get_num(ctl, "elbo_samples", cfg.elbo_samples);
+  cfg.eval_elbo = (int)get_num(ctl, "eval_elbo", cfg.eval_elbo);
+  cfg.output_samples = (int)get_num(ctl, "output_samples", cfg.output_samples);
+  cfg.adapt_engaged = (int)get_num(ctl, "adapt_engaged", cfg.adapt_engaged);
+  cfg.adapt_iter = (int)get_num(ctl, "adapt_iter", cfg.adapt_iter);
+  cfg.eta = get_num(ctl, "eta", cfg.eta);
+  cfg.tol_rel_obj = get_num(ctl, "tol_rel_obj", cfg.tol_rel_obj);
+  cfg.omega0 = get_num(ctl, "omega0", -3.0);
+  cfg.seed = (unsigned long long)get_num(ctl, "seed", 1234);
+  const int D = P.Nn + 5, P_out = P.Nn + 7;
+  SEXP mean = PROTECT(Rf_allocVector(REALSXP, P_out));
+  SEXP draws = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)cfg.output_samples * P_out));
+  SEXP mu = PROTECT(Rf_allocVector(REALSXP, D)), om = PROTECT(Rf_allocVector(REALSXP, D));
+  SEXP elbo = PROTECT(Rf_allocVector(REALSXP, 1)), eta = PROTECT(Rf_allocVector(REALSXP, 1));
+  SEXP it = PROTECT(Rf_allocVector(INTSXP, 1)), st = PROTECT(Rf_allocVector(INTSXP, 1));
+  foct_vb_result R;
+  R.mean = REAL(mean); R.draws = REAL(draws); R.mu = REAL(mu); R.omega = REAL(om); R.elbo = REAL(elbo); R.eta = REAL(eta);
+  R.iters = INTEGER(it); R.status = INTEGER(st);
+  int rc = foct_vb(FOCT_EXPGP, &P, 1, &spec, &cfg, &R);
+  if (rc) {
+    UNPROTECT(8);
+    Rf_error("fitoct_b200 error %d: %s", rc, foct_last_error());
+  }
+  const char* nm[] = {"mean", "draws", "mu", "omega", "elbo", "eta", "iters", "status", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
+  SET_VECTOR_ELT(out, 0, mean); SET_VECTOR_ELT(out, 1, draws); SET_VECTOR_ELT(out, 2, mu); SET_VECTOR_ELT(out, 3, om);
+  SET_VECTOR_ELT(out, 4, elbo); SET_VECTOR_ELT(out, 5, eta); SET_VECTOR_ELT(out, 6, it); SET_VECTOR_ELT(out, 7, st);
+  UNPROTECT(9);
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"foct_R_sample", (DL_FUNC)&foct_R_sample, 5},
     {"foct_R_monoexp_map", (DL_FUNC)&foct_R_monoexp_map, 4},
@@ -216,6 +270,7 @@ static const R_CallMethodDef call_methods[] = {
     {"foct_R_estimate_noise", (DL_FUNC)&foct_R_estimate_noise, 4},
     {"foct_R_birge_ci", (DL_FUNC)&foct_R_birge_ci, 1},
     {"foct_R_exp_prior", (DL_FUNC)&foct_R_exp_prior, 8},
+    {"foct_R_vb", (DL_FUNC)&foct_R_vb, 4},
     {NULL, NULL, 0}};
 
 void R_init_FitOCTb200(DllInfo* dll) {
