@@ -22,7 +22,7 @@ EXPORTS = (
     "foct_monoexp_sample", "foct_monoexp_map", "foct_expgp_map", "foct_predict", "foct_plan_create", "foct_plan_run",
     "foct_plan_sync", "foct_plan_timing", "foct_plan_fetch", "foct_plan_destroy", "foct_fp64_peak",
     "foct_estimate_noise", "foct_birge_ci", "foct_print_br", "foct_estimate_exp_prior", "foct_pipeline_cfg_default",
-    "foct_pipeline", "foct_vb_cfg_default", "foct_vb",
+    "foct_pipeline", "foct_vb_cfg_default", "foct_vb", "foct_release_cache",
 )
 
 _LIB = None
@@ -75,6 +75,8 @@ def lib():
         L.foct_estimate_exp_prior.argtypes = [PP, C.c_int, C.c_int, dp, dp, C.c_double, dp, dp, dp]
         L.foct_pipeline_cfg_default.argtypes = [C.POINTER(abi.PipelineCfg)]
         L.foct_pipeline_cfg_default.restype = None
+        L.foct_release_cache.argtypes = []
+        L.foct_release_cache.restype = None
         L.foct_vb_cfg_default.argtypes = [C.POINTER(abi.VbCfg)]
         L.foct_vb_cfg_default.restype = None
         L.foct_vb.argtypes = [C.c_int, PP, C.c_int, MS, C.POINTER(abi.VbCfg), C.POINTER(abi.VbResult)]
@@ -331,3 +333,8 @@ def vb(kind: int, batch: abi.ProblemBatch, n_problems: int, spec: abi.ModelSpec,
     out, R = abi.alloc_vb_result(kind, n_problems, Nn, cfg, draws)
     check(lib().foct_vb(kind, batch.array, n_problems, C.byref(spec), C.byref(cfg), C.byref(R)))
     return out
+
+
+def release_cache():
+    """Return the library's cached device buffers to the driver (foct_release_cache)."""
+    lib().foct_release_cache()

@@ -3,6 +3,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "foct_nuts.cuh"
 
 namespace foct {
@@ -62,6 +66,20 @@ struct InstEntry {
 // shared by the host translation units (defined in foct_lib.cu)
 int fail(int code, const char* fmt, ...);  // records the thread-local message behind foct_last_error(), returns code
 int check_device();
+
+// FOCT_TRACE=1: host-phase wall times of the host entry points on stderr
+struct Trace {
+  bool on;
+  const char* what;
+  std::chrono::steady_clock::time_point t0;
+  explicit Trace(const char* w) : on(std::getenv("FOCT_TRACE") != nullptr), what(w), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* phase) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[foct trace] %s: %s %.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 #define FOCT_DECL_INST(NN) const InstEntry* foct_inst_##NN();
 

@@ -8,8 +8,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "foct_launch.h"
@@ -50,6 +53,83 @@ int fail(int code, const char* fmt, ...) {
     cudaError_t e_ = (call);                                                                             \
     if (e_ != cudaSuccess) return fail(FOCT_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
+
+
+// ------------------------------------------------------------------ device-memory cache
+// cudaMalloc / cudaFree cost milliseconds (cudaFree also synchronises the device) and an R session calls the fit once per
+// profile, so freed blocks are kept and handed back to later requests of a similar size on the same device.  At most
+// FOCT_POOL_MB (default 8192) MB stay cached; foct_release_cache() returns everything to the driver.
+namespace {
+struct DevicePool {
+  std::mutex mu;
+  std::unordered_map<void*, std::pair<int, size_t>> live;
+  std::multimap<std::pair<int, size_t>, void*> idle;
+  size_t idle_bytes = 0;
+  size_t cap() const {
+    static const size_t c = [] {
+      const char* e = std::getenv("FOCT_POOL_MB");
+      return (size_t)((e ? std::atof(e) : 8192.0) * 1024.0 * 1024.0);
+    }();
+    return c;
+  }
+  void release(int dev) {  // dev < 0: every device.  Called with mu held.
+    for (auto it = idle.begin(); it != idle.end();) {
+      if (dev < 0 || it->first.first == dev) { idle_bytes -= it->first.second; cudaFree(it->second); it = idle.erase(it); }
+      else ++it;
+    }
+  }
+};
+DevicePool g_pool;
+}  // namespace
+
+template <class T>
+static cudaError_t pool_malloc(T** out, size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+  std::lock_guard<std::mutex> lk(g_pool.mu);
+  auto it = g_pool.idle.lower_bound({dev, bytes});
+  if (it != g_pool.idle.end() && it->first.first == dev && it->first.second <= bytes + bytes / 4 + (1u << 20)) {
+    void* p = it->second;
+    g_pool.live[p] = it->first;
+    g_pool.idle_bytes -= it->first.second;
+    g_pool.idle.erase(it);
+    *out = static_cast<T*>(p);
+    return cudaSuccess;
+  }
+  void* p = nullptr;
+  e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {  // give the cached blocks back and retry once
+    cudaGetLastError();
+    g_pool.release(dev);
+    e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+  }
+  g_pool.live[p] = {dev, bytes};
+  *out = static_cast<T*>(p);
+  return cudaSuccess;
+}
+
+static void pool_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pool.mu);
+  auto it = g_pool.live.find(p);
+  if (it == g_pool.live.end()) { cudaFree(p); return; }
+  const std::pair<int, size_t> key = it->second;
+  g_pool.live.erase(it);
+  if (g_pool.idle_bytes + key.second <= g_pool.cap()) {
+    g_pool.idle.emplace(key, p);
+    g_pool.idle_bytes += key.second;
+  } else {
+    cudaFree(p);
+  }
+}
+
+extern "C" void foct_release_cache(void) {
+  std::lock_guard<std::mutex> lk(g_pool.mu);
+  g_pool.release(-1);
+}
 
 // ------------------------------------------------------------------ setup kernel
 // Host-side description of one profile inside the concatenated upload buffer.
@@ -354,9 +434,9 @@ struct foct_plan {
 static void plan_free(foct_plan* p) {
   if (!p) return;
   cudaSetDevice(p->device);
-  cudaFree(p->d_blobs); cudaFree(p->d_draws); cudaFree(p->d_sparams); cudaFree(p->d_summary);
-  cudaFree(p->d_stepsize); cudaFree(p->d_invm); cudaFree(p->d_nleap); cudaFree(p->d_ndiv); cudaFree(p->d_init);
-  cudaFree(p->d_probs); cudaFree(p->d_counter);
+  pool_free(p->d_blobs); pool_free(p->d_draws); pool_free(p->d_sparams); pool_free(p->d_summary);
+  pool_free(p->d_stepsize); pool_free(p->d_invm); pool_free(p->d_nleap); pool_free(p->d_ndiv); pool_free(p->d_init);
+  pool_free(p->d_probs); pool_free(p->d_counter);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   if (p->ev2) cudaEventDestroy(p->ev2);
@@ -433,11 +513,11 @@ static int build_device_batch(int kind, const foct_problem* P, int n, const foct
   do {
     if (bad >= 0) { rc = fail(FOCT_EINVAL, "problem %d: singular Sigma0 or non-positive uy", bad); break; }
 #define CUB(call) if ((call) != cudaSuccess) { rc = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); break; }
-    CUB(cudaMalloc(&d_up, total * sizeof(double)));
-    CUB(cudaMalloc(&d_meta, (size_t)n * sizeof(HostMeta)));
-    CUB(cudaMalloc(&d_status, sizeof(int)));
-    CUB(cudaMalloc(d_blobs, (size_t)n * stride * sizeof(double)));
-    CUB(cudaMalloc(d_probs, (size_t)n * sizeof(DevProblem)));
+    CUB(pool_malloc(&d_up, total * sizeof(double)));
+    CUB(pool_malloc(&d_meta, (size_t)n * sizeof(HostMeta)));
+    CUB(pool_malloc(&d_status, sizeof(int)));
+    CUB(pool_malloc(d_blobs, (size_t)n * stride * sizeof(double)));
+    CUB(pool_malloc(d_probs, (size_t)n * sizeof(DevProblem)));
     CUB(cudaMemcpyAsync(d_up, h_up, total * sizeof(double), cudaMemcpyHostToDevice, st));
     CUB(cudaMemcpyAsync(d_meta, h_meta, (size_t)n * sizeof(HostMeta), cudaMemcpyHostToDevice, st));
     CUB(cudaMemsetAsync(d_status, 0, sizeof(int), st));
@@ -451,9 +531,9 @@ static int build_device_batch(int kind, const foct_problem* P, int n, const foct
     if (h_status) { rc = fail(FOCT_EINVAL, "problem %d: degenerate depth grid or Kgg not positive definite (rho, jitter?)", h_status - 1); break; }
 #undef CUB
   } while (0);
-  cudaFree(d_up); cudaFree(d_meta); cudaFree(d_status);
+  pool_free(d_up); pool_free(d_meta); pool_free(d_status);
   cudaFreeHost(h_up); cudaFreeHost(h_meta);
-  if (rc) { cudaFree(*d_blobs); cudaFree(*d_probs); *d_blobs = nullptr; *d_probs = nullptr; return rc; }
+  if (rc) { pool_free(*d_blobs); pool_free(*d_probs); *d_blobs = nullptr; *d_probs = nullptr; return rc; }
   *NN_out = NN; *npad_out = npad; *stride_out = stride;
   return 0;
 }
@@ -508,7 +588,7 @@ extern "C" int foct_expgp_basis(const foct_problem* P, const foct_model_spec* sp
   if (int rc = build_device_batch(FOCT_EXPGP, P, 1, spec, dev, 0, &NN, &npad, &stride, &d_blobs, &d_probs)) return rc;
   std::vector<double> h(stride);
   cudaError_t e = cudaMemcpy(h.data(), d_blobs, stride * sizeof(double), cudaMemcpyDeviceToHost);
-  cudaFree(d_blobs); cudaFree(d_probs);
+  pool_free(d_blobs); pool_free(d_probs);
   if (e == cudaSuccess)
     for (int k = 0; k < NN; ++k)
       for (int i = 0; i < P->N; ++i) B_out[(size_t)k * P->N + i] = h[blob_index(i, 3 + k, NN)];
@@ -532,10 +612,10 @@ extern "C" int foct_logp_grad(int kind, const foct_problem* P, int n, const foct
   int rc = 0;
   do {
 #define CUB(call) if ((call) != cudaSuccess) { rc = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); break; }
-    CUB(cudaMalloc(&d_q, nq * D * sizeof(double)));
-    CUB(cudaMalloc(&d_g, nq * D * sizeof(double)));
-    CUB(cudaMalloc(&d_lp, nq * sizeof(double)));
-    CUB(cudaMalloc(&d_c2, nq * sizeof(double)));
+    CUB(pool_malloc(&d_q, nq * D * sizeof(double)));
+    CUB(pool_malloc(&d_g, nq * D * sizeof(double)));
+    CUB(pool_malloc(&d_lp, nq * sizeof(double)));
+    CUB(pool_malloc(&d_c2, nq * sizeof(double)));
     CUB(cudaMemcpy(d_q, q, nq * D * sizeof(double), cudaMemcpyHostToDevice));
     LogpParams K;
     K.blobs = d_blobs; K.blob_stride = stride; K.npad = npad; K.probs = d_probs; K.n_problems = n;
@@ -548,7 +628,7 @@ extern "C" int foct_logp_grad(int kind, const foct_problem* P, int n, const foct
     if (chi2) CUB(cudaMemcpy(chi2, d_c2, nq * sizeof(double), cudaMemcpyDeviceToHost));
 #undef CUB
   } while (0);
-  cudaFree(d_q); cudaFree(d_g); cudaFree(d_lp); cudaFree(d_c2); cudaFree(d_blobs); cudaFree(d_probs);
+  pool_free(d_q); pool_free(d_g); pool_free(d_lp); pool_free(d_c2); pool_free(d_blobs); pool_free(d_probs);
   return rc;
 }
 
@@ -568,10 +648,10 @@ extern "C" int foct_predict(int kind, const foct_problem* P, const foct_model_sp
   int rc = 0;
   do {
 #define CUB(call) if ((call) != cudaSuccess) { rc = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); break; }
-    CUB(cudaMalloc(&d_dr, (size_t)n_draws * P_out * sizeof(double)));
-    CUB(cudaMalloc(&d_m, tot * sizeof(double)));
-    CUB(cudaMalloc(&d_r, tot * sizeof(double)));
-    CUB(cudaMalloc(&d_dl, tot * sizeof(double)));
+    CUB(pool_malloc(&d_dr, (size_t)n_draws * P_out * sizeof(double)));
+    CUB(pool_malloc(&d_m, tot * sizeof(double)));
+    CUB(pool_malloc(&d_r, tot * sizeof(double)));
+    CUB(pool_malloc(&d_dl, tot * sizeof(double)));
     CUB(cudaMemcpy(d_dr, draws, (size_t)n_draws * P_out * sizeof(double), cudaMemcpyHostToDevice));
     predict_kernel<<<(int)std::min<size_t>((tot + 255) / 256, 148 * 16), 256>>>(d_blobs, npad, P->N, NN, spec->modulation, P_out,
                                                                                 d_dr, n_draws, d_m, d_r, d_dl);
@@ -582,7 +662,7 @@ extern "C" int foct_predict(int kind, const foct_problem* P, const foct_model_sp
     if (dL) CUB(cudaMemcpy(dL, d_dl, tot * sizeof(double), cudaMemcpyDeviceToHost));
 #undef CUB
   } while (0);
-  cudaFree(d_dr); cudaFree(d_m); cudaFree(d_r); cudaFree(d_dl); cudaFree(d_blobs); cudaFree(d_probs);
+  pool_free(d_dr); pool_free(d_m); pool_free(d_r); pool_free(d_dl); pool_free(d_blobs); pool_free(d_probs);
   return rc;
 }
 
@@ -621,17 +701,17 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
   const size_t pc = (size_t)n * cfg->chains;
   const bool need_draws = p->want_draws || p->want_summary;
   if (need_draws) {
-    CUP(cudaMalloc(&p->d_draws, pc * p->n_saved * p->P_out * sizeof(double)));
-    if (p->want_draws) CUP(cudaMalloc(&p->d_sparams, pc * p->n_saved * 6 * sizeof(double)));
+    CUP(pool_malloc(&p->d_draws, pc * p->n_saved * p->P_out * sizeof(double)));
+    if (p->want_draws) CUP(pool_malloc(&p->d_sparams, pc * p->n_saved * 6 * sizeof(double)));
   }
-  if (p->want_summary) CUP(cudaMalloc(&p->d_summary, (size_t)n * p->P_out * FOCT_N_SUMMARY_COLS * sizeof(double)));
-  CUP(cudaMalloc(&p->d_stepsize, pc * sizeof(double)));
-  CUP(cudaMalloc(&p->d_invm, pc * p->D * sizeof(double)));
-  CUP(cudaMalloc(&p->d_nleap, pc * 2 * sizeof(double)));
-  CUP(cudaMalloc(&p->d_ndiv, pc * sizeof(double)));
-  CUP(cudaMalloc(&p->d_counter, sizeof(int)));
+  if (p->want_summary) CUP(pool_malloc(&p->d_summary, (size_t)n * p->P_out * FOCT_N_SUMMARY_COLS * sizeof(double)));
+  CUP(pool_malloc(&p->d_stepsize, pc * sizeof(double)));
+  CUP(pool_malloc(&p->d_invm, pc * p->D * sizeof(double)));
+  CUP(pool_malloc(&p->d_nleap, pc * 2 * sizeof(double)));
+  CUP(pool_malloc(&p->d_ndiv, pc * sizeof(double)));
+  CUP(pool_malloc(&p->d_counter, sizeof(int)));
   if (cfg->init_mode == 2) {
-    CUP(cudaMalloc(&p->d_init, pc * p->D * sizeof(double)));
+    CUP(pool_malloc(&p->d_init, pc * p->D * sizeof(double)));
     CUP(cudaMemcpy(p->d_init, init_slice, pc * p->D * sizeof(double), cudaMemcpyHostToDevice));
   }
   p->inst = inst_for(p->NN);
@@ -750,9 +830,12 @@ static int sample_chunk(int device, int kind, const foct_problem* P, int first, 
   const int n_saved = cfg->save_warmup ? cfg->n_iter : cfg->n_iter - cfg->n_warmup;
   foct_plan* p = nullptr;
   const double* init_slice = cfg->init_mode == 2 && cfg->init ? cfg->init + (size_t)first * C * D : nullptr;
+  Trace tr("foct_sample");
   int rc = plan_create_on(device, kind, P + first, n, spec, cfg, init_slice, R->draws || R->sampler_params, R->summary != nullptr, &p);
   if (rc) return rc;
+  tr.mark("plan (alloc, pack, upload, setup kernel)");
   rc = foct_plan_run(p, cfg->seed);
+  if (!rc && tr.on) { foct_plan_sync(p, nullptr); tr.mark("kernels"); }
   if (!rc) {
     foct_result S = *R;
     const size_t pc0 = (size_t)first * C;
@@ -764,8 +847,10 @@ static int sample_chunk(int device, int kind, const foct_problem* P, int first, 
     if (S.n_leapfrog) S.n_leapfrog += pc0 * 2;
     if (S.n_divergent) S.n_divergent += pc0;
     rc = foct_plan_fetch(p, &S);
+    tr.mark("fetch");
   }
   plan_free(p);
+  tr.mark("free");
   return rc;
 }
 
@@ -846,12 +931,12 @@ extern "C" int foct_monoexp_map(const foct_problem* P, int n, const foct_model_s
   int rc = 0;
   do {
 #define CUB(call) if ((call) != cudaSuccess) { rc = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); break; }
-    CUB(cudaMalloc(&d_th, (size_t)n * 3 * sizeof(double)));
-    CUB(cudaMalloc(&d_H, (size_t)n * 9 * sizeof(double)));
-    CUB(cudaMalloc(&d_br, (size_t)n * sizeof(double)));
-    CUB(cudaMalloc(&d_st, (size_t)n * sizeof(int)));
+    CUB(pool_malloc(&d_th, (size_t)n * 3 * sizeof(double)));
+    CUB(pool_malloc(&d_H, (size_t)n * 9 * sizeof(double)));
+    CUB(pool_malloc(&d_br, (size_t)n * sizeof(double)));
+    CUB(pool_malloc(&d_st, (size_t)n * sizeof(int)));
     if (init) {
-      CUB(cudaMalloc(&d_init, (size_t)n * 3 * sizeof(double)));
+      CUB(pool_malloc(&d_init, (size_t)n * 3 * sizeof(double)));
       CUB(cudaMemcpy(d_init, init, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
     }
     map_kernel<<<(n + 3) / 4, 128>>>(d_blobs, stride, npad, d_probs, n, spec->theta_prior, d_init, d_th, d_H, d_br, d_st);
@@ -863,7 +948,7 @@ extern "C" int foct_monoexp_map(const foct_problem* P, int n, const foct_model_s
     if (status) CUB(cudaMemcpy(status, d_st, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
 #undef CUB
   } while (0);
-  cudaFree(d_init); cudaFree(d_th); cudaFree(d_H); cudaFree(d_br); cudaFree(d_st); cudaFree(d_blobs); cudaFree(d_probs);
+  pool_free(d_init); pool_free(d_th); pool_free(d_H); pool_free(d_br); pool_free(d_st); pool_free(d_blobs); pool_free(d_probs);
   return rc;
 }
 
@@ -885,11 +970,11 @@ extern "C" int foct_expgp_map(const foct_problem* P, int n, const foct_model_spe
   int rc = 0;
   do {
 #define CUB(call) if ((call) != cudaSuccess) { rc = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); break; }
-    CUB(cudaMalloc(&d_par, (size_t)n * P_out * sizeof(double)));
-    CUB(cudaMalloc(&d_st, (size_t)n * sizeof(int)));
-    if (hessian) CUB(cudaMalloc(&d_H, (size_t)n * D * D * sizeof(double)));
+    CUB(pool_malloc(&d_par, (size_t)n * P_out * sizeof(double)));
+    CUB(pool_malloc(&d_st, (size_t)n * sizeof(int)));
+    if (hessian) CUB(pool_malloc(&d_H, (size_t)n * D * D * sizeof(double)));
     if (init) {
-      CUB(cudaMalloc(&d_init, (size_t)n * D * sizeof(double)));
+      CUB(pool_malloc(&d_init, (size_t)n * D * sizeof(double)));
       CUB(cudaMemcpy(d_init, init, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice));
     }
     MapParams K;
@@ -903,7 +988,7 @@ extern "C" int foct_expgp_map(const foct_problem* P, int n, const foct_model_spe
     if (status) CUB(cudaMemcpy(status, d_st, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
 #undef CUB
   } while (0);
-  cudaFree(d_init); cudaFree(d_par); cudaFree(d_H); cudaFree(d_st); cudaFree(d_blobs); cudaFree(d_probs);
+  pool_free(d_init); pool_free(d_par); pool_free(d_H); pool_free(d_st); pool_free(d_blobs); pool_free(d_probs);
   return rc;
 }
 
@@ -937,16 +1022,16 @@ extern "C" int foct_vb(int kind, const foct_problem* P, int n, const foct_model_
   int rc = 0;
   do {
 #define CUB(call) if ((call) != cudaSuccess) { rc = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); break; }
-    CUB(cudaMalloc(&d_mean, (size_t)n * P_out * sizeof(double)));
-    CUB(cudaMalloc(&d_mu, (size_t)n * D * sizeof(double)));
-    CUB(cudaMalloc(&d_om, (size_t)n * D * sizeof(double)));
-    CUB(cudaMalloc(&d_elbo, (size_t)n * sizeof(double)));
-    CUB(cudaMalloc(&d_eta, (size_t)n * sizeof(double)));
-    CUB(cudaMalloc(&d_it, (size_t)n * sizeof(int)));
-    CUB(cudaMalloc(&d_st, (size_t)n * sizeof(int)));
-    if (R->draws && nd) CUB(cudaMalloc(&d_draws, nd * sizeof(double)));
+    CUB(pool_malloc(&d_mean, (size_t)n * P_out * sizeof(double)));
+    CUB(pool_malloc(&d_mu, (size_t)n * D * sizeof(double)));
+    CUB(pool_malloc(&d_om, (size_t)n * D * sizeof(double)));
+    CUB(pool_malloc(&d_elbo, (size_t)n * sizeof(double)));
+    CUB(pool_malloc(&d_eta, (size_t)n * sizeof(double)));
+    CUB(pool_malloc(&d_it, (size_t)n * sizeof(int)));
+    CUB(pool_malloc(&d_st, (size_t)n * sizeof(int)));
+    if (R->draws && nd) CUB(pool_malloc(&d_draws, nd * sizeof(double)));
     if (cfg->init_mode == 2) {
-      CUB(cudaMalloc(&d_init, (size_t)n * D * sizeof(double)));
+      CUB(pool_malloc(&d_init, (size_t)n * D * sizeof(double)));
       CUB(cudaMemcpy(d_init, cfg->init, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice));
     }
     VbParams K;
@@ -969,8 +1054,8 @@ extern "C" int foct_vb(int kind, const foct_problem* P, int n, const foct_model_
     if (R->status) CUB(cudaMemcpy(R->status, d_st, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
 #undef CUB
   } while (0);
-  cudaFree(d_init); cudaFree(d_mean); cudaFree(d_draws); cudaFree(d_mu); cudaFree(d_om); cudaFree(d_elbo); cudaFree(d_eta);
-  cudaFree(d_it); cudaFree(d_st); cudaFree(d_blobs); cudaFree(d_probs);
+  pool_free(d_init); pool_free(d_mean); pool_free(d_draws); pool_free(d_mu); pool_free(d_om); pool_free(d_elbo); pool_free(d_eta);
+  pool_free(d_it); pool_free(d_st); pool_free(d_blobs); pool_free(d_probs);
   return rc;
 }
 
@@ -982,7 +1067,7 @@ extern "C" int foct_fp64_peak(int device, double* tflops, double* sm_mhz) {
   CU(cudaGetDeviceProperties(&prop, device));
   const int grid = prop.multiProcessorCount * 8, block = 256, iters = 1 << 16;
   double* d_out = nullptr;
-  CU(cudaMalloc(&d_out, (size_t)grid * block * sizeof(double)));
+  CU(pool_malloc(&d_out, (size_t)grid * block * sizeof(double)));
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0));
   CU(cudaEventCreate(&e1));
@@ -996,7 +1081,7 @@ extern "C" int foct_fp64_peak(int device, double* tflops, double* sm_mhz) {
     CU(cudaEventElapsedTime(&ms, e0, e1));
     if (rep > 0 && ms < best) best = ms;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); pool_free(d_out);
   const double flops = 2.0 * 8.0 * (double)iters * (double)grid * block;
   if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
   if (sm_mhz) *sm_mhz = prop.clockRate / 1000.0;

@@ -458,20 +458,6 @@ static double chisq_quantile(double p, double ndf) {
   return x;
 }
 
-// FOCT_TRACE=1: host-phase wall times of the prep entry points on stderr
-struct Trace {
-  bool on;
-  const char* what;
-  std::chrono::steady_clock::time_point t0;
-  explicit Trace(const char* w) : on(std::getenv("FOCT_TRACE") != nullptr), what(w), t0(std::chrono::steady_clock::now()) {}
-  void mark(const char* phase) {
-    if (!on) return;
-    const auto t1 = std::chrono::steady_clock::now();
-    std::fprintf(stderr, "[foct trace] %s: %s %.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
-    t0 = t1;
-  }
-};
-
 struct PrepUpload {
   std::vector<double> up;
   std::vector<PrepMeta> meta;

@@ -268,6 +268,10 @@ typedef struct foct_vb_result { /* caller-allocated; mean, mu, omega required, t
 int foct_vb(int kind, const foct_problem* P, int n_problems, const foct_model_spec* spec, const foct_vb_cfg* cfg,
             foct_vb_result* R);
 
+/* Device buffers freed by the entry points above are cached (up to FOCT_POOL_MB, default 8192 MB) and reused by later
+ * calls on the same device: an R session calls the fit once per profile.  This returns the cache to the driver. */
+void foct_release_cache(void);
+
 /* Measured fp64 FMA throughput of the device (DFMA-chain microbenchmark), the roofline denominator for
  * the sampling kernel (MEASURED_PEAKS.json has no fp64 figure). */
 int foct_fp64_peak(int device, double* tflops, double* sm_mhz);
