@@ -303,14 +303,19 @@ def estimateExpPrior(x, uy, dataType, priorType="mono", out=None, ru_theta=0.05,
 
 
 def FitOCT_batch(x, Y, ctrl=None, *, chains=4, seed=1234, gate=True, keep_draws=False, spec=None):
-    """FitOCT.R:74-124 for a batch of profiles on a shared depth grid, in one library call: estimateNoise -> fitMonoExp ->
-    printBr gate -> estimateExpPrior -> fitExpGP(method='sample') on the profiles the gate lets through.  `ctrl` holds
-    ctrlParams.yaml keys (load_ctrl_params()).  NB the reference `break`s out of its dataset loop at the first profile
+    """FitOCT.R:74-124 for a batch of profiles on a shared depth grid: estimateNoise -> fitMonoExp -> printBr gate ->
+    estimateExpPrior -> fitExpGP(method = ctrl['method']) on the profiles the gate lets through.  `ctrl` holds
+    ctrlParams.yaml keys (load_ctrl_params()).  method 'sample' is ONE library call (foct_pipeline); 'optim' and 'vb' chain
+    the batched entry points (foct_estimate_noise, foct_monoexp_map, foct_print_br, foct_estimate_exp_prior, then
+    foct_expgp_map / foct_vb on the gated subset).  NB the reference `break`s out of its dataset loop at the first profile
     whose MonoExp fit is OK (FitOCT.R:100); a batch treats that as `next`."""
     c = dict(CTRL_DEFAULTS)
     c.update(ctrl or {})
     from . import io as fio
 
+    method = c.get("method", "sample")
+    if method not in ("sample", "optim", "vb"):
+        raise ValueError("method must be one of 'sample', 'optim', 'vb' (FitOCT.R:42)")
     Y = np.atleast_2d(np.asarray(Y, dtype=np.float64))
     n = Y.shape[0]
     xs, Ys = [], []
@@ -319,15 +324,41 @@ def FitOCT_batch(x, Y, ctrl=None, *, chains=4, seed=1234, gate=True, keep_draws=
         xs.append(xj)
         Ys.append(yj)
     Ysel = np.stack(Ys)
-    batch = abi.make_problems_dense(xs[0], Ysel, np.ones_like(Ysel), np.tile([0.0, 0.0, 1.0], (n, 1)),
-                                    np.tile(np.eye(3), (n, 1, 1)), dataType=int(c["dataType"]), Nn=0)
-    pc = L.pipeline_cfg(smooth_df=float(c["smooth_df"]), prior_type={"mono": 0, "abc": 1}[c["priorType"]],
-                        ru_theta=float(c["ru_theta"]), Nn=int(c["Nn"]), gridType=_grid_code(c["gridType"]),
-                        rho_scale=float(c["rho_scale"]), lambda_rate=float(c["lambda_rate"]), gate=int(bool(gate)))
-    cfg = abi.default_cfg(chains=chains, n_warmup=int(c["nb_warmup"]), n_iter=int(c["nb_warmup"]) + int(c["nb_sample"]),
-                          seed=int(seed))
-    out = L.pipeline(batch, n, pc, cfg, spec_gp=spec, draws=keep_draws, summary=True)
+    Nn, gcode = int(c["Nn"]), _grid_code(c["gridType"])
+    th00, eye = np.tile([0.0, 0.0, 1.0], (n, 1)), np.tile(np.eye(3), (n, 1, 1))
+    batch = abi.make_problems_dense(xs[0], Ysel, np.ones_like(Ysel), th00, eye, dataType=int(c["dataType"]), Nn=0)
+    if method == "sample":
+        pc = L.pipeline_cfg(smooth_df=float(c["smooth_df"]), prior_type={"mono": 0, "abc": 1}[c["priorType"]],
+                            ru_theta=float(c["ru_theta"]), Nn=Nn, gridType=gcode, rho_scale=float(c["rho_scale"]),
+                            lambda_rate=float(c["lambda_rate"]), gate=int(bool(gate)))
+        cfg = abi.default_cfg(chains=chains, n_warmup=int(c["nb_warmup"]), n_iter=int(c["nb_warmup"]) + int(c["nb_sample"]),
+                              seed=int(seed))
+        out = L.pipeline(batch, n, pc, cfg, spec_gp=spec, draws=keep_draws, summary=True)
+    else:
+        nz = L.estimate_noise(batch, n, df=float(c["smooth_df"]))
+        UY = np.stack(nz["uy"])
+        spec_m = abi.default_spec(abi.FOCT_MONOEXP)
+        mono = abi.make_problems_dense(xs[0], Ysel, UY, th00, eye, dataType=int(c["dataType"]), Nn=0)
+        th, H, br, st = L.monoexp_map(mono, n, spec_m)
+        ci, alert = L.print_br(abi.FOCT_MONOEXP, mono, n, spec_m, br)
+        t0, S0, ru = L.estimate_exp_prior(mono, n, c["priorType"], th, H, ru_theta=float(c["ru_theta"]))
+        idx = np.flatnonzero(alert) if gate else np.arange(n)
+        out = dict(uy=nz["uy"], ySmooth=nz["ySmooth"], noise_theta=nz["theta"], mono_theta=th, mono_hessian=H, mono_br=br,
+                   mono_status=st, br_ci=ci, alert=alert, theta0=t0, Sigma0=S0, ru=ru, n_expgp=int(idx.size),
+                   expgp_index=idx.astype(np.int32), expgp=None)
+        if idx.size:
+            gp = abi.make_problems_dense(xs[0], Ysel[idx], UY[idx], t0[idx], S0[idx], dataType=int(c["dataType"]), Nn=Nn,
+                                         gridType=gcode, rho=resolve_rho(float(c["rho_scale"]), Nn),
+                                         lambda_rate=float(c["lambda_rate"]), ids=idx)
+            sg = spec or abi.default_spec(abi.FOCT_EXPGP)
+            if method == "optim":
+                par, Hq, stq = L.expgp_map(gp, int(idx.size), sg, hessian=True)
+                out["expgp"] = dict(par=par, hessian=Hq, status=stq)
+            else:
+                vc = abi.default_vb_cfg(seed=int(seed), omega0=float(c.get("vb_omega0", -3.0)))
+                out["expgp"] = L.vb(abi.FOCT_EXPGP, gp, int(idx.size), sg, vc, draws=keep_draws)
+    out["method"] = method
     out["x"] = xs[0]
-    out["par_names"] = abi.param_names(abi.FOCT_EXPGP, int(c["Nn"]))
-    out["xGP"] = L.grid(int(c["Nn"]), _grid_code(c["gridType"]))
+    out["par_names"] = abi.param_names(abi.FOCT_EXPGP, Nn)
+    out["xGP"] = L.grid(Nn, gcode)
     return out

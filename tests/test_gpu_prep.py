@@ -166,3 +166,23 @@ def test_fitoct_batch_driver_and_scale(L):
     k = out["n_expgp"]
     assert k == int(out["alert"].sum()) and out["expgp"]["summary"].shape[0] == k
     assert np.all(np.isfinite(out["expgp"]["summary"][:, :, 0]))
+
+
+def test_fitoct_batch_optim_and_vb_methods(L):
+    """ctrlParams' `method` (FitOCT.R:42): the Shiny default 'optim' and 'vb' through the same batch driver."""
+    from fitoct_b200 import api
+    S = synth.make_profiles(10)
+    kinds = S["mod_kind"]
+    o = api.FitOCT_batch(S["x"], S["Y"], dict(method="optim", Nn=8))
+    k = o["n_expgp"]
+    assert o["method"] == "optim" and k == int(o["alert"].sum()) == int((kinds > 0).sum())
+    assert o["expgp"]["par"].shape == (k, 8 + 7) and o["expgp"]["hessian"].shape == (k, 13, 13)
+    assert np.all(o["expgp"]["status"] == 0)
+    br_gp = o["expgp"]["par"][:, 8 + 5]
+    assert np.all(br_gp < o["mono_br"][o["expgp_index"]])          # the modulated model repairs every alerted fit
+    v = api.FitOCT_batch(S["x"], S["Y"], dict(method="vb", Nn=8))
+    assert v["n_expgp"] == k and np.all(v["expgp"]["status"] == 0)
+    # ADVI means (stopped at Stan's loose tol_rel_obj) and the MAP agree on the decay parameters to several per cent
+    assert np.allclose(v["expgp"]["mean"][:, :3], o["expgp"]["par"][:, :3], rtol=0.1)
+    with pytest.raises(ValueError):
+        api.FitOCT_batch(S["x"], S["Y"], dict(method="laplace"))
