@@ -84,3 +84,51 @@ def test_leapfrog_accounting(L, batch_run):
     # a tree that is rejected at depth d has still integrated up to 2^d more leaves (Stan reports the same)
     assert td.max() <= 10 and np.all(o["sampler_params"][..., 3] <= 2 ** (td + 1) - 1 + 1e-9)
     assert np.all((o["sampler_params"][..., 0] >= 0) & (o["sampler_params"][..., 0] <= 1))
+
+
+def test_simulation_based_calibration(L):
+    """Simulation-based calibration (Talts et al. 2018): draw parameters from the model's own prior, simulate a profile,
+    fit it, and rank the true value among the posterior draws.  For a sampler that targets exactly the posterior of the
+    stated model the ranks are uniform — a joint check of log density, gradient, transforms and NUTS that needs no
+    reference implementation.  Hyper-parameters are chosen so that the prior stays inside the model's domain (1 + dL > 0)."""
+    from scipy.stats import chi2 as chi2_dist
+    rng = np.random.default_rng(20240607)
+    n, Nn = 640, 10
+    x = synth.depth_grid()
+    N = x.size
+    theta0 = np.array([1000.0, 2000.0, 300.0])
+    Sigma0 = np.diag((0.03 * theta0) ** 2)
+    lam_rate = 60.0                                     # lambda ~ gamma(2, 60): mean 0.033  =>  |dL| stays below ~0.2
+    uy = 0.5 * np.sqrt(2000.0 * np.exp(-x / 150.0) + 1.0)
+    spec = abi.default_spec()
+    one = abi.make_problems_dense(x, np.ones((1, N)), uy[None, :], theta0[None, :], Sigma0[None], Nn=Nn, lambda_rate=lam_rate)
+    B = L.basis(one, 0, spec)                           # [Nn, N], depends on x only
+    th = theta0 + rng.standard_normal((n, 3)) * np.sqrt(np.diag(Sigma0))
+    lam = rng.gamma(2.0, 1.0 / lam_rate, n)
+    ygp = rng.standard_normal((n, Nn)) * lam[:, None]
+    sig = 1.0 + 0.1 * rng.standard_normal(n)
+    dL = ygp @ B
+    assert dL.min() > -0.9 and sig.min() > 0.5
+    m = th[:, :1] + th[:, 1:2] * np.exp(-2.0 * x[None, :] / (th[:, 2:3] * (1.0 + dL)))
+    Y = m + sig[:, None] * uy[None, :] * rng.standard_normal((n, N))
+    truth = np.column_stack([th, ygp, lam, sig])        # the 15 sampled quantities, constrained scale
+    b = abi.make_problems_dense(x, Y, np.tile(uy, (n, 1)), np.tile(theta0, (n, 1)), np.tile(Sigma0, (n, 1, 1)), Nn=Nn,
+                                lambda_rate=lam_rate)
+    cfg = abi.default_cfg(chains=4, n_warmup=400, n_iter=656, seed=77)
+    out = L.sample(abi.FOCT_EXPGP, b, n, spec, cfg, draws=True, summary=True)
+    assert out["n_divergent"].sum() <= 0.002 * n * 4 * 256
+    d = out["draws"][:, ::4, :, :15]                    # thin by 4: 64 x 4 chains = 256 nearly independent draws
+    Ld = d.shape[1] * d.shape[2]
+    ranks = (d.reshape(n, Ld, 15) < truth[:, None, :]).sum(axis=1)          # in 0..256
+    bins = 16
+    worst = 1.0
+    for k in range(15):
+        h = np.bincount(np.minimum(ranks[:, k] * bins // (Ld + 1), bins - 1), minlength=bins)
+        stat = np.sum((h - n / bins) ** 2 / (n / bins))
+        p = chi2_dist.sf(stat, bins - 1)
+        worst = min(worst, p)
+    # 15 tests: the smallest p-value of a calibrated sampler is below 1e-3 with probability 1.5 %
+    assert worst > 1e-3, worst
+    # and no parameter's ranks pile up at either end (over-/under-dispersed posterior)
+    edge = np.mean((ranks < Ld // 16) | (ranks > Ld - Ld // 16), axis=0)
+    assert np.all(np.abs(edge - 2 / 16.0) < 0.05), edge
