@@ -640,6 +640,9 @@ extern "C" int foct_pipeline(const foct_problem* P, int n, const foct_pipeline_c
     return fail(FOCT_EINVAL, "foct_pipeline_out has NULL buffers");
   if (pc->Nn < 1 || pc->Nn > FOCT_MAX_NN) return fail(FOCT_EINVAL, "Nn=%d outside 1..%d", pc->Nn, FOCT_MAX_NN);
   out->n_expgp = 0;
+  // the small steps run on the first device the caller listed (fitExpGP itself shards over all of them)
+  if (cfg->n_devices > 0 && cfg->devices && cudaSetDevice(cfg->devices[0]) != cudaSuccess)
+    return fail(FOCT_ECUDA, "cudaSetDevice(%d) failed: %s", cfg->devices[0], cudaGetErrorString(cudaGetLastError()));
   // 1. estimateNoise (FitOCT.R:89)
   std::vector<int> st(n);
   if (int rc = foct_estimate_noise(P, n, pc->smooth_df, pc->max_rate, out->uy, out->ySmooth, out->noise_theta, nullptr, st.data())) return rc;
