@@ -334,6 +334,7 @@ def FitOCT_batch(x, Y, ctrl=None, *, chains=4, seed=1234, gate=True, keep_draws=
         cfg = abi.default_cfg(chains=chains, n_warmup=int(c["nb_warmup"]), n_iter=int(c["nb_warmup"]) + int(c["nb_sample"]),
                               seed=int(seed))
         out = L.pipeline(batch, n, pc, cfg, spec_gp=spec, draws=keep_draws, summary=True)
+        out["sampler_cfg"] = cfg
     else:
         nz = L.estimate_noise(batch, n, df=float(c["smooth_df"]))
         UY = np.stack(nz["uy"])

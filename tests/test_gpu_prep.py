@@ -186,3 +186,32 @@ def test_fitoct_batch_optim_and_vb_methods(L):
     assert np.allclose(v["expgp"]["mean"][:, :3], o["expgp"]["par"][:, :3], rtol=0.1)
     with pytest.raises(ValueError):
         api.FitOCT_batch(S["x"], S["Y"], dict(method="laplace"))
+
+
+def test_batch_driver_on_a_data_directory(tmp_path, capsys):
+    """`python -m fitoct_b200 <dataDir>`: FitOCT.R:72-131 over a directory of Courbe.csv files."""
+    from fitoct_b200 import __main__ as drv
+    from fitoct_b200 import io as fio
+    S = synth.make_profiles(5)                       # modulation kinds 0..4
+    data = tmp_path / "DataSynth"
+    for j in range(5):
+        d = data / f"set{j}"
+        d.mkdir(parents=True)
+        fio.write_courbe_csv(str(d / "Courbe.csv"), S["x"], S["Y"][j])
+    ctrl = tmp_path / "ctrlParams.yaml"
+    ctrl.write_text("nb_warmup: 100\nnb_sample: 100\nNn: 6\nrho_scale: 0\n")
+    out = tmp_path / "Results"
+    assert drv.main([str(data), "--ctrl", str(ctrl), "--out", str(out), "--chains", "2"]) == 0
+    printed = capsys.readouterr().out
+    assert "DataSynth_set0" in printed and "MonoExp fit OK" in printed and "ExpGP (sample)" in printed
+    txt0 = (out / "DataSynth_set0_ctrl.txt").read_text()
+    assert "MonoExp decay parameters" in txt0 and "ExpGP parameters" not in txt0 and "WARNING" not in txt0
+    txt1 = (out / "DataSynth_set1_ctrl.txt").read_text()
+    assert "WARNING" in txt1 and "ExpGP parameters" in txt1 and "yGP[6]" in txt1
+    assert not (out / "DataSynth_set0_ExpGP_1.csv").exists()
+    back = fio.read_stan_csv([str(out / f"DataSynth_set1_ExpGP_{c}.csv") for c in (1, 2)])
+    assert back["draws"].shape == (100, 2, 6 + 7) and np.all(np.isfinite(back["draws"]))
+    # the Shiny default method through the same driver
+    ctrl.write_text("method: optim\nNn: 6\n")
+    assert drv.main([str(data), "--ctrl", str(ctrl), "--out", str(tmp_path / "R2")]) == 0
+    assert "theta  :" in (tmp_path / "R2" / "DataSynth_set2_ctrl.txt").read_text()
