@@ -1,6 +1,6 @@
 """First-contact GPU probe: parity of basis / logp / sampler vs the oracle, plus a first timing."""
 import sys, time, json
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from fitoct_b200 import _abi as abi, _lib as L, synth
 from oracle import oracle as O

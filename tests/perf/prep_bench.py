@@ -1,12 +1,12 @@
 """Timing of the steps either side of the sampling path through the C ABI with host buffers,
-beside the CPU oracle on a bounded sample.  Usage: python scripts/prep_bench.py [n_profiles] [n_cpu_sample]"""
+beside the CPU oracle on a bounded sample.  Usage: python tests/perf/prep_bench.py [n_profiles] [n_cpu_sample]"""
 import os
 import sys
 import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from fitoct_b200 import _abi as abi, _lib as L, synth  # noqa: E402
 from oracle import oracle as O  # noqa: E402  (CPU baseline leg only)

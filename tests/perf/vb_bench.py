@@ -1,7 +1,7 @@
-"""Timing of method='vb' (ADVI) for a batch through the C ABI.  Usage: python scripts/vb_bench.py [n_profiles] [n_cpu]"""
+"""Timing of method='vb' (ADVI) for a batch through the C ABI.  Usage: python tests/perf/vb_bench.py [n_profiles] [n_cpu]"""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from fitoct_b200 import _abi as abi, _lib as L, synth  # noqa: E402
 from oracle import oracle as O  # noqa: E402  (CPU baseline leg only)
