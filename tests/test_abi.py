@@ -125,3 +125,8 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "foct_oracle" not in txt, f
+    # nor may the helper scripts: only tests/, smoke() and bench.py's baseline legs may execute the oracle
+    for f in os.listdir(os.path.join(ROOT, "scripts")):
+        if f.endswith(".py"):
+            txt = open(os.path.join(ROOT, "scripts", f)).read()
+            assert "import oracle" not in txt and "from oracle" not in txt, f
