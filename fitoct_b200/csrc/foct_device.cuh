@@ -356,7 +356,10 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
 #ifndef FOCT_UNROLL
 #define FOCT_UNROLL 2
 #endif
-  constexpr int UNROLL = NN <= 12 ? FOCT_UNROLL : 1;  // above 12 control points the second basis row spills (measured: Nn=15 is 9 % faster with 1)
+#ifndef FOCT_UNROLL_MAXNN
+#define FOCT_UNROLL_MAXNN 12
+#endif
+  constexpr int UNROLL = NN <= FOCT_UNROLL_MAXNN ? FOCT_UNROLL : 1;  // above 12 control points the second basis row spills (measured: Nn=15 is 9 % faster with 1)
   const double th1 = bcast(qd, 0), th2 = bcast(qd, 1), th3 = bcast(qd, 2);
   double yg[NN > 0 ? NN : 1];
 #pragma unroll
