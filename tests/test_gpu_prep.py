@@ -215,3 +215,32 @@ def test_batch_driver_on_a_data_directory(tmp_path, capsys):
     ctrl.write_text("method: optim\nNn: 6\n")
     assert drv.main([str(data), "--ctrl", str(ctrl), "--out", str(tmp_path / "R2")]) == 0
     assert "theta  :" in (tmp_path / "R2" / "DataSynth_set2_ctrl.txt").read_text()
+
+
+def test_prep_edge_cases(L, O):
+    rng = np.random.default_rng(3)
+    # the smallest spline R accepts (4 points: every x a knot) and a df just above the straight line
+    x = np.array([0.0, 1.0, 2.5, 4.0])
+    y = np.array([1.0, 2.2, 2.9, 4.5])
+    b = _xy_batch([x], [y])
+    g = L.estimate_noise(b, 1, df=2.5)
+    _, ys_o, th_o, info_o = O.estimate_noise(b, 1, df=2.5)
+    assert g["status"][0] == 0 and np.allclose(g["ySmooth"][0], ys_o[0], rtol=1e-9) and abs(g["info"][0, 2] - 2.5) < 1e-9
+    # a pipeline whose gate lets nothing through returns without sampling
+    S = synth.make_profiles(10)
+    keep = np.flatnonzero(S["mod_kind"] == 0)
+    xy = abi.make_problems_dense(S["x"], S["Y"][keep], np.ones_like(S["Y"][keep]), np.tile([0.0, 0.0, 1.0], (keep.size, 1)),
+                                 np.tile(np.eye(3), (keep.size, 1, 1)), Nn=0)
+    cfg = abi.default_cfg(chains=2, n_warmup=30, n_iter=60)
+    out = L.pipeline(xy, keep.size, L.pipeline_cfg(), cfg)
+    assert out["n_expgp"] == 0 and out["alert"].sum() == 0 and out["expgp"]["summary"].shape[0] == 0
+    # a single profile, gate off
+    out1 = L.pipeline(xy, 1, L.pipeline_cfg(gate=0, Nn=5), cfg)
+    assert out1["n_expgp"] == 1 and np.all(np.isfinite(out1["expgp"]["summary"][0, :10, 0]))
+    # print_br needs degrees of freedom
+    from fitoct_b200._lib import FitOCTError
+    tiny = abi.make_problems([dict(x=x, y=y, uy=np.ones(4), dataType=2, Nn=10)])
+    ci, al = L.print_br(abi.FOCT_MONOEXP, tiny, 1, abi.default_spec(abi.FOCT_MONOEXP), np.array([1.0]))   # N - 3 = 1 is fine ...
+    assert ci.shape == (1, 2) and al.tolist() == [0]
+    with pytest.raises(FitOCTError):
+        L.print_br(abi.FOCT_EXPGP, tiny, 1, abi.default_spec(abi.FOCT_EXPGP), np.array([1.0]))           # ... N - 3 - Nn < 1 is not

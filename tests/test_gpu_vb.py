@@ -80,3 +80,16 @@ def test_vb_monoexp_and_api(L, O):
     with pytest.raises(RuntimeError):
         api.fitExpGP(Sm["x"], Sm["Y"][0], Sm["UY"][0], Nn=10, method="vb", theta0=Sm["theta0"][0], Sigma0=Sm["Sigma0"][0],
                      control=dict(omega0=0.0))
+
+
+def test_vb_edge_configs(L, O):
+    """Fewer iterations than one ELBO evaluation: the loop ends at the limit with no estimate; grad_samples > 1; no draws."""
+    S, batch = _batch(2)
+    spec = abi.default_spec(abi.FOCT_EXPGP)
+    cfg = abi.default_vb_cfg(omega0=-3.0, iter=60, adapt_engaged=0, eta=0.1, grad_samples=3, output_samples=0)
+    g = L.vb(abi.FOCT_EXPGP, batch, 2, spec, cfg, draws=False)
+    o = O.vb(abi.FOCT_EXPGP, batch, 2, spec, cfg, draws=False)
+    assert g["status"].tolist() == o["status"].tolist() == [1, 1] and g["iters"].tolist() == [60, 60]
+    assert np.all(g["elbo"] == 0.0) and np.all(o["elbo"] == 0.0)
+    assert np.max(np.abs(g["mu"] - o["mu"]) / np.exp(o["omega"])) < 1e-7
+    assert np.allclose(g["mean"], o["mean"], rtol=1e-9, atol=1e-12)
