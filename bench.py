@@ -48,6 +48,20 @@ def make_batch(n, first_id, Nn):
     return S, b
 
 
+def measured_traffic(n, Nn, n_warmup, n_iter, chains):
+    """DRAM bytes of one sampling-kernel launch from the committed ncu capture, if it was taken on this workload."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_dram_traffic.json")
+    try:
+        with open(path) as fh:
+            t = json.load(fh)
+    except (OSError, ValueError):
+        return None, "no ncu capture committed"
+    w = t.get("workload", {})
+    if (w.get("profiles_per_gpu"), w.get("Nn"), w.get("n_warmup"), w.get("n_iter"), w.get("chains")) != (n, Nn, n_warmup, n_iter, chains):
+        return None, "ncu capture is for another workload (profiles/r1_dram_traffic.json)"
+    return t["dram_bytes_per_launch"], "profiles/r1_dram_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+
+
 def min_ess_sum(summary, Nn):
     """Sum over profiles of min over the Nn+5 sampled parameters of Bulk_ESS."""
     cols = list(range(0, Nn + 5))  # theta, yGP, lambda, sigma  (br, lp__ are derived)
@@ -306,6 +320,7 @@ def main():
 
     if rank == 0:
         achieved = leap_all / world * f_grad(481, args.nn) / Ts_max / 1e12  # per-GPU TFLOP/s of the sampling kernel
+        traffic, traffic_src = measured_traffic(n, args.nn, args.n_warmup, args.n_iter, chains)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * T_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -313,7 +328,9 @@ def main():
             "draws_per_s": draws_per_s, "grad_per_s": leap_all / Ts_max,
             "config": workload_config(args, n),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": None,
+                         "frac": achieved / peak_tf, "traffic": traffic, "traffic_unit": "DRAM bytes per launch",
+                         "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": n * ((3 + args.nn) * 512 * 8 + chains * n_post * (args.nn + 7) * 8),
                          "peak_source": "DFMA-chain microbenchmark measured in this run (foct_fp64_peak); "
                                         "MEASURED_PEAKS.json has no fp64 figure",
                          "kernel": "foct::nuts_kernel", "algorithmic_flop_per_grad": f_grad(481, args.nn),
