@@ -287,17 +287,17 @@ __device__ __forceinline__ bool dev_inv3(const double* S, double* Pi) {
 }
 
 // f = -lp, g[3], H[9] (of -lp), chi2; all lanes receive all values.
-__device__ void mono_nlp(const double* __restrict__ blob, int npad, const DevProblem& P, int theta_prior,
+__device__ void mono_nlp(const double* __restrict__ blob, int NN, const DevProblem& P, int theta_prior,
                          const double* th, double& f, double* g, double* H, double& chi2, int lane) {
   double v[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) v[k] = 0.0;
   for (int i = lane; i < P.N; i += 32) {
-    const double w = blob[blob_index(i, 2, 0)], w2 = w * w;
-    const double t = blob[blob_index(i, 0, 0)] / th[2];
+    const double w = blob[blob_index(i, 2, NN)], w2 = w * w;
+    const double t = blob[blob_index(i, 0, NN)] / th[2];
     const double e = exp(-t);
     const double m = th[0] + th[1] * e;
-    const double r = blob[blob_index(i, 1, 0)] - m;
+    const double r = blob[blob_index(i, 1, NN)] - m;
     const double J0 = 1.0, J1 = e, J2 = th[1] * e * t / th[2];
     const double m23 = e * t / th[2];
     const double m33 = th[1] * e * (t * t - 2.0 * t) / (th[2] * th[2]);
@@ -325,7 +325,7 @@ __device__ void mono_nlp(const double* __restrict__ blob, int npad, const DevPro
   }
 }
 
-__global__ void __launch_bounds__(128) map_kernel(const double* __restrict__ blobs, size_t blob_stride, int npad,
+__global__ void __launch_bounds__(128) map_kernel(const double* __restrict__ blobs, size_t blob_stride, int NN,
                                                   const DevProblem* __restrict__ probs, int n, int theta_prior,
                                                   const double* __restrict__ init, double* theta_out,
                                                   double* hess_out, double* br_out, int* status_out) {
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(128) map_kernel(const double* __restrict__ blo
   } else {
     // log-linear start: theta1 just below min(y), regress log(y - theta1) on x
     double ymin = CUDART_INF, ymax = -CUDART_INF;
-    for (int i = lane; i < P.N; i += 32) { ymin = fmin(ymin, blob[blob_index(i, 1, 0)]); ymax = fmax(ymax, blob[blob_index(i, 1, 0)]); }
+    for (int i = lane; i < P.N; i += 32) { ymin = fmin(ymin, blob[blob_index(i, 1, NN)]); ymax = fmax(ymax, blob[blob_index(i, 1, NN)]); }
     for (int o = 16; o > 0; o >>= 1) {
       ymin = fmin(ymin, __shfl_xor_sync(FOCT_FULL, ymin, o));
       ymax = fmax(ymax, __shfl_xor_sync(FOCT_FULL, ymax, o));
@@ -348,9 +348,9 @@ __global__ void __launch_bounds__(128) map_kernel(const double* __restrict__ blo
     const double th1 = ymin - 0.05 * (ymax - ymin);
     double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = lane; i < P.N; i += 32) {
-      const double yy = blob[blob_index(i, 1, 0)] - th1;
+      const double yy = blob[blob_index(i, 1, NN)] - th1;
       if (yy > 0.0) {
-        const double x = blob[blob_index(i, 0, 0)] / P.c, ly = log(yy);
+        const double x = blob[blob_index(i, 0, NN)] / P.c, ly = log(yy);
         v[0] += x; v[1] += ly; v[2] += x * x; v[3] += x * ly; v[4] += 1.0;
       }
     }
@@ -361,9 +361,9 @@ __global__ void __launch_bounds__(128) map_kernel(const double* __restrict__ blo
     const double slope = (nn * sxy - sx * sy) / (nn * sxx - sx * sx);
     const double icpt = (sy - slope * sx) / nn;
     th[0] = th1; th[1] = exp(icpt);
-    th[2] = slope < 0.0 ? -P.c / slope : (blob[blob_index(P.N - 1, 0, 0)] - blob[0]) / P.c;
+    th[2] = slope < 0.0 ? -P.c / slope : (blob[blob_index(P.N - 1, 0, NN)] - blob[0]) / P.c;
   }
-  mono_nlp(blob, npad, P, theta_prior, th, f, g, H, c2, lane);
+  mono_nlp(blob, NN, P, theta_prior, th, f, g, H, c2, lane);
   double mu = 1e-3;
   int st = 1;
   for (int it = 0; it < 200; ++it) {
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(128) map_kernel(const double* __restrict__ blo
     if (!dev_inv3(A, Ai)) { mu *= 10.0; continue; }
     for (int a = 0; a < 3; ++a) step[a] = -(Ai[a * 3] * g[0] + Ai[a * 3 + 1] * g[1] + Ai[a * 3 + 2] * g[2]);
     for (int a = 0; a < 3; ++a) tn[a] = th[a] + step[a];
-    mono_nlp(blob, npad, P, theta_prior, tn, fn, gn, Hn, c2n, lane);
+    mono_nlp(blob, NN, P, theta_prior, tn, fn, gn, Hn, c2n, lane);
     if (isfinite(fn) && fn <= f) {
       double rel = 0.0;
       for (int a = 0; a < 3; ++a) rel = fmax(rel, fabs(step[a]) / (fabs(th[a]) + 1e-300));
@@ -425,6 +425,7 @@ struct foct_plan {
          *d_invm = nullptr, *d_nleap = nullptr, *d_ndiv = nullptr, *d_init = nullptr;
   DevProblem* d_probs = nullptr;
   int* d_counter = nullptr;
+  int* d_order = nullptr;  // work-item order: longest expected fits first (see plan_order)
   const InstEntry* inst = nullptr;
   int grid = 0, block = 0, blocks_per_sm = 0, regs = 0;
   size_t smem = 0;
@@ -436,7 +437,7 @@ static void plan_free(foct_plan* p) {
   cudaSetDevice(p->device);
   pool_free(p->d_blobs); pool_free(p->d_draws); pool_free(p->d_sparams); pool_free(p->d_summary);
   pool_free(p->d_stepsize); pool_free(p->d_invm); pool_free(p->d_nleap); pool_free(p->d_ndiv); pool_free(p->d_init);
-  pool_free(p->d_probs); pool_free(p->d_counter);
+  pool_free(p->d_probs); pool_free(p->d_counter); pool_free(p->d_order);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   if (p->ev2) cudaEventDestroy(p->ev2);
@@ -723,6 +724,34 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
   CUP(cudaGetDeviceProperties(&prop, device));
   const int groups = (cfg->chains + FOCT_CTA_CHAINS - 1) / FOCT_CTA_CHAINS;
   p->grid = (int)std::min<long long>((long long)n * groups, (long long)prop.multiProcessorCount * p->blocks_per_sm);
+  // Longest-processing-time-first scheduling.  Fits differ in cost by up to 4x (an unmodulated profile needs a third of
+  // the leapfrogs of a strongly modulated one), and with more work items than resident CTAs the order in which the
+  // persistent CTAs claim them decides how long the last ones run alone.  The Birge ratio of a mono-exponential MAP fit
+  // (map_kernel on the blobs already on the device, ~0.2 ms per 1000 profiles) ranks the fits by expected cost (Spearman
+  // 0.9 against the leapfrog count); the result of a fit does not depend on when it runs (per-profile Philox keys).
+  if (kind == FOCT_EXPGP && n * groups > p->grid && !std::getenv("FOCT_NO_LPT")) {
+    double *d_th = nullptr, *d_br = nullptr;
+    int* d_st = nullptr;
+    CUP(pool_malloc(&d_th, (size_t)n * 3 * sizeof(double)));
+    CUP(pool_malloc(&d_br, (size_t)n * sizeof(double)));
+    CUP(pool_malloc(&d_st, (size_t)n * sizeof(int)));
+    map_kernel<<<(n + 3) / 4, 128, 0, p->stream>>>(p->d_blobs, p->blob_stride, p->NN, p->d_probs, n, /*theta_prior flat*/ 1,
+                                                  nullptr, d_th, nullptr, d_br, d_st);
+    std::vector<double> br(n);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(br.data(), d_br, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    pool_free(d_th); pool_free(d_br); pool_free(d_st);
+    if (e != cudaSuccess) { plan_free(p); return fail(FOCT_ECUDA, "cost ranking failed: %s", cudaGetErrorString(e)); }
+    std::vector<int> order(n);
+    for (int j = 0; j < n; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      const double ca = std::isfinite(br[a]) ? br[a] : 1e300, cb = std::isfinite(br[b]) ? br[b] : 1e300;  // failed fit: assume costly
+      return ca > cb;
+    });
+    CUP(pool_malloc(&p->d_order, (size_t)n * sizeof(int)));
+    CUP(cudaMemcpy(p->d_order, order.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+  }
 #undef CUP
   *out = p;
   return 0;
@@ -752,7 +781,7 @@ extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
   K.init_buffer = c.init_buffer; K.term_buffer = c.term_buffer; K.window = c.window;
   K.seed = seed; K.init = p->d_init;
   K.draws = p->d_draws; K.sparams = p->d_sparams; K.stepsize = p->d_stepsize; K.inv_metric = p->d_invm;
-  K.n_leapfrog = p->d_nleap; K.n_divergent = p->d_ndiv; K.work_counter = p->d_counter;
+  K.n_leapfrog = p->d_nleap; K.n_divergent = p->d_ndiv; K.work_counter = p->d_counter; K.order = p->d_order;
   CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), p->stream));
   CU(cudaEventRecord(p->ev0, p->stream));
   CU(p->inst->launch_nuts(p->spec.modulation, p->grid, p->block, p->smem, p->stream, K));
@@ -939,7 +968,7 @@ extern "C" int foct_monoexp_map(const foct_problem* P, int n, const foct_model_s
       CUB(pool_malloc(&d_init, (size_t)n * 3 * sizeof(double)));
       CUB(cudaMemcpy(d_init, init, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
     }
-    map_kernel<<<(n + 3) / 4, 128>>>(d_blobs, stride, npad, d_probs, n, spec->theta_prior, d_init, d_th, d_H, d_br, d_st);
+    map_kernel<<<(n + 3) / 4, 128>>>(d_blobs, stride, 0, d_probs, n, spec->theta_prior, d_init, d_th, d_H, d_br, d_st);
     CUB(cudaGetLastError());
     CUB(cudaDeviceSynchronize());
     CUB(cudaMemcpy(theta, d_th, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost));

@@ -33,6 +33,7 @@ struct SamplerParams {
   double* n_leapfrog;       // [n_problems][chains][2]
   double* n_divergent;      // [n_problems][chains]
   int* work_counter;        // dynamic profile scheduler
+  const int* order;         // [n_problems] profile served by work item w (longest expected first), or nullptr
 };
 
 // log(exp(a) + exp(b)) and exp(b - lse) = w_b / (w_a + w_b) from ONE exponential (Stan computes
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(32 * FOCT_CTA_CHAINS, NutsBounds<NN>::MINB) nu
     __syncthreads();
     const int w = s_next;
     if (w >= n_items) break;
-    const int j = w / groups, chain = (w % groups) * FOCT_CTA_CHAINS + warp;
+    const int j = K.order ? K.order[w / groups] : w / groups, chain = (w % groups) * FOCT_CTA_CHAINS + warp;
     if (threadIdx.x == 0) s_prob = K.probs[j];
     stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase);
     __syncthreads();
