@@ -126,9 +126,69 @@ static void pool_free(void* p) {
   }
 }
 
+
+// Pinned staging buffers are cached the same way: cudaMallocHost / cudaFreeHost map and unmap the pages in every CUDA
+// context of the process and were measured at 0.4 - 0.7 s per call of foct_sample inside a process that also runs torch.
+namespace {
+struct PinnedPool {
+  std::mutex mu;
+  std::unordered_map<void*, size_t> live;
+  std::multimap<size_t, void*> idle;
+  size_t idle_bytes = 0;
+  static constexpr size_t kCap = (size_t)512 << 20;
+};
+PinnedPool g_pinned;
+}  // namespace
+
+template <class T>
+static cudaError_t pinned_malloc(T** out, size_t bytes) {
+  bytes = (std::max<size_t>(bytes, 1) + 4095) & ~(size_t)4095;
+  {
+    std::lock_guard<std::mutex> lk(g_pinned.mu);
+    auto it = g_pinned.idle.lower_bound(bytes);
+    if (it != g_pinned.idle.end() && it->first <= 2 * bytes + (1u << 20)) {
+      void* p = it->second;
+      g_pinned.live[p] = it->first;
+      g_pinned.idle_bytes -= it->first;
+      g_pinned.idle.erase(it);
+      *out = static_cast<T*>(p);
+      return cudaSuccess;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMallocHost(&p, bytes);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(g_pinned.mu);
+  g_pinned.live[p] = bytes;
+  *out = static_cast<T*>(p);
+  return cudaSuccess;
+}
+
+static void pinned_free(void* p) {
+  if (!p) return;
+  std::unique_lock<std::mutex> lk(g_pinned.mu);
+  auto it = g_pinned.live.find(p);
+  if (it == g_pinned.live.end()) { lk.unlock(); cudaFreeHost(p); return; }
+  const size_t bytes = it->second;
+  g_pinned.live.erase(it);
+  if (g_pinned.idle_bytes + bytes <= PinnedPool::kCap) {
+    g_pinned.idle.emplace(bytes, p);
+    g_pinned.idle_bytes += bytes;
+    return;
+  }
+  lk.unlock();
+  cudaFreeHost(p);
+}
+
 extern "C" void foct_release_cache(void) {
-  std::lock_guard<std::mutex> lk(g_pool.mu);
-  g_pool.release(-1);
+  {
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    g_pool.release(-1);
+  }
+  std::lock_guard<std::mutex> lk(g_pinned.mu);
+  for (auto& kv : g_pinned.idle) cudaFreeHost(kv.second);
+  g_pinned.idle.clear();
+  g_pinned.idle_bytes = 0;
 }
 
 // ------------------------------------------------------------------ setup kernel
@@ -487,8 +547,8 @@ static int build_device_batch(int kind, const foct_problem* P, int n, const foct
   double* h_up = nullptr;
   HostMeta* h_meta = nullptr;
   CU(cudaSetDevice(device));
-  CU(cudaMallocHost(&h_up, total * sizeof(double)));
-  if (cudaMallocHost(&h_meta, (size_t)n * sizeof(HostMeta)) != cudaSuccess) { cudaFreeHost(h_up); return fail(FOCT_ENOMEM, "pinned alloc"); }
+  CU(pinned_malloc(&h_up, total * sizeof(double)));
+  if (pinned_malloc(&h_meta, (size_t)n * sizeof(HostMeta)) != cudaSuccess) { pinned_free(h_up); return fail(FOCT_ENOMEM, "pinned alloc"); }
   size_t off = 0;
   int bad = -1;
   for (int j = 0; j < n; ++j) {
@@ -533,7 +593,7 @@ static int build_device_batch(int kind, const foct_problem* P, int n, const foct
 #undef CUB
   } while (0);
   pool_free(d_up); pool_free(d_meta); pool_free(d_status);
-  cudaFreeHost(h_up); cudaFreeHost(h_meta);
+  pinned_free(h_up); pinned_free(h_meta);
   if (rc) { pool_free(*d_blobs); pool_free(*d_probs); *d_blobs = nullptr; *d_probs = nullptr; return rc; }
   *NN_out = NN; *npad_out = npad; *stride_out = stride;
   return 0;
@@ -688,15 +748,18 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
   p->n_post = cfg->n_iter - cfg->n_warmup;
   p->n_saved = cfg->save_warmup ? cfg->n_iter : p->n_post;
 #define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int rc_ = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); plan_free(p); return rc_; } } while (0)
+  Trace tr("plan_create");
   CUP(cudaSetDevice(device));
   CUP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   CUP(cudaEventCreate(&p->ev0));
   CUP(cudaEventCreate(&p->ev1));
   CUP(cudaEventCreate(&p->ev2));
+  tr.mark("stream + events");
   if (int rc = build_device_batch(kind, P, n, spec, device, p->stream, &p->NN, &p->npad, &p->blob_stride, &p->d_blobs, &p->d_probs)) {
     plan_free(p);
     return rc;
   }
+  tr.mark("pack + upload + setup kernel");
   p->D = kind == FOCT_EXPGP ? p->NN + 5 : 3;
   p->P_out = p->D + 2;
   const size_t pc = (size_t)n * cfg->chains;
@@ -715,20 +778,22 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
     CUP(pool_malloc(&p->d_init, pc * p->D * sizeof(double)));
     CUP(cudaMemcpy(p->d_init, init_slice, pc * p->D * sizeof(double), cudaMemcpyHostToDevice));
   }
+  tr.mark("output buffers");
   p->inst = inst_for(p->NN);
   p->block = 32 * std::min(cfg->chains, FOCT_CTA_CHAINS);
   p->smem = p->blob_stride * sizeof(double);
   CUP(p->inst->nuts_occupancy(spec->modulation, p->block, p->smem, &p->blocks_per_sm, &p->regs));
   if (p->blocks_per_sm < 1) { plan_free(p); return fail(FOCT_EINVAL, "sampling kernel does not fit an SM (smem %zu B)", p->smem); }
-  cudaDeviceProp prop;
-  CUP(cudaGetDeviceProperties(&prop, device));
+  int n_sm = 0;  // (cudaGetDeviceProperties costs milliseconds; one attribute does not)
+  CUP(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
   const int groups = (cfg->chains + FOCT_CTA_CHAINS - 1) / FOCT_CTA_CHAINS;
-  p->grid = (int)std::min<long long>((long long)n * groups, (long long)prop.multiProcessorCount * p->blocks_per_sm);
+  p->grid = (int)std::min<long long>((long long)n * groups, (long long)n_sm * p->blocks_per_sm);
   // Longest-processing-time-first scheduling.  Fits differ in cost by up to 4x (an unmodulated profile needs a third of
   // the leapfrogs of a strongly modulated one), and with more work items than resident CTAs the order in which the
   // persistent CTAs claim them decides how long the last ones run alone.  The Birge ratio of a mono-exponential MAP fit
   // (map_kernel on the blobs already on the device, ~0.2 ms per 1000 profiles) ranks the fits by expected cost (Spearman
   // 0.9 against the leapfrog count); the result of a fit does not depend on when it runs (per-profile Philox keys).
+  tr.mark("occupancy + device properties");
   if (kind == FOCT_EXPGP && n * groups > p->grid && !std::getenv("FOCT_NO_LPT")) {
     double *d_th = nullptr, *d_br = nullptr;
     int* d_st = nullptr;
@@ -751,6 +816,7 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
     });
     CUP(pool_malloc(&p->d_order, (size_t)n * sizeof(int)));
     CUP(cudaMemcpy(p->d_order, order.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    tr.mark("cost ranking");
   }
 #undef CUP
   *out = p;
