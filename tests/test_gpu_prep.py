@@ -244,3 +244,38 @@ def test_prep_edge_cases(L, O):
     assert ci.shape == (1, 2) and al.tolist() == [0]
     with pytest.raises(FitOCTError):
         L.print_br(abi.FOCT_EXPGP, tiny, 1, abi.default_spec(abi.FOCT_EXPGP), np.array([1.0]))           # ... N - 3 - Nn < 1 is not
+
+
+def test_pripost_flow_prior_predictive_known_answers(L):
+    """priPost.R:2-16: the same call with prior_PD = 1 samples the prior.  (a) the three-parameter model with the MVN prior
+    switched on is a pure Gaussian target with known moments; (b) for fitExpGP the prior of (yGP, lambda) is a funnel that
+    NUTS mixes slowly in (as it does in Stan), so only robust statements are made: br is dropped, the prior is centred on
+    theta0 and wider than the posterior."""
+    from fitoct_b200 import api
+    S = synth.make_profiles(2, modulated_only=True)
+    x, y, uy = S["x"], S["Y"][0], S["UY"][0]
+    theta0 = S["theta0"][0]
+    sd0 = 0.05 * theta0
+    cor = np.array([[1.0, -0.5, 0.3], [-0.5, 1.0, -0.4], [0.3, -0.4, 1.0]])
+    Sigma0 = np.outer(sd0, sd0) * cor
+    # (a)
+    spec = abi.default_spec(abi.FOCT_MONOEXP)
+    spec.theta_prior = 0
+    b = abi.make_problems_dense(x, y[None, :], uy[None, :], theta0[None, :], Sigma0[None], Nn=0, prior_PD=1)
+    out = L.sample(abi.FOCT_MONOEXP, b, 1, spec, abi.default_cfg(chains=4, n_warmup=500, n_iter=2500, seed=11))
+    t = out["summary"][0]
+    assert np.all(np.abs(t[:3, 0] - theta0) < 4 * t[:3, 1])
+    assert np.allclose(t[:3, 2], sd0, rtol=0.06)
+    c = np.corrcoef(out["draws"][0].reshape(-1, 5)[:, :3].T)
+    assert np.max(np.abs(c - cor)) < 0.06
+    assert np.all(np.isnan(t[3]))                                                          # br is undefined without data
+    # (b)
+    kw = dict(dataType=2, Nn=10, gridType="internal", method="sample", theta0=theta0, Sigma0=Sigma0, lambda_rate=0.1,
+              rho_scale=0, nb_warmup=500, nb_iter=1500)
+    pri = api.fitExpGP(x, y, uy, prior_PD=1, **kw)
+    pos = api.fitExpGP(x, y, uy, prior_PD=0, **kw)
+    assert pri["prior_PD"] == 1 and np.all(np.isnan(pri["fit"].extract("br")["br"]))      # plotExpGP.R:42-43 drops br
+    tp, tq = pri["fit"].summary_table, pos["fit"].summary_table
+    assert np.all(np.abs(tp[:3, 0] - theta0) < 5 * tp[:3, 1] + 0.005 * sd0)
+    assert np.allclose(tp[:3, 2], sd0, rtol=0.3) and abs(tp[14, 0] - 1.0) < 0.05
+    assert np.all(tq[:3, 2] < tp[:3, 2]) and tq[14, 2] < tp[14, 2]                         # the data inform theta and sigma
