@@ -180,6 +180,12 @@ static void pinned_free(void* p) {
   cudaFreeHost(p);
 }
 
+// shared with foct_prep.cu (declared in foct_launch.h)
+cudaError_t device_cache_alloc(void** p, size_t bytes) { return pool_malloc(p, bytes); }
+void device_cache_free(void* p) { pool_free(p); }
+cudaError_t pinned_cache_alloc(void** p, size_t bytes) { return pinned_malloc(p, bytes); }
+void pinned_cache_free(void* p) { pinned_free(p); }
+
 extern "C" void foct_release_cache(void) {
   {
     std::lock_guard<std::mutex> lk(g_pool.mu);

@@ -459,13 +459,13 @@ static double chisq_quantile(double p, double ndf) {
 }
 
 struct PrepUpload {
-  std::vector<double> up;
+  double* up = nullptr;  // pinned staging: x | y per problem
   std::vector<PrepMeta> meta;
   size_t total = 0;
   int nkmax = 0;
   double* d_up = nullptr;
   PrepMeta* d_meta = nullptr;
-  ~PrepUpload() { cudaFree(d_up); cudaFree(d_meta); }
+  ~PrepUpload() { device_cache_free(d_up); device_cache_free(d_meta); pinned_cache_free(up); }
 };
 
 static int prep_upload(const foct_problem* P, int n, PrepUpload& U) {
@@ -477,7 +477,7 @@ static int prep_upload(const foct_problem* P, int n, PrepUpload& U) {
     tot += (size_t)P[j].N;
   }
   U.total = tot;
-  U.up.resize(2 * tot);
+  if (pinned_cache_alloc((void**)&U.up, 2 * tot * sizeof(double)) != cudaSuccess) return fail(FOCT_ENOMEM, "pinned staging buffer of %zu bytes", 2 * tot * sizeof(double));
   U.meta.resize(n);
   size_t off = 0, out = 0;
   for (int j = 0; j < n; ++j) {
@@ -490,19 +490,20 @@ static int prep_upload(const foct_problem* P, int n, PrepUpload& U) {
     off += 2 * (size_t)N;
     out += (size_t)N;
   }
-  if (cudaMalloc(&U.d_up, U.up.size() * sizeof(double)) != cudaSuccess || cudaMalloc(&U.d_meta, n * sizeof(PrepMeta)) != cudaSuccess)
-    return fail(FOCT_ENOMEM, "device allocation of %zu bytes failed", U.up.size() * sizeof(double));
-  if (cudaMemcpy(U.d_up, U.up.data(), U.up.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+  if (device_cache_alloc((void**)&U.d_up, 2 * tot * sizeof(double)) != cudaSuccess ||
+      device_cache_alloc((void**)&U.d_meta, n * sizeof(PrepMeta)) != cudaSuccess)
+    return fail(FOCT_ENOMEM, "device allocation of %zu bytes failed", 2 * tot * sizeof(double));
+  if (cudaMemcpy(U.d_up, U.up, 2 * tot * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(U.d_meta, U.meta.data(), n * sizeof(PrepMeta), cudaMemcpyHostToDevice) != cudaSuccess)
     return fail(FOCT_ECUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
 
-struct DevBuf {  // frees on scope exit
+struct DevBuf {  // returns the block to the cache on scope exit
   void* p = nullptr;
-  ~DevBuf() { cudaFree(p); }
+  ~DevBuf() { device_cache_free(p); }
   template <class T> T* as() { return static_cast<T*>(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+  cudaError_t alloc(size_t bytes) { return device_cache_alloc(&p, bytes ? bytes : 8); }
 };
 
 static double ndf_of(int kind, const foct_problem& P, const foct_model_spec* spec) {
