@@ -78,6 +78,12 @@ class SamplerCfg(C.Structure):
         ("window", C.c_int),
         ("n_devices", C.c_int),
         ("devices", C.POINTER(C.c_int)),
+        # ABI 2: continuation / run until converged
+        ("inv_metric_init", c_double_p),
+        ("stepsize_init", c_double_p),
+        ("iter_offset", C.c_int),
+        ("rhat_target", C.c_double),
+        ("max_extend", C.c_int),
     ]
 
 
@@ -90,6 +96,8 @@ class Result(C.Structure):
         ("inv_metric", c_double_p),
         ("n_leapfrog", c_double_p),
         ("n_divergent", c_double_p),
+        ("last_q", c_double_p),
+        ("n_extend", C.POINTER(C.c_int)),
     ]
 
 

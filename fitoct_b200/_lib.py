@@ -132,11 +132,31 @@ def alloc_result(kind, n_problems, Nn, cfg: abi.SamplerCfg, draws=True, summary=
         inv_metric=np.full((n_problems, Cn, D), np.nan),
         n_leapfrog=np.zeros((n_problems, Cn, 2)),
         n_divergent=np.zeros((n_problems, Cn)),
+        last_q=np.full((n_problems, Cn, D), np.nan),
+        n_extend=np.zeros(n_problems, dtype=np.int32),
     )
     R = abi.Result()
     for k, v in out.items():
-        setattr(R, k, abi.as_ptr(v))
+        setattr(R, k, v.ctypes.data_as(C.POINTER(C.c_int)) if v is not None and v.dtype == np.int32 else abi.as_ptr(v))
     return out, R
+
+
+def continuation_cfg(cfg: abi.SamplerCfg, prev: dict, n_more: int, iters_done: int, keep: list) -> abi.SamplerCfg:
+    """Sampler options that continue the run whose result is `prev` for `n_more` draws: no warm-up, the adapted metric
+    and step size, start = the last state, Philox sites after the `iters_done` iterations already made.  `keep`
+    receives the arrays the returned struct points into."""
+    c = abi.SamplerCfg()
+    C.memmove(C.byref(c), C.byref(cfg), C.sizeof(abi.SamplerCfg))
+    init = np.ascontiguousarray(prev["last_q"], dtype=np.float64)
+    invm = np.ascontiguousarray(prev["inv_metric"], dtype=np.float64)
+    eps = np.ascontiguousarray(prev["stepsize"], dtype=np.float64)
+    keep += [init, invm, eps]
+    c.n_warmup, c.n_iter, c.save_warmup = 0, int(n_more), 0
+    c.init_mode, c.init = 2, abi.as_ptr(init)
+    c.inv_metric_init, c.stepsize_init = abi.as_ptr(invm), abi.as_ptr(eps)
+    c.iter_offset = int(iters_done)
+    c.rhat_target, c.max_extend = 0.0, 0
+    return c
 
 
 def sample(kind: int, batch: abi.ProblemBatch, n_problems: int, spec: abi.ModelSpec, cfg: abi.SamplerCfg, draws=True,

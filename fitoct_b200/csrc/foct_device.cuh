@@ -100,9 +100,14 @@ __host__ __device__ __forceinline__ size_t blob_index(int i, int r, int NN) {
 // variant with 18 instructions and 14 constants; the table version won by 3-4 % because fewer constants stay in
 // registers across the sweep.)  Constants are literals so that ptxas may feed them as immediate / uniform operands.
 #define FEXP_MAGIC 6755399441055744.0     /* 1.5 * 2^52 */
-#define FEXPT_L2E32 0x1.71547652b82fep+5
-#define FEXPT_NHI (-0x1.62e42fefa39efp-6)
-#define FEXPT_NLO (-0x1.abc9e3b39803fp-61)
+// Constants with a zero low word are fp64 IMMEDIATES (no register, two register-file reads per DFMA):
+//  - 32/ln2 only selects n; rounded to 21 bits it moves n by at most one near a tie, i.e. |r| <= 1.02 ln2/64;
+//  - Cody-Waite split of ln2/32 with a 21-bit head, so that n * head is exact and head is an immediate;
+//  - 1/120 and 1/720 multiply r^5 <= 1.5e-10 and r^6 <= 1.7e-12: their 6e-8 relative rounding is far below 1 ulp.
+#define FEXPT_L2E32 0x1.71547p+5
+#define FEXPT_NHI (-0x1.62e43p-6)
+#define FEXPT_C5 0x1.11111p-7
+#define FEXPT_C6 0x1.6c16cp-10
 static __device__ const double FEXP_TAB[32] = {
     0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
     0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
@@ -112,28 +117,47 @@ static __device__ const double FEXP_TAB[32] = {
     0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
     0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
     0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+// The three constants that need all 53 bits cannot be immediates.  Round 1 wrote every constant as a literal and ptxas
+// parked each in a vector register pair for the whole sweep (14 registers; a DFMA with three register-file operands
+// issues every 3.0 cycles instead of 2.06, profiles/r1_microbench.txt).  From __constant__ memory ptxas can feed them
+// through uniform registers (`DFMA R2, R4, UR8, R2`) where it has them to spare.
+__constant__ double FEXP_K[4] = {
+    0x1.05c610ca86c39p-34 /* head - ln2/32 */, 0x1.5555555555555p-3 /* 1/6 */, 0x1.5555555555555p-5 /* 1/24 */, 0.0};
 
-// Branch-free: |x| >= 700 saturates to 0 / +inf (exp(-700) ~ 1e-304 is below anything the model can resolve;
-// a positive argument that large only arises from a negative decay length, i.e. a state that is non-finite
-// anyway), NaN propagates.  Being branch-free lets ptxas interleave two points of the sweep.
+// E(r) = exp(r) on |r| <= ln2/64: degree-6 Taylor polynomial in Horner form — six DFMAs with an immediate or uniform
+// operand each (12.4 pipe cycles; round 1's Estrin form was seven operations, three of them with three register
+// operands: 19 cycles.  The kernel is bound by fp64 issue, not by the length of this chain).
+__device__ __forceinline__ double fexp_poly(double r) {
+  double p = fma(r, FEXPT_C6, FEXPT_C5);
+  p = fma(p, r, FEXP_K[2]);
+  p = fma(p, r, FEXP_K[1]);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  return fma(p, r, 1.0);
+}
+
+// Assemble 2^m * p and saturate on the INTEGER pipe: |x| >= 700 gives 0 / +inf (exp(-700) ~ 1e-304 is below anything
+// the model can resolve; a positive argument that large only arises from a negative decay length, i.e. a state that is
+// non-finite anyway), NaN propagates through the polynomial.  hx = high word of x.  (Round 1 compared x in fp64:
+// two DSETP on the fp64 pipe and four FSEL per point.)
+__device__ __forceinline__ double fexp_scale(double p, int n, int hx) {
+  int hi = __double2hiint(p) + ((n >> 5) << 20), lo = __double2loint(p);
+  // |x| in [700, inf]  <=>  0x4085E000 <= (hx & 0x7fffffff) <= 0x7ff00000; NaN lies above
+  const bool big = (unsigned)((hx & 0x7fffffff) - 0x4085E000) <= (unsigned)(0x7ff00000 - 0x4085E000);
+  hi = big ? (hx < 0 ? 0 : 0x7ff00000) : hi;
+  lo = big ? 0 : lo;
+  return __hiloint2double(hi, lo);
+}
+
+// exp(x), branch-free (ptxas can interleave the points of the sweep).
 __device__ __forceinline__ double fexp(double x) {
   const double t = fma(x, FEXPT_L2E32, FEXP_MAGIC);
   const double nd = t - FEXP_MAGIC;
   const int n = __double2loint(t);
   const double tj = __ldg(&FEXP_TAB[n & 31]);
   double r = fma(nd, FEXPT_NHI, x);
-  r = fma(nd, FEXPT_NLO, r);
-  const double r2 = r * r;
-  double pa = fma(0x1.5555555555555p-3, r, 0.5);
-  double pb = fma(0x1.1111111111111p-7, r, 0x1.5555555555555p-5);
-  pb = fma(0x1.6c16c16c16c17p-10, r2, pb);
-  pa = fma(pb, r2, pa);
-  pa = fma(pa, r2, 1.0 + r);
-  const double p = pa * tj;
-  double res = __hiloint2double(__double2hiint(p) + ((n >> 5) << 20), __double2loint(p));
-  res = x < -700.0 ? 0.0 : res;
-  res = x > 700.0 ? CUDART_INF : res;
-  return res;
+  r = fma(nd, FEXP_K[0], r);
+  return fexp_scale(fexp_poly(r) * tj, n, __double2hiint(x));
 }
 
 // Branch-free reciprocal: MUFU.RCP64H seed (~20 bits), one cubic and one quadratic Newton step (the fast
@@ -155,21 +179,27 @@ __device__ __forceinline__ double selp(bool c, double a, double b) {
   asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b), "r"((int)c));
   return r;
 }
-__device__ __forceinline__ double warp_sum(double v) {
+// Lane groups: a chain is owned by a group of W lanes — the whole warp (W = 32) or one half of it (W = 16, two chains
+// per warp: foct_nuts2.cuh).  Shuffles carry the group width, so a butterfly or a broadcast never leaves its group;
+// `mask` names the lanes that execute the call together (FOCT_FULL when the warp is converged, the half's own 16 bits
+// inside per-chain control flow).
+template <int W = 32>
+__device__ __forceinline__ double warp_sum(double v, unsigned mask = FOCT_FULL) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FOCT_FULL, v, o);
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, W);
   return v;
 }
-__device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(FOCT_FULL, v, src); }
-// Transposed ("reduce-scatter") warp reduction of KP (= 8, 16 or 32) per-lane accumulators: KP-1 + (5-log2 KP)
-// 64-bit shuffles instead of 5*KP.  On return, the full sum of accumulator index a is returned to lane a
-// (a < KP); lanes >= KP get accumulator (lane mod KP).
-template <int KP>
-__device__ __forceinline__ double warp_reduce_scatter(double (&v)[KP], int lane) {
-  static_assert(KP == 8 || KP == 16 || KP == 32, "KP");
+template <int W = 32>
+__device__ __forceinline__ double bcast(double v, int src, unsigned mask = FOCT_FULL) { return __shfl_sync(mask, v, src, W); }
+// Transposed ("reduce-scatter") reduction of KP per-lane accumulators over a group of W lanes: KP-1 + log2(W/KP)
+// 64-bit shuffles instead of KP log2 W.  On return, the full sum of accumulator index a is returned to lane a of the
+// group (a < KP); lanes >= KP get accumulator (lane mod KP).  `lane` is the index inside the group.
+template <int KP, int W = 32>
+__device__ __forceinline__ double warp_reduce_scatter(double (&v)[KP], int lane, unsigned mask = FOCT_FULL) {
+  static_assert((KP == 8 || KP == 16 || KP == 32) && KP <= W, "KP");
   int width = KP;
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
+  for (int off = W / 2; off >= 1; off >>= 1) {
     if (width > 1) {
       const int half = width / 2;
       const bool upper = (lane & off) != 0;
@@ -177,18 +207,17 @@ __device__ __forceinline__ double warp_reduce_scatter(double (&v)[KP], int lane)
       for (int j = 0; j < half; ++j) {
         const double keep = selp(upper, v[j + half], v[j]);
         const double send = selp(upper, v[j], v[j + half]);
-        v[j] = keep + __shfl_xor_sync(FOCT_FULL, send, off);
+        v[j] = keep + __shfl_xor_sync(mask, send, off, W);
       }
       width = half;
     } else {
-      v[0] += __shfl_xor_sync(FOCT_FULL, v[0], off);
+      v[0] += __shfl_xor_sync(mask, v[0], off, W);
     }
   }
-  // lane L now holds accumulator index: bits of L taken from the top (off=16 first) for log2(KP) levels
-  // i.e. idx = L >> (5 - log2 KP).  Route index a to lane a.
-  constexpr int SH = KP == 32 ? 0 : (KP == 16 ? 1 : 2);
+  // lane L now holds accumulator index L >> log2(W / KP).  Route index a to lane a.
+  constexpr int SH = KP == W ? 0 : (2 * KP == W ? 1 : 2);
   if (SH == 0) return v[0];
-  return __shfl_sync(FOCT_FULL, v[0], (lane << SH) & 31);
+  return __shfl_sync(mask, v[0], (lane << SH) & (W - 1), W);
 }
 
 // ---------------------------------------------------------------- model sweep
@@ -212,28 +241,33 @@ struct Dims {
 // flight; two inlined copies of a one-point body were scheduled back to back — profiles/r1_ncu_nuts_v2).
 // Lane-private loads at compile-time offsets from pp, ~52 fp64 instructions per point, no branches.
 // Raw sums go to acc[] (theta2 / theta3 factors are applied once, after the reduction).
-template <int NN, int MOD, int KP, int ZI, int U>
-__device__ __forceinline__ void sweep_points(const double* __restrict__ pp, double th1, double th2, double th3, double r3,
+// W = 32: point u of the iteration sits one pass block further (pp + u * block); W = 16 (half-warp lane groups, pp
+// carries the lane index inside the group): the points are the two 16-point halves of consecutive 32-point blocks.
+template <int NN, int MOD, int KP, int ZI, int U, int W = 32>
+__device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, double th1, double th2, double th3, double r3,
                                              const double (&yg)[NN > 0 ? NN : 1], double (&acc)[KP]) {
-  constexpr int STRIDE = (3 + NN) * 32;
+  static_assert(W == 32 || (W == 16 && U % 2 == 0), "half-warp groups take the two halves of a block together");
+  constexpr int STRIDE = W == 32 ? (3 + NN) * 32 : 16;
+  const double* __restrict__ pp = pp0;
+#define FOCT_PT(u) (W == 32 ? (u) * STRIDE : ((u) >> 1) * (3 + NN) * 32 + ((u) & 1) * 16)
   double b[U][NN > 0 ? NN : 1];
   double dl0[U], dl1[U], s[U], cx[U], y[U], ws[U], r[U], t[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) { dl0[u] = 0.0; dl1[u] = 0.0; }
+  for (int u = 0; u < U; ++u) { dl0[u] = 1.0; dl1[u] = 0.0; }  // s = 1 + dL: the 1 rides in the first partial sum
 #pragma unroll
   for (int k = 0; k < NN; ++k) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      b[u][k] = pp[u * STRIDE + (3 + k) * 32];
+      b[u][k] = pp[FOCT_PT(u) + (3 + k) * 32];
       if (k & 1) dl1[u] = fma(b[u][k], yg[k], dl1[u]); else dl0[u] = fma(b[u][k], yg[k], dl0[u]);
     }
   }
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    s[u] = 1.0 + (dl0[u] + dl1[u]);
-    cx[u] = pp[u * STRIDE];
-    y[u] = pp[u * STRIDE + 32];
-    ws[u] = pp[u * STRIDE + 64];  // 1/uy; the 1/sigma^2 common to every sum is applied once after the reduction
+    s[u] = dl0[u] + dl1[u];
+    cx[u] = pp[FOCT_PT(u)];
+    y[u] = pp[FOCT_PT(u) + 32];
+    ws[u] = pp[FOCT_PT(u) + 64];  // 1/uy; the 1/sigma^2 common to every sum is applied once after the reduction
   }
   // reciprocal of the local decay length (length modulation with a GP); otherwise r3 is hoisted
   if (MOD == 0 && NN > 0) {
@@ -263,36 +297,31 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
   }
 #pragma unroll
   for (int u = 0; u < U; ++u) t[u] = cx[u] * r[u];
-  // e = exp(-t): table-driven variant (see FEXP_TAB), staged across the U points
-  double x[U], tt[U], nd[U], rr[U], r2[U], pa[U], pb[U], tj[U], e[U];
+  // e = exp(-t): table-driven (see FEXP_TAB), staged across the U points
+  double tt[U], nd[U], rr[U], pe[U], tj[U], e[U];
   int n[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) { x[u] = -t[u]; tt[u] = fma(x[u], FEXPT_L2E32, FEXP_MAGIC); }
+  for (int u = 0; u < U; ++u) tt[u] = fma(-t[u], FEXPT_L2E32, FEXP_MAGIC);
 #pragma unroll
   for (int u = 0; u < U; ++u) { nd[u] = tt[u] - FEXP_MAGIC; n[u] = __double2loint(tt[u]); tj[u] = __ldg(&FEXP_TAB[n[u] & 31]); }
 #pragma unroll
-  for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXPT_NHI, x[u]);
+  for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXPT_NHI, -t[u]);
 #pragma unroll
-  for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXPT_NLO, rr[u]);
+  for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXP_K[0], rr[u]);
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    r2[u] = rr[u] * rr[u];
-    pa[u] = fma(0x1.5555555555555p-3, rr[u], 0.5);                         // 1/2 + r/6
-    pb[u] = fma(0x1.1111111111111p-7, rr[u], 0x1.5555555555555p-5);        // 1/24 + r/120
-  }
+  for (int u = 0; u < U; ++u) pe[u] = fma(rr[u], FEXPT_C6, FEXPT_C5);
 #pragma unroll
-  for (int u = 0; u < U; ++u) pb[u] = fma(0x1.6c16c16c16c17p-10, r2[u], pb[u]);   // + r^2/720
+  for (int u = 0; u < U; ++u) pe[u] = fma(pe[u], rr[u], FEXP_K[2]);
 #pragma unroll
-  for (int u = 0; u < U; ++u) pa[u] = fma(pb[u], r2[u], pa[u]);
+  for (int u = 0; u < U; ++u) pe[u] = fma(pe[u], rr[u], FEXP_K[1]);
 #pragma unroll
-  for (int u = 0; u < U; ++u) pa[u] = fma(pa[u], r2[u], 1.0 + rr[u]);              // E(r)
+  for (int u = 0; u < U; ++u) pe[u] = fma(pe[u], rr[u], 0.5);
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const double p = pa[u] * tj[u];
-    double res = __hiloint2double(__double2hiint(p) + ((n[u] >> 5) << 20), __double2loint(p));
-    res = x[u] < -700.0 ? 0.0 : res;
-    e[u] = x[u] > 700.0 ? CUDART_INF : res;
-  }
+  for (int u = 0; u < U; ++u) pe[u] = fma(pe[u], rr[u], 1.0);
+#pragma unroll
+  for (int u = 0; u < U; ++u) pe[u] = fma(pe[u], rr[u], 1.0);
+#pragma unroll
+  for (int u = 0; u < U; ++u) e[u] = fexp_scale(pe[u] * tj[u], n[u], __double2hiint(t[u]) ^ 0x80000000);
   if (MOD == 0) {
     double m[U], z[U], gi[U], ge[U], qq[U];
 #pragma unroll
@@ -303,14 +332,18 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
     for (int u = 0; u < U; ++u) gi[u] = z[u] * ws[u];
 #pragma unroll
     for (int u = 0; u < U; ++u) ge[u] = gi[u] * e[u];
+    // qq s = ge t / theta3 (r s = 1/theta3): the theta3 sum needs neither qq nor s, and its 1/theta3 moves behind the reduction
+    double gt[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) qq[u] = ge[u] * t[u] * r[u];
+    for (int u = 0; u < U; ++u) gt[u] = ge[u] * t[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) qq[u] = gt[u] * r[u];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       acc[ZI] = fma(z[u], z[u], acc[ZI]);
       acc[0] += gi[u];
       acc[1] += ge[u];
-      acc[2] = fma(qq[u], s[u], acc[2]);
+      acc[2] += gt[u];
     }
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -342,13 +375,18 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp, doub
   }
 }
 
+#undef FOCT_PT
+
 // Fused sweep over the staged profile.  qd = this lane's component of q.  Everything a lane needs from
 // the other lanes is fetched with shuffles up front; the per-point loop touches only shared memory and
 // processes two passes (64 points per warp) per iteration so that two independent dependency chains are
 // in flight per warp (the fp64 pipe was latency-, not throughput-bound with one: profiles/r1_*v1*).
-template <int NN, int MOD>
+// W = 32: one chain per warp.  W = 16: one chain per half-warp — `lane` is then the index inside the half, both halves
+// must call together (full-mask shuffles of width 16) and walk the same profile, so every LDS is a 16-word broadcast.
+template <int NN, int MOD, int W = 32>
 __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, const DevProblem& P, const DevSpec& S,
                                                double qd, int lane) {
+  static_assert(W == 32 || Dims<NN>::D <= 16, "a half-warp holds at most 16 components");
   FOCT_T(t_g0);
   using DM = Dims<NN>;
   constexpr int D = DM::D;
@@ -360,12 +398,12 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
 #define FOCT_UNROLL_MAXNN 12
 #endif
   constexpr int UNROLL = NN <= FOCT_UNROLL_MAXNN ? FOCT_UNROLL : 1;  // above 12 control points the second basis row spills (measured: Nn=15 is 9 % faster with 1)
-  const double th1 = bcast(qd, 0), th2 = bcast(qd, 1), th3 = bcast(qd, 2);
+  const double th1 = bcast<W>(qd, 0), th2 = bcast<W>(qd, 1), th3 = bcast<W>(qd, 2);
   double yg[NN > 0 ? NN : 1];
 #pragma unroll
-  for (int k = 0; k < NN; ++k) yg[k] = bcast(qd, 3 + k);
-  const double qlam = DM::GP ? bcast(qd, 3 + NN) : 0.0;
-  const double qsig = DM::GP ? bcast(qd, 4 + NN) : 0.0;
+  for (int k = 0; k < NN; ++k) yg[k] = bcast<W>(qd, 3 + k);
+  const double qlam = DM::GP ? bcast<W>(qd, 3 + NN) : 0.0;
+  const double qsig = DM::GP ? bcast<W>(qd, 4 + NN) : 0.0;
   const double lam = DM::GP ? fexp(qlam) : 1.0;
   const double sig = DM::GP ? fexp(qsig) : 1.0;
   const double isig = DM::GP ? frcp(sig) : 1.0;
@@ -428,29 +466,35 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
   Eval out;
   double zz = 0.0;
   if (!P.prior_PD) {
-    const double r3 = 1.0 / th3;
+    const double r3 = frcp(th3);  // (a full division drags its exponent-range slow path into every leaf)
     constexpr int ROWS = 3 + NN;
     const double* pp = blob + lane;
     FOCT_T(t_l0);
     FOCT_TADD(3, t_g0, t_l0);
     int pass = 0;
-    if (UNROLL >= 2) {
+    if (W == 16) {
+      // one 32-point block per iteration: its two 16-point halves are the two points in flight per lane
 #pragma unroll 1
-      for (; pass + UNROLL <= P.npass; pass += UNROLL, pp += UNROLL * ROWS * 32)
-        sweep_points<NN, MOD, KP, ZI, UNROLL>(pp, th1, th2, th3, r3, yg, acc);
+      for (; pass < P.npass; ++pass, pp += ROWS * 32) sweep_points<NN, MOD, KP, ZI, 2, W>(pp, th1, th2, th3, r3, yg, acc);
+    } else {
+      if (UNROLL >= 2) {
+#pragma unroll 1
+        for (; pass + UNROLL <= P.npass; pass += UNROLL, pp += UNROLL * ROWS * 32)
+          sweep_points<NN, MOD, KP, ZI, UNROLL>(pp, th1, th2, th3, r3, yg, acc);
+      }
+#pragma unroll 1
+      for (; pass < P.npass; ++pass, pp += ROWS * 32) sweep_points<NN, MOD, KP, ZI, 1>(pp, th1, th2, th3, r3, yg, acc);
     }
-#pragma unroll 1
-    for (; pass < P.npass; ++pass, pp += ROWS * 32) sweep_points<NN, MOD, KP, ZI, 1>(pp, th1, th2, th3, r3, yg, acc);
     FOCT_T(t_l1);
     FOCT_TADD(1, t_l0, t_l1);
-    const double red = warp_reduce_scatter<KP>(acc, lane) * isig2;  // every sum carries the factor 1/sigma^2
-    zz = bcast(red, ZI);
+    const double red = warp_reduce_scatter<KP, W>(acc, lane) * isig2;  // every sum carries the factor 1/sigma^2
+    zz = bcast<W>(red, ZI);
     FOCT_T(t_l2);
     FOCT_TADD(2, t_l1, t_l2);
     // scale the raw sums into gradient components
     double scale = 1.0;
     if (MOD == 0) {
-      if (lane == 2) scale = th2;
+      if (lane == 2) scale = th2 * r3;
       if (lane >= 3 && lane < 3 + NN) scale = th2 * th3;
     } else {
       if (lane == 2) scale = th2 * r3;

@@ -1,6 +1,7 @@
 // foct_inst.cu — instantiates the sampling and parity kernels for ONE control-point count
 // (-DFOCT_INST_NN=<NN>, NN = 0 is the mono-exponential) and both modulation sites.
 #include "foct_launch.h"
+#include "foct_nuts2.cuh"
 
 #ifndef FOCT_INST_NN
 #error "compile with -DFOCT_INST_NN=<NN>"
@@ -22,6 +23,27 @@ __global__ void __launch_bounds__(128) logp_kernel(const LogpParams K) {
     if (threadIdx.x == 0) s_prob = K.probs[j];
     stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase);
     __syncthreads();
+    if constexpr (D <= 16) {
+      if (K.width == 16) {
+        // the half-warp evaluation used by the two-chains-per-warp sampler: each half takes its own q, both halves
+        // of a warp call together (full-mask shuffles of width 16)
+        const int l = lane & 15, half = lane >> 4;
+        for (int base = 0; base < K.n_q; base += 2 * nwarp) {
+          const int iq = base + 2 * warp + half;
+          const bool ok = iq < K.n_q;
+          const size_t r = (size_t)j * K.n_q + (ok ? iq : 0);
+          const double qd = ok && l < D ? K.q[r * D + l] : 0.0;
+          const Eval ev = warp_logp_grad<NN, MOD, 16>(smem, s_prob, K.spec, qd, l);
+          if (ok && l < D) K.grad[r * D + l] = ev.g;
+          if (ok && l == 0) {
+            K.lp[r] = ev.lp;
+            if (K.chi2) K.chi2[r] = ev.chi2;
+          }
+        }
+        __syncthreads();
+        continue;
+      }
+    }
     for (int iq = warp; iq < K.n_q; iq += nwarp) {
       const size_t r = (size_t)j * K.n_q + iq;
       const double qd = lane < D ? K.q[r * D + lane] : 0.0;
@@ -352,19 +374,40 @@ static cudaError_t launch_map(int mod, int grid, size_t smem, cudaStream_t st, c
   return cudaGetLastError();
 }
 
+// Nn <= 11 (D <= 16) and the mono-exponential run two chains per warp (foct_nuts2.cuh); FOCT_NO_PAIR=1 forces the
+// one-chain-per-warp kernel for A/B runs.
+template <int NN>
+static bool use_pair() {
+  if (Dims<NN>::D > 16) return false;
+  static const bool off = std::getenv("FOCT_NO_PAIR") != nullptr;
+  return !off;
+}
+template <int NN>
+static int nuts_block(int chains) {
+  if (use_pair<NN>()) return 32 * ((std::min(chains, FOCT_PAIR_CTA_CHAINS) + 1) / 2);
+  return 32 * std::min(chains, FOCT_CTA_CHAINS);
+}
+
+template <int NN, int MOD>
+static cudaError_t launch_nuts_mod(int grid, int block, size_t smem, cudaStream_t st, const SamplerParams& K) {
+  cudaError_t e;
+  if constexpr (Dims<NN>::D <= 16) {
+    if (use_pair<NN>()) {
+      e = cudaFuncSetAttribute(nuts2_kernel<NN, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      nuts2_kernel<NN, MOD><<<grid, block, smem, st>>>(K);
+      return cudaGetLastError();
+    }
+  }
+  e = cudaFuncSetAttribute(nuts_kernel<NN, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  nuts_kernel<NN, MOD><<<grid, block, smem, st>>>(K);
+  return cudaGetLastError();
+}
+
 template <int NN>
 static cudaError_t launch_nuts(int mod, int grid, int block, size_t smem, cudaStream_t st, const SamplerParams& K) {
-  cudaError_t e;
-  if (mod == 0) {
-    e = cudaFuncSetAttribute(nuts_kernel<NN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    nuts_kernel<NN, 0><<<grid, block, smem, st>>>(K);
-  } else {
-    e = cudaFuncSetAttribute(nuts_kernel<NN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    nuts_kernel<NN, 1><<<grid, block, smem, st>>>(K);
-  }
-  return cudaGetLastError();
+  return mod == 0 ? launch_nuts_mod<NN, 0>(grid, block, smem, st, K) : launch_nuts_mod<NN, 1>(grid, block, smem, st, K);
 }
 
 template <int NN>
@@ -382,25 +425,33 @@ static cudaError_t launch_logp(int mod, int grid, int block, size_t smem, cudaSt
   return cudaGetLastError();
 }
 
-template <int NN>
-static cudaError_t nuts_occupancy(int mod, int block, size_t smem, int* blocks_per_sm, int* regs) {
+template <class KernelT>
+static cudaError_t occupancy_of(KernelT kernel, int block, size_t smem, int* blocks_per_sm, int* regs) {
   cudaFuncAttributes fa;
-  cudaError_t e;
-  if (mod == 0) {
-    e = cudaFuncSetAttribute(nuts_kernel<NN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, nuts_kernel<NN, 0>, block, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&fa, nuts_kernel<NN, 0>);
-  } else {
-    e = cudaFuncSetAttribute(nuts_kernel<NN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, nuts_kernel<NN, 1>, block, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&fa, nuts_kernel<NN, 1>);
-  }
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, block, smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncGetAttributes(&fa, kernel);
   if (e == cudaSuccess && regs) *regs = fa.numRegs;
   return e;
+}
+
+// Launch geometry of the sampling kernel for `chains` chains per profile: threads per CTA, resident CTAs per SM,
+// chains a CTA serves per work item, registers per thread.
+template <int NN>
+static cudaError_t nuts_occupancy(int mod, int chains, size_t smem, int* block, int* blocks_per_sm, int* cta_chains, int* regs) {
+  *block = nuts_block<NN>(chains);
+  if constexpr (Dims<NN>::D <= 16) {
+    if (use_pair<NN>()) {
+      *cta_chains = FOCT_PAIR_CTA_CHAINS;
+      return mod == 0 ? occupancy_of(nuts2_kernel<NN, 0>, *block, smem, blocks_per_sm, regs)
+                      : occupancy_of(nuts2_kernel<NN, 1>, *block, smem, blocks_per_sm, regs);
+    }
+  }
+  *cta_chains = FOCT_CTA_CHAINS;
+  return mod == 0 ? occupancy_of(nuts_kernel<NN, 0>, *block, smem, blocks_per_sm, regs)
+                  : occupancy_of(nuts_kernel<NN, 1>, *block, smem, blocks_per_sm, regs);
 }
 
 #define FOCT_CAT_(a, b) a##b

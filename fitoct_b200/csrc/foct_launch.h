@@ -23,6 +23,7 @@ struct LogpParams {
   double* lp;    // [n_problems][n_q]
   double* grad;  // [n_problems][n_q][D]
   double* chi2;  // [n_problems][n_q] or nullptr
+  int width;     // lanes per evaluation: 16 = the half-warp path of the two-chains-per-warp sampler (D <= 16), else 32
 };
 
 struct MapParams {
@@ -58,7 +59,7 @@ struct InstEntry {
   int NN;  // 0 = mono-exponential
   cudaError_t (*launch_nuts)(int mod, int grid, int block, size_t smem, cudaStream_t st, const SamplerParams& K);
   cudaError_t (*launch_logp)(int mod, int grid, int block, size_t smem, cudaStream_t st, const LogpParams& K);
-  cudaError_t (*nuts_occupancy)(int mod, int block, size_t smem, int* blocks_per_sm, int* regs);
+  cudaError_t (*nuts_occupancy)(int mod, int chains, size_t smem, int* block, int* blocks_per_sm, int* cta_chains, int* regs);
   cudaError_t (*launch_map)(int mod, int grid, size_t smem, cudaStream_t st, const MapParams& K);
   cudaError_t (*launch_vb)(int mod, int grid, size_t smem, cudaStream_t st, const VbParams& K);
 };

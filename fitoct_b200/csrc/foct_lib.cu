@@ -493,14 +493,59 @@ struct foct_plan {
   int* d_counter = nullptr;
   int* d_order = nullptr;  // work-item order: longest expected fits first (see plan_order)
   const InstEntry* inst = nullptr;
-  int grid = 0, block = 0, blocks_per_sm = 0, regs = 0;
+  int grid = 0, block = 0, blocks_per_sm = 0, regs = 0, groups = 1, n_sm = 0;
   size_t smem = 0;
   bool ran = false;
+  // continuation inputs (cfg.inv_metric_init / stepsize_init) and the state a continuation starts from
+  double *d_invm_init = nullptr, *d_eps_init = nullptr, *d_lastq = nullptr;
+  // run until converged (cfg.rhat_target): extension blocks of the profiles that were continued
+  bool extend_pending = false, thinned = false;
+  int x_cap = 0, x_slots = 0;
+  double *d_xdraws = nullptr, *d_xsparams = nullptr;
+  int *d_slot_of = nullptr, *d_sel = nullptr, *d_sel_slots = nullptr;
+  std::vector<int> n_extend, slot_of;
+  cudaEvent_t evx0 = nullptr, evx1 = nullptr, evx2 = nullptr;
+  float ext_sample_ms = 0.f, ext_summary_ms = 0.f;
+  unsigned long long seed = 0;
 };
+
+// Copy the post-warm-up draws of the selected profiles into their extension blocks.
+__global__ void gather_blocks_kernel(const double* __restrict__ src, size_t src_stride, size_t src_off, double* __restrict__ dst,
+                                     size_t dst_stride, size_t len, const int* __restrict__ sel, const int* __restrict__ slots, int m) {
+  for (int k = blockIdx.y; k < m; k += gridDim.y) {
+    const double* a = src + (size_t)sel[k] * src_stride + src_off;
+    double* b = dst + (size_t)slots[k] * dst_stride;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
+  }
+}
+// Thin an extension block back into the profile's post-warm-up rows: row t <- row (t + 1) * step - 1.
+__global__ void thin_blocks_kernel(const double* __restrict__ xsrc, size_t x_stride, double* __restrict__ dst, size_t dst_stride,
+                                   size_t dst_off, int n_post, size_t row_len, const int* __restrict__ slot_of,
+                                   const int* __restrict__ n_extend, int n) {
+  for (int j = blockIdx.y; j < n; j += gridDim.y) {
+    const int e = n_extend[j];
+    if (e <= 0) continue;
+    const double* a = xsrc + (size_t)slot_of[j] * x_stride;
+    double* b = dst + (size_t)j * dst_stride + dst_off;
+    const size_t tot = (size_t)n_post * row_len;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+      const size_t t = i / row_len, c = i % row_len;
+      b[i] = a[((t + 1) * (size_t)(e + 1) - 1) * row_len + c];
+    }
+  }
+}
 
 static void plan_free(foct_plan* p) {
   if (!p) return;
   cudaSetDevice(p->device);
+  // foct_plan_run is asynchronous: the kernels may still be reading and writing these buffers, and pool_free hands
+  // them to the next pool_malloc of any thread without the implicit synchronisation cudaFree would have done
+  if (p->stream && p->ran) cudaStreamSynchronize(p->stream);
+  pool_free(p->d_invm_init); pool_free(p->d_eps_init); pool_free(p->d_lastq);
+  pool_free(p->d_xdraws); pool_free(p->d_xsparams); pool_free(p->d_slot_of); pool_free(p->d_sel); pool_free(p->d_sel_slots);
+  if (p->evx0) cudaEventDestroy(p->evx0);
+  if (p->evx1) cudaEventDestroy(p->evx1);
+  if (p->evx2) cudaEventDestroy(p->evx2);
   pool_free(p->d_blobs); pool_free(p->d_draws); pool_free(p->d_sparams); pool_free(p->d_summary);
   pool_free(p->d_stepsize); pool_free(p->d_invm); pool_free(p->d_nleap); pool_free(p->d_ndiv); pool_free(p->d_init);
   pool_free(p->d_probs); pool_free(p->d_counter); pool_free(p->d_order);
@@ -687,6 +732,10 @@ extern "C" int foct_logp_grad(int kind, const foct_problem* P, int n, const foct
     LogpParams K;
     K.blobs = d_blobs; K.blob_stride = stride; K.npad = npad; K.probs = d_probs; K.n_problems = n;
     K.spec = dev_spec(*spec); K.q = d_q; K.n_q = n_q; K.lp = d_lp; K.grad = d_g; K.chi2 = d_c2;
+    {  // the parity hook exercises the evaluation the sampler uses: half-warps for D <= 16 (FOCT_LOGP_WIDTH=32: full warps)
+      const char* wenv = std::getenv("FOCT_LOGP_WIDTH");
+      K.width = (wenv && std::atoi(wenv) == 32) ? 32 : 16;
+    }
     const InstEntry* inst = inst_for(NN);
     CUB(inst->launch_logp(spec->modulation, std::min(n, 148 * 4), 128, stride * sizeof(double), 0, K));
     CUB(cudaDeviceSynchronize());
@@ -740,16 +789,23 @@ static int validate_cfg(const foct_sampler_cfg* c) {
   if (c->n_warmup < 0 || c->n_iter < c->n_warmup || c->n_iter < 1) return fail(FOCT_EINVAL, "need 0 <= n_warmup <= n_iter, n_iter >= 1 (nb_iter = nb_warmup + nb_sample, FitOCT.R:121)");
   if (c->max_treedepth > FOCT_STACK_LEVELS + 1) return fail(FOCT_EINVAL, "max_treedepth=%d > %d", c->max_treedepth, FOCT_STACK_LEVELS + 1);
   if (c->init_mode < 0 || c->init_mode > 2 || (c->init_mode == 2 && !c->init)) return fail(FOCT_EINVAL, "bad init_mode / init");
+  if (c->iter_offset < 0) return fail(FOCT_EINVAL, "iter_offset=%d < 0", c->iter_offset);
+  if (c->rhat_target > 0.0 && (c->max_extend < 0 || c->max_extend > 64)) return fail(FOCT_EINVAL, "max_extend=%d outside 0..64", c->max_extend);
+  if (c->rhat_target > 0.0 && !(c->rhat_target > 1.0)) return fail(FOCT_EINVAL, "rhat_target=%g must exceed 1", c->rhat_target);
   return 0;
 }
 
 static int plan_create_on(int device, int kind, const foct_problem* P, int n, const foct_model_spec* spec,
-                          const foct_sampler_cfg* cfg, const double* init_slice, int want_draws, int want_summary,
-                          foct_plan** out) {
+                          const foct_sampler_cfg* cfg, const double* init_slice, const double* invm_slice,
+                          const double* eps_slice, int want_draws, int want_summary, foct_plan** out) {
+  if (!spec || !P || !out) return fail(FOCT_EINVAL, "NULL problem / spec / plan pointer");
   if (int rc = validate_cfg(cfg)) return rc;
+  if (cfg->rhat_target > 0.0 && cfg->max_extend > 0 && !want_summary)
+    return fail(FOCT_EINVAL, "rhat_target needs the summary output (the continuation is decided from the split R-hat)");
   foct_plan* p = new foct_plan();
   p->device = device; p->kind = kind; p->n = n; p->spec = *spec; p->cfg = *cfg;
   p->cfg.init = nullptr; p->cfg.devices = nullptr; p->cfg.n_devices = 0;
+  p->cfg.inv_metric_init = nullptr; p->cfg.stepsize_init = nullptr;
   p->want_draws = want_draws != 0; p->want_summary = want_summary != 0;
   p->n_post = cfg->n_iter - cfg->n_warmup;
   p->n_saved = cfg->save_warmup ? cfg->n_iter : p->n_post;
@@ -760,6 +816,9 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
   CUP(cudaEventCreate(&p->ev0));
   CUP(cudaEventCreate(&p->ev1));
   CUP(cudaEventCreate(&p->ev2));
+  CUP(cudaEventCreate(&p->evx0));
+  CUP(cudaEventCreate(&p->evx1));
+  CUP(cudaEventCreate(&p->evx2));
   tr.mark("stream + events");
   if (int rc = build_device_batch(kind, P, n, spec, device, p->stream, &p->NN, &p->npad, &p->blob_stride, &p->d_blobs, &p->d_probs)) {
     plan_free(p);
@@ -784,15 +843,25 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
     CUP(pool_malloc(&p->d_init, pc * p->D * sizeof(double)));
     CUP(cudaMemcpy(p->d_init, init_slice, pc * p->D * sizeof(double), cudaMemcpyHostToDevice));
   }
+  CUP(pool_malloc(&p->d_lastq, pc * p->D * sizeof(double)));
+  if (invm_slice) {
+    CUP(pool_malloc(&p->d_invm_init, pc * p->D * sizeof(double)));
+    CUP(cudaMemcpy(p->d_invm_init, invm_slice, pc * p->D * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  if (eps_slice) {
+    CUP(pool_malloc(&p->d_eps_init, pc * sizeof(double)));
+    CUP(cudaMemcpy(p->d_eps_init, eps_slice, pc * sizeof(double), cudaMemcpyHostToDevice));
+  }
   tr.mark("output buffers");
   p->inst = inst_for(p->NN);
-  p->block = 32 * std::min(cfg->chains, FOCT_CTA_CHAINS);
   p->smem = p->blob_stride * sizeof(double);
-  CUP(p->inst->nuts_occupancy(spec->modulation, p->block, p->smem, &p->blocks_per_sm, &p->regs));
+  int cta_chains = FOCT_CTA_CHAINS;
+  CUP(p->inst->nuts_occupancy(spec->modulation, cfg->chains, p->smem, &p->block, &p->blocks_per_sm, &cta_chains, &p->regs));
   if (p->blocks_per_sm < 1) { plan_free(p); return fail(FOCT_EINVAL, "sampling kernel does not fit an SM (smem %zu B)", p->smem); }
   int n_sm = 0;  // (cudaGetDeviceProperties costs milliseconds; one attribute does not)
   CUP(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
-  const int groups = (cfg->chains + FOCT_CTA_CHAINS - 1) / FOCT_CTA_CHAINS;
+  const int groups = (cfg->chains + cta_chains - 1) / cta_chains;
+  p->groups = groups; p->n_sm = n_sm;
   p->grid = (int)std::min<long long>((long long)n * groups, (long long)n_sm * p->blocks_per_sm);
   // Longest-processing-time-first scheduling.  Fits differ in cost by up to 4x (an unmodulated profile needs a third of
   // the leapfrogs of a strongly modulated one), and with more work items than resident CTAs the order in which the
@@ -836,13 +905,11 @@ extern "C" int foct_plan_create(int kind, const foct_problem* P, int n, const fo
   int dev = 0;
   CU(cudaGetDevice(&dev));
   if (cfg && cfg->n_devices == 1 && cfg->devices) dev = cfg->devices[0];
-  return plan_create_on(dev, kind, P, n, spec, cfg, cfg ? cfg->init : nullptr, want_draws, want_summary, plan);
+  return plan_create_on(dev, kind, P, n, spec, cfg, cfg ? cfg->init : nullptr, cfg ? cfg->inv_metric_init : nullptr,
+                        cfg ? cfg->stepsize_init : nullptr, want_draws, want_summary, plan);
 }
 
-extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
-  if (!p) return fail(FOCT_EINVAL, "NULL plan");
-  CU(cudaSetDevice(p->device));
-  SamplerParams K;
+static void plan_params(const foct_plan* p, unsigned long long seed, SamplerParams& K) {
   std::memset(&K, 0, sizeof(K));
   K.blobs = p->d_blobs; K.blob_stride = p->blob_stride; K.npad = p->npad; K.probs = p->d_probs; K.n_problems = p->n;
   K.spec = dev_spec(p->spec);
@@ -854,6 +921,15 @@ extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
   K.seed = seed; K.init = p->d_init;
   K.draws = p->d_draws; K.sparams = p->d_sparams; K.stepsize = p->d_stepsize; K.inv_metric = p->d_invm;
   K.n_leapfrog = p->d_nleap; K.n_divergent = p->d_ndiv; K.work_counter = p->d_counter; K.order = p->d_order;
+  K.invm_init = p->d_invm_init; K.eps_init = p->d_eps_init; K.last_q = p->d_lastq; K.it_offset = c.iter_offset;
+}
+
+extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
+  if (!p) return fail(FOCT_EINVAL, "NULL plan");
+  CU(cudaSetDevice(p->device));
+  SamplerParams K;
+  plan_params(p, seed, K);
+  const foct_sampler_cfg& c = p->cfg;
   CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), p->stream));
   CU(cudaEventRecord(p->ev0, p->stream));
   CU(p->inst->launch_nuts(p->spec.modulation, p->grid, p->block, p->smem, p->stream, K));
@@ -864,6 +940,101 @@ extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
   }
   CU(cudaEventRecord(p->ev2, p->stream));
   p->ran = true;
+  p->seed = seed;
+  p->thinned = false;
+  p->ext_sample_ms = p->ext_summary_ms = 0.f;
+  p->n_extend.assign(p->n, 0);
+  p->extend_pending = c.rhat_target > 0.0 && c.max_extend > 0 && p->want_summary && p->n_post >= 2;
+  return 0;
+}
+
+// Run until converged (cfg.rhat_target): continue the profiles whose largest split R-hat over the sampled parameters
+// is still >= the target — same adapted metric and step size, start = the last state, Philox sites after the ones
+// already used — for another n_post draws per round, and summarise all their post-warm-up draws again.  Host logic
+// between device rounds: called by the first sync / fetch / timing after foct_plan_run.
+static int plan_extend(foct_plan* p) {
+  if (!p->extend_pending) return 0;
+  p->extend_pending = false;
+  const foct_sampler_cfg& c = p->cfg;
+  const int n = p->n, C = c.chains, P_out = p->P_out, D = p->D, n_post = p->n_post;
+  CU(cudaStreamSynchronize(p->stream));
+  std::vector<double> rh((size_t)n * P_out * FOCT_N_SUMMARY_COLS);
+  std::vector<int> sel, slots;
+  auto select = [&](const std::vector<int>& among) {
+    std::vector<int> out;
+    for (int j : among) {
+      double mx = 0.0;
+      for (int d = 0; d < D; ++d) {
+        const double r = rh[((size_t)j * P_out + d) * FOCT_N_SUMMARY_COLS + 9];
+        if (r > mx) mx = r;  // NaN (a constant or non-finite column) never selects
+      }
+      if (mx >= c.rhat_target) out.push_back(j);
+    }
+    return out;
+  };
+  CU(cudaMemcpy(rh.data(), p->d_summary, rh.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  std::vector<int> all(n);
+  for (int j = 0; j < n; ++j) all[j] = j;
+  sel = select(all);
+  if (sel.empty()) return 0;
+  // extension blocks: one per profile selected in the first round
+  const int m0 = (int)sel.size();
+  p->x_cap = (c.max_extend + 1) * n_post;
+  p->x_slots = m0;
+  p->slot_of.assign(n, -1);
+  for (int k = 0; k < m0; ++k) p->slot_of[sel[k]] = k;
+  const size_t row = (size_t)C * P_out, blk = (size_t)p->x_cap * row;
+  pool_free(p->d_xdraws); pool_free(p->d_xsparams); pool_free(p->d_slot_of); pool_free(p->d_sel); pool_free(p->d_sel_slots);
+  p->d_xdraws = p->d_xsparams = nullptr; p->d_slot_of = p->d_sel = p->d_sel_slots = nullptr;
+  CU(pool_malloc(&p->d_xdraws, (size_t)m0 * blk * sizeof(double)));
+  if (p->d_sparams) CU(pool_malloc(&p->d_xsparams, (size_t)m0 * p->x_cap * C * 6 * sizeof(double)));
+  CU(pool_malloc(&p->d_slot_of, (size_t)n * sizeof(int)));
+  CU(pool_malloc(&p->d_sel, (size_t)m0 * sizeof(int)));
+  CU(pool_malloc(&p->d_sel_slots, (size_t)m0 * sizeof(int)));
+  CU(cudaMemcpyAsync(p->d_slot_of, p->slot_of.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+  const int off = c.save_warmup ? c.n_warmup : 0;
+  CU(cudaEventRecord(p->evx0, p->stream));
+  for (int e = 1; e <= c.max_extend && !sel.empty(); ++e) {
+    const int m = (int)sel.size();
+    slots.resize(m);
+    for (int k = 0; k < m; ++k) slots[k] = p->slot_of[sel[k]];
+    CU(cudaMemcpyAsync(p->d_sel, sel.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemcpyAsync(p->d_sel_slots, slots.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    if (e == 1) {
+      const dim3 grid(32, std::min(m, 65535));
+      gather_blocks_kernel<<<grid, 256, 0, p->stream>>>(p->d_draws, (size_t)p->n_saved * row, (size_t)off * row, p->d_xdraws, blk,
+                                                        (size_t)n_post * row, p->d_sel, p->d_sel_slots, m);
+      if (p->d_xsparams)
+        gather_blocks_kernel<<<grid, 256, 0, p->stream>>>(p->d_sparams, (size_t)p->n_saved * C * 6, (size_t)off * C * 6, p->d_xsparams,
+                                                          (size_t)p->x_cap * C * 6, (size_t)n_post * C * 6, p->d_sel, p->d_sel_slots, m);
+      CU(cudaGetLastError());
+    }
+    SamplerParams K;
+    plan_params(p, p->seed, K);
+    K.n_problems = m; K.order = p->d_sel;
+    K.n_warmup = 0; K.n_iter = n_post; K.save_warmup = 0;
+    K.init_mode = 2; K.init = p->d_lastq; K.invm_init = p->d_invm; K.eps_init = p->d_stepsize;
+    K.it_offset = c.iter_offset + c.n_iter + (e - 1) * n_post;
+    K.draws = p->d_xdraws; K.sparams = p->d_xsparams; K.slot_of = p->d_slot_of;
+    K.save_stride = p->x_cap; K.save_offset = e * n_post; K.accumulate = 1;
+    CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), p->stream));
+    cudaEvent_t a0, a1, a2;
+    CU(cudaEventCreate(&a0)); CU(cudaEventCreate(&a1)); CU(cudaEventCreate(&a2));
+    CU(cudaEventRecord(a0, p->stream));
+    const int grid = (int)std::min<long long>((long long)m * p->groups, (long long)p->n_sm * p->blocks_per_sm);
+    CU(p->inst->launch_nuts(p->spec.modulation, grid, p->block, p->smem, p->stream, K));
+    CU(cudaEventRecord(a1, p->stream));
+    CU(launch_summary(p->d_xdraws, m, p->x_cap, 0, (e + 1) * n_post, C, P_out, p->d_summary, p->stream, p->d_sel_slots, p->d_sel));
+    CU(cudaEventRecord(a2, p->stream));
+    CU(cudaMemcpyAsync(rh.data(), p->d_summary, rh.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    float t1 = 0.f, t2 = 0.f;
+    cudaEventElapsedTime(&t1, a0, a1); cudaEventElapsedTime(&t2, a1, a2);
+    cudaEventDestroy(a0); cudaEventDestroy(a1); cudaEventDestroy(a2);
+    p->ext_sample_ms += t1; p->ext_summary_ms += t2;
+    for (int j : sel) p->n_extend[j] = e;
+    sel = select(sel);
+  }
   return 0;
 }
 
@@ -871,9 +1042,10 @@ extern "C" int foct_plan_sync(foct_plan* p, float* kernel_ms) {
   if (!p) return fail(FOCT_EINVAL, "NULL plan");
   CU(cudaSetDevice(p->device));
   CU(cudaStreamSynchronize(p->stream));
+  if (int rc = plan_extend(p)) return rc;
   if (kernel_ms) {
     *kernel_ms = 0.f;
-    if (p->ran) CU(cudaEventElapsedTime(kernel_ms, p->ev0, p->ev1));
+    if (p->ran) { CU(cudaEventElapsedTime(kernel_ms, p->ev0, p->ev1)); *kernel_ms += p->ext_sample_ms; }
   }
   return 0;
 }
@@ -884,8 +1056,9 @@ extern "C" int foct_plan_timing(foct_plan* p, float* sample_ms, float* summary_m
   CU(cudaSetDevice(p->device));
   if (p->ran) {
     CU(cudaEventSynchronize(p->ev2));
-    if (sample_ms) CU(cudaEventElapsedTime(sample_ms, p->ev0, p->ev1));
-    if (summary_ms) CU(cudaEventElapsedTime(summary_ms, p->ev1, p->ev2));
+    if (int rc = plan_extend(p)) return rc;
+    if (sample_ms) { CU(cudaEventElapsedTime(sample_ms, p->ev0, p->ev1)); *sample_ms += p->ext_sample_ms; }
+    if (summary_ms) { CU(cudaEventElapsedTime(summary_ms, p->ev1, p->ev2)); *summary_ms += p->ext_summary_ms; }
   }
   if (grid) *grid = p->grid;
   if (block) *block = p->block;
@@ -900,7 +1073,27 @@ extern "C" int foct_plan_fetch(foct_plan* p, foct_result* R) {
   if (!p->ran) return fail(FOCT_EINVAL, "plan has not been run");
   CU(cudaSetDevice(p->device));
   CU(cudaStreamSynchronize(p->stream));
+  if (int rc = plan_extend(p)) return rc;
   const size_t pc = (size_t)p->n * p->cfg.chains;
+  if (p->x_slots > 0 && !p->thinned && p->want_draws && (R->draws || R->sampler_params)) {
+    // continued profiles: their post-warm-up rows become every (1 + n_extend)-th draw of the extension block
+    int* d_next = nullptr;
+    CU(pool_malloc(&d_next, (size_t)p->n * sizeof(int)));
+    CU(cudaMemcpyAsync(d_next, p->n_extend.data(), (size_t)p->n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    const int C = p->cfg.chains, off = p->cfg.save_warmup ? p->cfg.n_warmup : 0;
+    const size_t row = (size_t)C * p->P_out;
+    const dim3 grid(32, std::min(p->n, 65535));
+    thin_blocks_kernel<<<grid, 256, 0, p->stream>>>(p->d_xdraws, (size_t)p->x_cap * row, p->d_draws, (size_t)p->n_saved * row,
+                                                    (size_t)off * row, p->n_post, row, p->d_slot_of, d_next, p->n);
+    if (p->d_xsparams)
+      thin_blocks_kernel<<<grid, 256, 0, p->stream>>>(p->d_xsparams, (size_t)p->x_cap * C * 6, p->d_sparams, (size_t)p->n_saved * C * 6,
+                                                      (size_t)off * C * 6, p->n_post, (size_t)C * 6, p->d_slot_of, d_next, p->n);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    pool_free(d_next);
+    if (e != cudaSuccess) return fail(FOCT_ECUDA, "thinning of the continued draws failed: %s", cudaGetErrorString(e));
+    p->thinned = true;
+  }
   if (R->draws && p->n_saved > 0) {
     if (!p->want_draws) return fail(FOCT_EINVAL, "plan was created without draws");
     CU(cudaMemcpy(R->draws, p->d_draws, pc * p->n_saved * p->P_out * sizeof(double), cudaMemcpyDeviceToHost));
@@ -919,6 +1112,8 @@ extern "C" int foct_plan_fetch(foct_plan* p, foct_result* R) {
   if (R->inv_metric) CU(cudaMemcpy(R->inv_metric, p->d_invm, pc * p->D * sizeof(double), cudaMemcpyDeviceToHost));
   if (R->n_leapfrog) CU(cudaMemcpy(R->n_leapfrog, p->d_nleap, pc * 2 * sizeof(double), cudaMemcpyDeviceToHost));
   if (R->n_divergent) CU(cudaMemcpy(R->n_divergent, p->d_ndiv, pc * sizeof(double), cudaMemcpyDeviceToHost));
+  if (R->last_q) CU(cudaMemcpy(R->last_q, p->d_lastq, pc * p->D * sizeof(double), cudaMemcpyDeviceToHost));
+  if (R->n_extend) for (int j = 0; j < p->n; ++j) R->n_extend[j] = p->n_extend.empty() ? 0 : p->n_extend[j];
   return 0;
 }
 
@@ -931,8 +1126,11 @@ static int sample_chunk(int device, int kind, const foct_problem* P, int first, 
   const int n_saved = cfg->save_warmup ? cfg->n_iter : cfg->n_iter - cfg->n_warmup;
   foct_plan* p = nullptr;
   const double* init_slice = cfg->init_mode == 2 && cfg->init ? cfg->init + (size_t)first * C * D : nullptr;
+  const double* invm_slice = cfg->inv_metric_init ? cfg->inv_metric_init + (size_t)first * C * D : nullptr;
+  const double* eps_slice = cfg->stepsize_init ? cfg->stepsize_init + (size_t)first * C : nullptr;
   Trace tr("foct_sample");
-  int rc = plan_create_on(device, kind, P + first, n, spec, cfg, init_slice, R->draws || R->sampler_params, R->summary != nullptr, &p);
+  int rc = plan_create_on(device, kind, P + first, n, spec, cfg, init_slice, invm_slice, eps_slice,
+                          R->draws || R->sampler_params, R->summary != nullptr, &p);
   if (rc) return rc;
   tr.mark("plan (alloc, pack, upload, setup kernel)");
   rc = foct_plan_run(p, cfg->seed);
@@ -947,6 +1145,8 @@ static int sample_chunk(int device, int kind, const foct_problem* P, int first, 
     if (S.inv_metric) S.inv_metric += pc0 * D;
     if (S.n_leapfrog) S.n_leapfrog += pc0 * 2;
     if (S.n_divergent) S.n_divergent += pc0;
+    if (S.last_q) S.last_q += pc0 * D;
+    if (S.n_extend) S.n_extend += first;
     rc = foct_plan_fetch(p, &S);
     tr.mark("fetch");
   }
@@ -966,7 +1166,7 @@ static int sample_shard(int device, int kind, const foct_problem* P, int first, 
   double budget = 48.0 * 1024 * 1024 * 1024;
   if (const char* env = std::getenv("FOCT_DRAW_BUDGET_MB")) budget = std::atof(env) * 1024 * 1024;
   long long chunk = (long long)(budget / per_profile);
-  if (chunk >= 444 * 2) chunk -= chunk % 444;
+  if (chunk >= 2048) chunk -= chunk % 592;  // whole waves of resident CTAs where the chunk is many waves anyway (4 per SM x 148)
   chunk = std::max<long long>(1, std::min<long long>(chunk, n));
   for (int off = 0; off < n; off += (int)chunk) {
     const int m = (int)std::min<long long>(chunk, n - off);

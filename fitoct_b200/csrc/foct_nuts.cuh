@@ -34,7 +34,24 @@ struct SamplerParams {
   double* n_divergent;      // [n_problems][chains]
   int* work_counter;        // dynamic profile scheduler
   const int* order;         // [n_problems] profile served by work item w (longest expected first), or nullptr
+  // ---- continuation of an earlier run (foct_sampler_cfg.inv_metric_init / stepsize_init / iter_offset; the
+  //      run-until-converged rounds of foct_plan_run): adapted state in, last state out
+  const double* invm_init;  // [..][chains][D] or nullptr (unit metric)
+  const double* eps_init;   // [..][chains] or nullptr (stepsize0)
+  double* last_q;           // [..][chains][D] unconstrained state after the last transition, or nullptr
+  int it_offset;            // added to the iteration index of every Philox site
+  int accumulate;           // 1: n_leapfrog / n_divergent are added to what the buffers hold
+  int save_stride;          // saved iterations a profile's draw block holds (0: n_saved of this launch)
+  int save_offset;          // first row of this launch inside the block
+  const int* slot_of;       // [..] draw block of profile j (nullptr: j)
 };
+
+// Row of (profile, saved iteration, chain) in draws / sampler_params.
+__device__ __forceinline__ size_t save_row(const SamplerParams& K, int prob, int n_saved, int save_idx, int chain) {
+  const int stride = K.save_stride > 0 ? K.save_stride : n_saved;
+  const int slot = K.slot_of ? K.slot_of[prob] : prob;
+  return ((size_t)slot * stride + K.save_offset + save_idx) * K.chains + chain;
+}
 
 // log(exp(a) + exp(b)) and exp(b - lse) = w_b / (w_a + w_b) from ONE exponential (Stan computes
 // log_sum_exp and then exp(lsw_final - lsw_subtree); same quantities).
@@ -107,9 +124,11 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
   }
   Eval ev = warp_logp_grad<NN, MOD>(blob, P, K.spec, q, lane);
   double g = ev.g, V = -ev.lp, c2 = ev.chi2;
-  const double invM0 = 1.0;
-  double invM = invM0;
+  double invM = 1.0;
   double eps = K.stepsize0 > 0.0 ? K.stepsize0 : 1.0;
+  if (K.invm_init && act) invM = K.invm_init[((size_t)prob * K.chains + chain) * D + lane];
+  if (K.eps_init) eps = K.eps_init[(size_t)prob * K.chains + chain];
+  const uint32_t it0 = (uint32_t)K.it_offset;
 
   // ---- adaptation state (Stan windowed_adaptation / welford_var_estimator / stepsize_adaptation)
   int a_num_warmup, a_init_buffer, a_term_buffer, a_base_window;
@@ -163,7 +182,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
     }
   };
 
-  if (K.n_warmup > 0) init_stepsize(0);
+  if (K.n_warmup > 0) init_stepsize(it0);
 
   // pending "init" subtrees, one slot per level (local memory; touched only at merges)
   double st_rho[FOCT_STACK_LEVELS], st_pbeg[FOCT_STACK_LEVELS], st_pend[FOCT_STACK_LEVELS];
@@ -174,7 +193,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
     // ================================================================ one NUTS transition
     double p = 0.0;
     if (act) {
-      rng.block((uint32_t)it, SITE_MOM, 0, (uint32_t)lane, 0, rb);
+      rng.block(it0 + (uint32_t)it, SITE_MOM, 0, (uint32_t)lane, 0, rb);
       p = normal_from(rb) / sqrt(invM);
     }
     const double H0 = V + 0.5 * warp_sum(invM * p * p);
@@ -187,7 +206,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
     bool divergent = false;
 
     while (depth < max_depth) {
-      rng.block((uint32_t)it, SITE_DIR, (uint32_t)depth, 0, 0, rb);
+      rng.block(it0 + (uint32_t)it, SITE_DIR, (uint32_t)depth, 0, 0, rb);
       const bool fwd = u53(rb[0], rb[1]) > 0.5;
       const double u_top = u53(rb[2], rb[3]);
       // integrator starts from the end being extended; the old trajectory is the "init" half of the top merge
@@ -220,7 +239,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
           // one Philox block serves the merges of four consecutive levels at this leaf (32-bit uniforms)
           if ((k >> 2) != mb_group) {
             mb_group = k >> 2;
-            rng.block((uint32_t)it, SITE_MERGE, (uint32_t)depth, n, (uint32_t)mb_group, rb);
+            rng.block(it0 + (uint32_t)it, SITE_MERGE, (uint32_t)depth, n, (uint32_t)mb_group, rb);
           }
           const uint32_t w = (k & 3) == 0 ? rb[0] : ((k & 3) == 1 ? rb[1] : ((k & 3) == 2 ? rb[2] : rb[3]));
           const bool take_final = ((double)w + 0.5) * 0x1.0p-32 < prob_final;
@@ -267,7 +286,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
     if (warm) nlf_warm += n_leap; else { nlf_samp += n_leap; ndiv += divergent ? 1.0 : 0.0; }
     const int save_idx = K.save_warmup ? it : it - K.n_warmup;
     if (save_idx >= 0) {
-      const size_t row = ((size_t)prob * n_saved + save_idx) * K.chains + chain;
+      const size_t row = save_row(K, prob, n_saved, save_idx, chain);
       if (K.draws) {
         double v;
         if (DM::GP) {
@@ -321,7 +340,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
         if (act) invM = (w_n / (w_n + 5.0)) * var + 1e-3 * (5.0 / (w_n + 5.0));
         w_n = 0.0; w_mean = 0.0; w_m2 = 0.0;
         ++a_counter;
-        init_stepsize((uint32_t)(it + 1));
+        init_stepsize(it0 + (uint32_t)(it + 1));
         da_mu = log(10.0 * eps);
         da_counter = 0.0; da_sbar = 0.0; da_xbar = 0.0;
       } else {
@@ -333,10 +352,14 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
   const size_t pc = (size_t)prob * K.chains + chain;
   if (lane == 0) {
     if (K.stepsize) K.stepsize[pc] = eps;
-    if (K.n_leapfrog) { K.n_leapfrog[pc * 2] = nlf_warm; K.n_leapfrog[pc * 2 + 1] = nlf_samp; }
-    if (K.n_divergent) K.n_divergent[pc] = ndiv;
+    if (K.n_leapfrog) {
+      K.n_leapfrog[pc * 2] = (K.accumulate ? K.n_leapfrog[pc * 2] : 0.0) + nlf_warm;
+      K.n_leapfrog[pc * 2 + 1] = (K.accumulate ? K.n_leapfrog[pc * 2 + 1] : 0.0) + nlf_samp;
+    }
+    if (K.n_divergent) K.n_divergent[pc] = (K.accumulate ? K.n_divergent[pc] : 0.0) + ndiv;
   }
   if (K.inv_metric && act) K.inv_metric[pc * D + lane] = invM;
+  if (K.last_q && act) K.last_q[pc * D + lane] = q;
 }
 
 // Persistent CTAs of up to FOCT_CTA_CHAINS warps.  A work item is (profile, group of <= 4 chains); each CTA

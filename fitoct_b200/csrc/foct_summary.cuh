@@ -135,9 +135,13 @@ __device__ double ess_block(double* x, int len, int CC, double* scratch) {
 }
 
 // Dynamic shared memory layout: A[S] doubles | W[Spad] doubles | I[Spad] ints.
+// in_slot / out_row (either may be nullptr = identity): item group g reads the draw block in_slot[g] and writes summary
+// row out_row[g] — the run-until-converged rounds summarise a subset of profiles out of their extension blocks.
 __global__ void __launch_bounds__(SUM_THREADS) summary_kernel(const double* __restrict__ draws, int n_saved, int off,
                                                               int n, int C, int P_out, int Spad, int n_items,
-                                                              double* __restrict__ out, double* __restrict__ gwork) {
+                                                              double* __restrict__ out, double* __restrict__ gwork,
+                                                              const int* __restrict__ in_slot,
+                                                              const int* __restrict__ out_row) {
   extern __shared__ __align__(16) unsigned char sraw[];
   __shared__ double scratch[18];
   __shared__ int s_bad;
@@ -152,8 +156,9 @@ __global__ void __launch_bounds__(SUM_THREADS) summary_kernel(const double* __re
     A = (double*)sraw; W = A + S; I = (int*)(W + Spad);
   }
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-  const int prob = item / P_out, p = item % P_out;
-  double* o = out + ((size_t)prob * P_out + p) * FOCT_N_SUMMARY_COLS;
+  const int grp = item / P_out, p = item % P_out;
+  const int prob = in_slot ? in_slot[grp] : grp;
+  double* o = out + ((size_t)(out_row ? out_row[grp] : grp) * P_out + p) * FOCT_N_SUMMARY_COLS;
   __syncthreads();
   if (threadIdx.x == 0) s_bad = 0;
   __syncthreads();
@@ -279,7 +284,8 @@ __global__ void __launch_bounds__(SUM_THREADS) summary_kernel(const double* __re
 // Launch one CTA per (profile, column).  Workspace lives in shared memory when it fits, else in a
 // caller-independent global scratch buffer allocated here and released after the kernel.
 static cudaError_t launch_summary(const double* d_draws, int n_problems, int n_saved, int off, int n_post, int C,
-                                  int P_out, double* d_summary, cudaStream_t st) {
+                                  int P_out, double* d_summary, cudaStream_t st, const int* in_slot = nullptr,
+                                  const int* out_row = nullptr) {
   const int S = n_post * C;
   int Spad = 1;
   while (Spad < S) Spad <<= 1;
@@ -290,14 +296,14 @@ static cudaError_t launch_summary(const double* d_draws, int n_problems, int n_s
     e = cudaFuncSetAttribute(summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     const int grid = n_items < 148 * 64 ? n_items : 148 * 64;
-    summary_kernel<<<grid, SUM_THREADS, bytes, st>>>(d_draws, n_saved, off, n_post, C, P_out, Spad, n_items, d_summary, nullptr);
+    summary_kernel<<<grid, SUM_THREADS, bytes, st>>>(d_draws, n_saved, off, n_post, C, P_out, Spad, n_items, d_summary, nullptr, in_slot, out_row);
     return cudaGetLastError();
   }
   double* gwork = nullptr;
   const int grid = n_items < 148 * 4 ? n_items : 148 * 4;
   e = cudaMallocAsync((void**)&gwork, bytes * (size_t)grid, st);
   if (e != cudaSuccess) return e;
-  summary_kernel<<<grid, SUM_THREADS, 0, st>>>(d_draws, n_saved, off, n_post, C, P_out, Spad, n_items, d_summary, gwork);
+  summary_kernel<<<grid, SUM_THREADS, 0, st>>>(d_draws, n_saved, off, n_post, C, P_out, Spad, n_items, d_summary, gwork, in_slot, out_row);
   e = cudaGetLastError();
   cudaFreeAsync(gwork, st);
   return e;

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FOCT_ABI_VERSION 1
+#define FOCT_ABI_VERSION 2 /* 2: continuation / run-until-converged fields at the END of foct_sampler_cfg and foct_result */
 
 #define FOCT_MAX_D 32        /* unconstrained dimensions live one-per-lane in a warp */
 #define FOCT_MAX_NN 25       /* => D = Nn + 5 <= 30, P_out = Nn + 7 <= 32 (reference UI range is 5..20, ShinyInterface/ui.R:200-207) */
@@ -92,6 +92,20 @@ typedef struct foct_sampler_cfg {
   /* devices to shard profiles over (independent shards, no collective); n_devices == 0 => current device */
   int n_devices;
   const int* devices;
+  /* ---- ABI 2: continuation.  rstan cannot continue a stanfit; the reference reaches convergence by raising nb_warmup /
+   * nb_sample and refitting (FitOCT.R:43-44).  Here a run can start from an adapted sampler instead of adapting one:
+   * n_warmup = 0, init_mode = 2 with init = foct_result.last_q of the earlier run, inv_metric_init = its inv_metric,
+   * stepsize_init = its stepsize, iter_offset = the iterations it did (keeps the Philox sites of the two runs apart). */
+  const double* inv_metric_init; /* [n_problems][chains][D], NULL => unit metric */
+  const double* stepsize_init;   /* [n_problems][chains], NULL => stepsize0 */
+  int iter_offset;
+  /* Run until converged (BASELINE north_star: "sampled to R-hat < 1.01"): after the n_iter iterations, every profile
+   * whose largest split R-hat over the sampled parameters is >= rhat_target is continued on the device — same adapted
+   * metric and step size, no new warm-up — for another n_iter - n_warmup draws, at most max_extend times.  The summary
+   * then covers ALL post-warm-up draws of the profile; the returned post-warm-up draws / sampler_params keep their shape
+   * and hold every (1 + n_extend)-th draw.  rhat_target <= 0: off.  Needs the summary output. */
+  double rhat_target;
+  int max_extend;
 } foct_sampler_cfg;
 
 /* Caller-allocated outputs; any pointer may be NULL to skip that output.
@@ -104,6 +118,9 @@ typedef struct foct_result {
   double* inv_metric;     /* [n_problems][chains][D] adapted diagonal inverse metric */
   double* n_leapfrog;     /* [n_problems][chains][2] total leapfrog steps: {warm-up, sampling} */
   double* n_divergent;    /* [n_problems][chains] post-warm-up divergences */
+  /* ---- ABI 2 */
+  double* last_q;         /* [n_problems][chains][D] unconstrained state after the last transition (continuation) */
+  int* n_extend;          /* [n_problems] continuation rounds the profile received (rhat_target) */
 } foct_result;
 
 int foct_version(void);

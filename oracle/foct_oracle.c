@@ -680,6 +680,9 @@ typedef struct {
   double* sp; size_t sp_stride;
   int P_out;
   double* stepsize; double* inv_metric; double* n_leapfrog; double* n_divergent;
+  double* last_q;                      /* [D] unconstrained state after the last transition */
+  const double* invm_init;             /* [D] continuation: adapted metric, or NULL */
+  const double* eps_init;              /* continuation: adapted step size, or NULL */
 } chain_out;
 
 static void write_draw(const nuts_t* S, const pspoint* cur, double accept, double eps_used, double* row,
@@ -714,20 +717,23 @@ static void run_chain(nuts_t* S, const foct_problem* P, const foct_sampler_cfg* 
   const int D = S->D;
   pspoint cur;
   memset(&cur, 0, sizeof(cur));
-  for (int d = 0; d < D; ++d) S->invM[d] = 1.0;
+  for (int d = 0; d < D; ++d) S->invM[d] = O->invm_init ? O->invm_init[d] : 1.0;
   S->eps = cfg->stepsize0 > 0 ? cfg->stepsize0 : 1.0;
+  if (O->eps_init) S->eps = *O->eps_init;
   S->max_depth = cfg->max_treedepth > 0 ? cfg->max_treedepth : 10;
   S->max_dH = 1000.0;
   S->it = 0;
+  const uint32_t it0 = (uint32_t)cfg->iter_offset; /* continuation: Philox sites after those of the earlier run */
   initial_point(S, P, cfg, init, &cur);
   adapt_t A;
   adapt_init(&A, cfg, D);
   A.mu = log(10.0 * S->eps);
   da_restart(&A);
   double nlf[2] = {0, 0}, ndiv = 0;
+  S->it = it0;
   if (cfg->n_warmup > 0) init_stepsize(S, &cur);
   for (int it = 0; it < cfg->n_iter; ++it) {
-    S->it = (uint32_t)it;
+    S->it = it0 + (uint32_t)it;
     double eps_used = S->eps;
     double accept = nuts_transition(S, &cur);
     int warm = it < cfg->n_warmup;
@@ -740,7 +746,7 @@ static void run_chain(nuts_t* S, const foct_problem* P, const foct_sampler_cfg* 
     if (warm) {
       S->eps = da_learn(&A, accept);
       if (learn_variance(&A, S->invM, cur.q, D)) {
-        S->it = (uint32_t)(it + 1);
+        S->it = it0 + (uint32_t)(it + 1);
         init_stepsize(S, &cur);
         A.mu = log(10.0 * S->eps);
         da_restart(&A);
@@ -752,6 +758,7 @@ static void run_chain(nuts_t* S, const foct_problem* P, const foct_sampler_cfg* 
   if (O->inv_metric) memcpy(O->inv_metric, S->invM, sizeof(double) * D);
   if (O->n_leapfrog) { O->n_leapfrog[0] = nlf[0]; O->n_leapfrog[1] = nlf[1]; }
   if (O->n_divergent) *O->n_divergent = ndiv;
+  if (O->last_q) memcpy(O->last_q, cur.q, sizeof(double) * D);
 }
 
 int foct_oracle_sample(int kind, const foct_problem* P, int n_problems, const foct_model_spec* spec,
@@ -794,6 +801,9 @@ int foct_oracle_sample(int kind, const foct_problem* P, int n_problems, const fo
       if (R->inv_metric) O.inv_metric = R->inv_metric + ((size_t)j * C + c) * D;
       if (R->n_leapfrog) O.n_leapfrog = R->n_leapfrog + ((size_t)j * C + c) * 2;
       if (R->n_divergent) O.n_divergent = R->n_divergent + (size_t)j * C + c;
+      if (R->last_q) O.last_q = R->last_q + ((size_t)j * C + c) * D;
+      if (cfg->inv_metric_init) O.invm_init = cfg->inv_metric_init + ((size_t)j * C + c) * D;
+      if (cfg->stepsize_init) O.eps_init = cfg->stepsize_init + (size_t)j * C + c;
       const double* init = cfg->init_mode == 2 && cfg->init ? cfg->init + ((size_t)j * C + c) * D : NULL;
       run_chain(S, &P[j], cfg, init, &O);
       free(S);

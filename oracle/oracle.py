@@ -117,6 +117,7 @@ def alloc_result(kind, n_problems, Nn, cfg: abi.SamplerCfg, draws=True, summary=
         inv_metric=np.full((n_problems, Cn, D), np.nan),
         n_leapfrog=np.zeros((n_problems, Cn, 2)),
         n_divergent=np.zeros((n_problems, Cn)),
+        last_q=np.full((n_problems, Cn, D), np.nan),
     )
     R = abi.Result()
     for k, v in out.items():

@@ -77,7 +77,7 @@ def test_defaults_and_dims_without_device():
     for name, _ in abi.VbCfg._fields_:
         if name != "init":
             assert getattr(v, name) == getattr(w, name), name
-    assert L.foct_version() == 1
+    assert L.foct_version() == 2
     for kind in (abi.FOCT_EXPGP, abi.FOCT_MONOEXP):
         s = abi.ModelSpec()
         L.foct_model_spec_default(C.byref(s), kind)

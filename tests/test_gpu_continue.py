@@ -1,0 +1,143 @@
+"""GPU (-m gpu): continuation of a run (ABI 2: inv_metric_init / stepsize_init / iter_offset / last_q), the
+run-until-converged rounds (rhat_target), and a deterministic GPU-vs-oracle comparison across the warm-up windows.
+
+The reference has no continuation (rstan cannot extend a stanfit; FitOCT.R:43-44 raises nb_warmup / nb_sample and
+refits), so these are property tests plus oracle identities:
+  * a run split in two (k iterations, then a continuation of the rest) is BIT-IDENTICAL to the unsplit run — the Philox
+    sites are indexed by the global iteration number and the whole sampler state is (q, inv_metric, stepsize);
+  * the continuation builds the same trees as the oracle's continuation;
+  * the thinned draws of a continued profile are exactly the draws of an explicit continuation.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from fitoct_b200 import _abi as abi
+from fitoct_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def batch_of(n, Nn=10, first_id=0):
+    S = synth.make_profiles(n, modulated_only=True, first_id=first_id)
+    return S, abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=Nn, ids=S["ids"])
+
+
+@pytest.mark.parametrize("Nn", [10, 15])   # two chains per warp / one chain per warp
+def test_split_run_is_bit_identical_to_the_unsplit_run(L, Nn):
+    _, b = batch_of(3, Nn)
+    spec = abi.default_spec()
+    full = L.sample(0, b, 3, spec, abi.default_cfg(n_warmup=40, n_iter=90, seed=7))
+    first = L.sample(0, b, 3, spec, abi.default_cfg(n_warmup=40, n_iter=60, seed=7))
+    np.testing.assert_array_equal(first["draws"], full["draws"][:, :20])
+    keep = []
+    cfg2 = L.continuation_cfg(abi.default_cfg(n_warmup=40, n_iter=60, seed=7), first, n_more=30, iters_done=60, keep=keep)
+    rest = L.sample(0, b, 3, spec, cfg2)
+    np.testing.assert_array_equal(rest["draws"], full["draws"][:, 20:])
+    np.testing.assert_array_equal(rest["sampler_params"], full["sampler_params"][:, 20:])
+    np.testing.assert_array_equal(rest["last_q"], full["last_q"])
+    np.testing.assert_array_equal(rest["inv_metric"], full["inv_metric"])   # no adaptation in a continuation
+    np.testing.assert_array_equal(rest["stepsize"], full["stepsize"])
+    # last_q is the unconstrained image of the last draw
+    D = Nn + 5
+    last = full["draws"][:, -1, :, :D].copy()
+    last[..., Nn + 3:] = np.log(last[..., Nn + 3:])
+    np.testing.assert_allclose(full["last_q"], last, rtol=1e-14)
+
+
+def test_continuation_builds_the_same_trees_as_the_oracle(L, O):
+    _, b = batch_of(2, 10, first_id=11)
+    spec = abi.default_spec()
+    cfg = abi.default_cfg(n_warmup=30, n_iter=40, seed=99)
+    first = O.sample(0, b, 2, spec, cfg)     # both continuations start from the ORACLE's adapted state
+    keep = []
+    cfg2 = L.continuation_cfg(cfg, first, n_more=8, iters_done=40, keep=keep)
+    out = L.sample(0, b, 2, spec, cfg2)
+    ref = O.sample(0, b, 2, spec, cfg2)
+    K = 5
+    np.testing.assert_array_equal(out["sampler_params"][:, :K, :, 2:5], ref["sampler_params"][:, :K, :, 2:5])
+    np.testing.assert_allclose(out["draws"][:, :K], ref["draws"][:, :K], rtol=1e-7, atol=1e-9)
+    np.testing.assert_array_equal(out["stepsize"], first["stepsize"])
+
+
+@pytest.mark.parametrize("Nn,n_warmup", [(10, 150), (10, 40), (15, 40)])
+def test_adaptation_windows_match_the_oracle(L, O, Nn, n_warmup):
+    """Deterministic comparison ACROSS the metric windows (tree identity stopped at transition 6).
+    Shallow trees (max_treedepth 3) keep the floating-point chaos of the trajectories small enough for the GPU and
+    the CPU restatement to stay on the same path through init_buffer, every metric window (regularised Welford
+    variance, step-size re-initialisation, dual-averaging restart) and the final exp(x_bar)."""
+    _, b = batch_of(2, Nn, first_id=5)
+    spec = abi.default_spec()
+    n_iter = n_warmup + 10
+    cfg = abi.default_cfg(n_warmup=n_warmup, n_iter=n_iter, seed=31, save_warmup=1, max_treedepth=3)
+    out = L.sample(0, b, 2, spec, cfg)
+    ref = O.sample(0, b, 2, spec, cfg)
+    sp, spr = out["sampler_params"], ref["sampler_params"]
+    same = np.all(sp[..., 2:5] == spr[..., 2:5], axis=(0, 2, 3))
+    first_diff = int(np.argmin(same)) if not same.all() else n_iter
+    # window schedule for this n_warmup (Stan: 75/25/50, or 15 % / 75 % / 10 % below 150 iterations)
+    if n_warmup >= 150:
+        closes = [99]          # 75 + 25 - 1; the next window would end inside term_buffer, so it is stretched to 99
+    else:
+        closes = [int(0.15 * n_warmup) + (n_warmup - int(0.15 * n_warmup) - int(0.1 * n_warmup)) - 1]
+    assert first_diff > closes[-1] + 5, f"trees diverge at transition {first_diff}, before the window close {closes}"
+    upto = min(first_diff, n_iter)
+    # step size used at every transition (column 1): identical path through dual averaging and both restarts
+    np.testing.assert_allclose(sp[:, :upto, :, 1], spr[:, :upto, :, 1], rtol=1e-6)
+    # the step size jumps at the window close (re-initialised from the new metric), on both sides at the same place
+    c = closes[-1]
+    assert np.all(sp[:, c + 1, :, 1] != sp[:, c, :, 1])
+    np.testing.assert_allclose(out["draws"][:, :upto], ref["draws"][:, :upto], rtol=1e-6, atol=1e-8)
+    if first_diff == n_iter:
+        np.testing.assert_allclose(out["inv_metric"], ref["inv_metric"], rtol=1e-6)
+        np.testing.assert_allclose(out["stepsize"], ref["stepsize"], rtol=1e-6)
+    assert np.all(out["inv_metric"] != 1.0)   # the metric was adapted
+
+
+def test_run_until_converged(L, O):
+    n = 12
+    _, b = batch_of(n, 10, first_id=40)
+    spec = abi.default_spec()
+    base = dict(n_warmup=150, n_iter=250, seed=5)
+    plain = L.sample(0, b, n, spec, abi.default_cfg(**base))
+    rh0 = np.nanmax(plain["summary"][:, :15, 9], axis=1)
+    target = float(np.sort(rh0)[n // 2])           # half of the profiles are above the target after the plain run
+    cfg = abi.default_cfg(**base)
+    cfg.rhat_target, cfg.max_extend = target, 3
+    out = L.sample(0, b, n, spec, cfg)
+    ne = out["n_extend"]
+    rh = np.nanmax(out["summary"][:, :15, 9], axis=1)
+    # exactly the profiles above the target were continued; every profile ends below it or at the round limit
+    np.testing.assert_array_equal(ne > 0, rh0 >= target)
+    assert np.all((rh < target) | (ne == 3))
+    assert np.all(rh[ne > 0] <= rh0[ne > 0] + 0.02)
+    # untouched profiles are bit-identical to the plain run
+    same = ne == 0
+    np.testing.assert_array_equal(out["draws"][same], plain["draws"][same])
+    np.testing.assert_array_equal(out["summary"][same], plain["summary"][same])
+    # a continued profile: its returned draws are every (1 + e)-th draw of (plain run ++ explicit continuation), and its
+    # summary is the summary of all of them
+    j = int(np.argmax(ne))
+    e = int(ne[j])
+    keep = []
+    cfg2 = L.continuation_cfg(abi.default_cfg(**base), plain, n_more=100 * e, iters_done=250, keep=keep)
+    cont = L.sample(0, b, n, spec, cfg2)
+    allj = np.concatenate([plain["draws"][j], cont["draws"][j]], axis=0)
+    np.testing.assert_array_equal(out["draws"][j], allj[e::e + 1])
+    np.testing.assert_allclose(out["summary"][j], O.summary(allj), rtol=1e-9, atol=1e-12)
+    np.testing.assert_array_equal(out["last_q"][j], cont["last_q"][j])
+    # leapfrog counts accumulate over the rounds
+    assert np.all(out["n_leapfrog"][ne > 0, :, 1] > plain["n_leapfrog"][ne > 0, :, 1])
+    np.testing.assert_array_equal(out["n_leapfrog"][j], plain["n_leapfrog"][j] + cont["n_leapfrog"][j])
+
+
+def test_rhat_target_needs_the_summary(L):
+    _, b = batch_of(1)
+    cfg = abi.default_cfg(n_warmup=20, n_iter=40)
+    cfg.rhat_target, cfg.max_extend = 1.01, 2
+    with pytest.raises(L.FitOCTError, match="summary"):
+        L.sample(0, b, 1, abi.default_spec(), cfg, draws=True, summary=False)
+    cfg.rhat_target = 0.9
+    with pytest.raises(L.FitOCTError, match="rhat_target"):
+        L.sample(0, b, 1, abi.default_spec(), cfg)
