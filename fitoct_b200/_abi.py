@@ -137,6 +137,7 @@ class PipelineOut(C.Structure):
         ("n_expgp", C.c_int),
         ("expgp_index", c_int_p),
         ("expgp", Result),
+        ("status", c_int_p),
     ]
 
 

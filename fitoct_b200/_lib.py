@@ -13,7 +13,8 @@ import numpy as np
 from . import _abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfitoct_b200.so")
+# FOCT_LIB_PATH: load another build of the same library (kernel A/B runs: scripts/build_variant.sh)
+LIB_PATH = os.environ.get("FOCT_LIB_PATH") or os.path.join(_HERE, "libfitoct_b200.so")
 
 # every symbol include/fitoct_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = (
@@ -23,7 +24,10 @@ EXPORTS = (
     "foct_plan_sync", "foct_plan_timing", "foct_plan_fetch", "foct_plan_destroy", "foct_fp64_peak",
     "foct_estimate_noise", "foct_birge_ci", "foct_print_br", "foct_estimate_exp_prior", "foct_pipeline_cfg_default",
     "foct_pipeline", "foct_vb_cfg_default", "foct_vb", "foct_release_cache",
+    "foct_sample_cb", "foct_plan_query", "foct_plan_cancel", "foct_expgp_logp_grad",
 )
+
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_double, C.c_char_p, C.c_void_p)
 
 _LIB = None
 
@@ -56,6 +60,10 @@ def lib():
         L.foct_logp_grad.argtypes = [C.c_int, PP, C.c_int, MS, dp, C.c_int, dp, dp, dp]
         for name in ("foct_sample",):
             getattr(L, name).argtypes = [C.c_int, PP, C.c_int, MS, SC, RS]
+        L.foct_sample_cb.argtypes = [C.c_int, PP, C.c_int, MS, SC, RS, PROGRESS_FN, C.c_void_p, C.c_int]
+        L.foct_expgp_logp_grad.argtypes = [PP, C.c_int, MS, dp, C.c_int, dp, dp, dp]
+        L.foct_plan_query.argtypes = [C.c_void_p, ip, dp]
+        L.foct_plan_cancel.argtypes = [C.c_void_p]
         for name in ("foct_expgp_sample", "foct_monoexp_sample"):
             getattr(L, name).argtypes = [PP, C.c_int, MS, SC, RS]
         L.foct_monoexp_map.argtypes = [PP, C.c_int, MS, dp, dp, dp, dp, ip]
@@ -160,8 +168,9 @@ def continuation_cfg(cfg: abi.SamplerCfg, prev: dict, n_more: int, iters_done: i
 
 
 def sample(kind: int, batch: abi.ProblemBatch, n_problems: int, spec: abi.ModelSpec, cfg: abi.SamplerCfg, draws=True,
-           summary=True, devices=None):
-    """One-shot batched NUTS through the C ABI with host buffers (the `e2e` path)."""
+           summary=True, devices=None, progress=None, poll_ms=100):
+    """One-shot batched NUTS through the C ABI with host buffers (the `e2e` path).  progress(fraction, phase) -> truthy to
+    cancel: called on this thread while the kernels run (foct_sample_cb); a cancelled run raises FitOCTError(-5)."""
     Nn = batch.array[0].Nn if kind == abi.FOCT_EXPGP else 0
     out, R = alloc_result(kind, n_problems, Nn, cfg, draws, summary)
     keep = None
@@ -170,7 +179,11 @@ def sample(kind: int, batch: abi.ProblemBatch, n_problems: int, spec: abi.ModelS
         cfg.n_devices = len(devices)
         cfg.devices = C.cast(keep, C.POINTER(C.c_int))
     try:
-        check(lib().foct_sample(kind, batch.array, n_problems, C.byref(spec), C.byref(cfg), C.byref(R)))
+        if progress is None:
+            check(lib().foct_sample(kind, batch.array, n_problems, C.byref(spec), C.byref(cfg), C.byref(R)))
+        else:
+            cb = PROGRESS_FN(lambda f, phase, _u: 1 if progress(float(f), phase.decode()) else 0)
+            check(lib().foct_sample_cb(kind, batch.array, n_problems, C.byref(spec), C.byref(cfg), C.byref(R), cb, None, int(poll_ms)))
     finally:
         if devices is not None:
             cfg.n_devices = 0
@@ -203,6 +216,15 @@ class Plan:
         check(lib().foct_plan_timing(self._h, C.byref(a), C.byref(b), *[C.byref(v) for v in g]))
         return dict(sample_ms=float(a.value), summary_ms=float(b.value), grid=g[0].value, block=g[1].value,
                     blocks_per_sm=g[2].value, regs=g[3].value, smem_bytes=g[4].value)
+
+    def query(self):
+        """Non-blocking: (done, fraction of chain-iterations completed)."""
+        d, f = C.c_int(), np.zeros(1)
+        check(lib().foct_plan_query(self._h, C.byref(d), abi.as_ptr(f)))
+        return bool(d.value), float(f[0])
+
+    def cancel(self):
+        check(lib().foct_plan_cancel(self._h))
 
     def fetch(self):
         out, R = alloc_result(self.kind, self.n, self.Nn, self.cfg, self.want_draws, self.want_summary)
@@ -329,7 +351,7 @@ def pipeline(batch: abi.ProblemBatch, n_problems: int, pcfg: abi.PipelineCfg, cf
     o = dict(uy=np.empty(tot), ySmooth=np.empty(tot), noise_theta=np.empty((n, 2)), mono_theta=np.empty((n, 3)),
              mono_hessian=np.empty((n, 3, 3)), mono_br=np.empty(n), mono_status=np.empty(n, dtype=np.int32),
              br_ci=np.empty((n, 2)), alert=np.empty(n, dtype=np.int32), theta0=np.empty((n, 3)), Sigma0=np.empty((n, 3, 3)),
-             ru=np.empty(n), expgp_index=np.full(n, -1, dtype=np.int32))
+             ru=np.empty(n), expgp_index=np.full(n, -1, dtype=np.int32), status=np.full(n, -1, dtype=np.int32))
     res, R = alloc_result(abi.FOCT_EXPGP, n, pcfg.Nn, cfg, draws, summary)
     out = abi.PipelineOut()
     for k, v in o.items():

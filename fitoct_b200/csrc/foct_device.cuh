@@ -160,6 +160,44 @@ __device__ __forceinline__ double fexp(double x) {
   return fexp_scale(fexp_poly(r) * tj, n, __double2hiint(x));
 }
 
+// log(1 + e) for 0 <= e <= 1 (the log-sum-exp of the multinomial tree weights), absolute error ~2e-16: u = 1 + e in [1, 2]
+// is split as u = (1 + f) / ic_j with ic_j = 1 / (1 + (j + 1/2) / 32) from a 32-entry table (|f| <= 1/64), so that
+// log u = -log(ic_j) + log1p(f) with an 8-term series.  ~20 instructions; the libdevice log1p it replaces was 75
+// executed instructions per leaf and 4 percent of the sampling kernel's stall samples (profiles/r2_ncu_pair_v1_regions.txt).
+static __device__ const double2 FLOG_TAB[32] = {
+    {0x1.f81f81f81f820p-1, 0x1.fc0a8b0fc03c4p-7}, {0x1.e9131abf0b767p-1, 0x1.77458f632dcffp-5},
+    {0x1.dae6076b981dbp-1, 0x1.341d7961bd1d0p-4}, {0x1.cd85689039b0bp-1, 0x1.a926d3a4ad562p-4},
+    {0x1.c0e070381c0e0p-1, 0x1.0d77e7cd08e5bp-3}, {0x1.b4e81b4e81b4fp-1, 0x1.44d2b6ccb7d1cp-3},
+    {0x1.a98ef606a63bep-1, 0x1.7ab890210d907p-3}, {0x1.9ec8e951033d9p-1, 0x1.af3c94e80bff3p-3},
+    {0x1.948b0fcd6e9e0p-1, 0x1.e27076e2af2e8p-3}, {0x1.8acb90f6bf3aap-1, 0x1.0a324e27390e2p-2},
+    {0x1.8181818181818p-1, 0x1.22941fbcf7966p-2}, {0x1.78a4c8178a4c8p-1, 0x1.3a64c556945eap-2},
+    {0x1.702e05c0b8170p-1, 0x1.51aad872df82ep-2}, {0x1.6816816816817p-1, 0x1.686c81e9b14adp-2},
+    {0x1.6058160581606p-1, 0x1.7eaf83b82afc2p-2}, {0x1.58ed2308158edp-1, 0x1.947941c2116fbp-2},
+    {0x1.51d07eae2f815p-1, 0x1.a9cec9a9a084ap-2}, {0x1.4afd6a052bf5bp-1, 0x1.beb4d9da71b7ap-2},
+    {0x1.446f86562d9fbp-1, 0x1.d32fe7e00ebd5p-2}, {0x1.3e22cbce4a902p-1, 0x1.e744261d68789p-2},
+    {0x1.3813813813814p-1, 0x1.faf588f78f31dp-2}, {0x1.323e34a2b10bfp-1, 0x1.0723e5c1cdf41p-1},
+    {0x1.2c9fb4d812ca0p-1, 0x1.109f39e2d4c96p-1}, {0x1.27350b8812735p-1, 0x1.19ee6b467c96fp-1},
+    {0x1.21fb78121fb78p-1, 0x1.23130d7bebf43p-1}, {0x1.1cf06ada2811dp-1, 0x1.2c0e9ed448e8cp-1},
+    {0x1.1811811811812p-1, 0x1.34e289d9ce1d2p-1}, {0x1.135c81135c811p-1, 0x1.3d9026a7156fbp-1},
+    {0x1.0ecf56be69c90p-1, 0x1.4618bc21c5ec2p-1}, {0x1.0a6810a6810a7p-1, 0x1.4e7d811b75bb0p-1},
+    {0x1.0624dd2f1a9fcp-1, 0x1.56bf9d5b3f399p-1}, {0x1.0204081020408p-1, 0x1.5ee02a9241676p-1}};
+__constant__ double FLOG_K[2] = {0x1.5555555555555p-2 /* 1/3 */, 0x1.999999999999ap-3 /* 1/5 */};
+__device__ __forceinline__ double flog1p_unit(double e) {
+  const double u = 1.0 + e;
+  int j = (__double2hiint(u) - 0x3ff00000) >> 15;
+  j = max(0, min(j, 31));  // u == 2 lands on the last entry; a NaN on any entry
+  const double2 t = __ldg(&FLOG_TAB[j]);
+  const double f = fma(u, t.x, -1.0);
+  double p = fma(f, -0.125, 0x1.24924p-3 /* 1/7 */);   // the truncated 1/7 and 1/6 multiply f^7 and f^6 <= 1.5e-11
+  p = fma(p, f, -0x1.55555p-3 /* 1/6 */);
+  p = fma(p, f, FLOG_K[1]);
+  p = fma(p, f, -0.25);
+  p = fma(p, f, FLOG_K[0]);
+  p = fma(p, f, -0.5);
+  p = fma(p, f, 1.0);
+  return fma(p, f, t.y);
+}
+
 // Branch-free reciprocal: MUFU.RCP64H seed (~20 bits), one cubic and one quadratic Newton step (the fast
 // path of the CUDA division, without its exponent-range slow path: a == 0 or denormal yields NaN, i.e. a
 // non-finite state, instead of +-inf).
@@ -243,13 +281,17 @@ struct Dims {
 // Raw sums go to acc[] (theta2 / theta3 factors are applied once, after the reduction).
 // W = 32: point u of the iteration sits one pass block further (pp + u * block); W = 16 (half-warp lane groups, pp
 // carries the lane index inside the group): the points are the two 16-point halves of consecutive 32-point blocks.
-template <int NN, int MOD, int KP, int ZI, int U, int W = 32>
+// GB: the basis rows are not in the staged block (which then holds cx | y | w only) but read through L1 from `pg`, a
+// blob in global memory that every profile of the batch shares (same depth grid => same basis).
+template <int NN, int MOD, int KP, int ZI, int U, int W = 32, bool GB = false>
 __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, double th1, double th2, double th3, double r3,
-                                             const double (&yg)[NN > 0 ? NN : 1], double (&acc)[KP]) {
+                                             const double (&yg)[NN > 0 ? NN : 1], double (&acc)[KP],
+                                             const double* __restrict__ pg = nullptr) {
   static_assert(W == 32 || (W == 16 && U % 2 == 0), "half-warp groups take the two halves of a block together");
-  constexpr int STRIDE = W == 32 ? (3 + NN) * 32 : 16;
+  constexpr int SROWS = GB ? 3 : 3 + NN;   // rows of a staged block
   const double* __restrict__ pp = pp0;
-#define FOCT_PT(u) (W == 32 ? (u) * STRIDE : ((u) >> 1) * (3 + NN) * 32 + ((u) & 1) * 16)
+#define FOCT_PT(u) (W == 32 ? (u) * SROWS * 32 : ((u) >> 1) * SROWS * 32 + ((u) & 1) * 16)
+#define FOCT_PTG(u) (W == 32 ? (u) * (3 + NN) * 32 : ((u) >> 1) * (3 + NN) * 32 + ((u) & 1) * 16)
   double b[U][NN > 0 ? NN : 1];
   double dl0[U], dl1[U], s[U], cx[U], y[U], ws[U], r[U], t[U];
 #pragma unroll
@@ -258,7 +300,7 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
   for (int k = 0; k < NN; ++k) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      b[u][k] = pp[FOCT_PT(u) + (3 + k) * 32];
+      b[u][k] = GB ? __ldg(pg + FOCT_PTG(u) + (3 + k) * 32) : pp[FOCT_PT(u) + (3 + k) * 32];
       if (k & 1) dl1[u] = fma(b[u][k], yg[k], dl1[u]); else dl0[u] = fma(b[u][k], yg[k], dl0[u]);
     }
   }
@@ -376,6 +418,7 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
 }
 
 #undef FOCT_PT
+#undef FOCT_PTG
 
 // Fused sweep over the staged profile.  qd = this lane's component of q.  Everything a lane needs from
 // the other lanes is fetched with shuffles up front; the per-point loop touches only shared memory and
@@ -383,9 +426,9 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
 // in flight per warp (the fp64 pipe was latency-, not throughput-bound with one: profiles/r1_*v1*).
 // W = 32: one chain per warp.  W = 16: one chain per half-warp — `lane` is then the index inside the half, both halves
 // must call together (full-mask shuffles of width 16) and walk the same profile, so every LDS is a 16-word broadcast.
-template <int NN, int MOD, int W = 32>
+template <int NN, int MOD, int W = 32, bool GB = false>
 __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, const DevProblem& P, const DevSpec& S,
-                                               double qd, int lane) {
+                                               double qd, int lane, const double* __restrict__ gbasis = nullptr) {
   static_assert(W == 32 || Dims<NN>::D <= 16, "a half-warp holds at most 16 components");
   FOCT_T(t_g0);
   using DM = Dims<NN>;
@@ -467,23 +510,41 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
   double zz = 0.0;
   if (!P.prior_PD) {
     const double r3 = frcp(th3);  // (a full division drags its exponent-range slow path into every leaf)
-    constexpr int ROWS = 3 + NN;
+    constexpr int ROWS = GB ? 3 : 3 + NN;     // rows of a staged block
+    constexpr int GROWS = 3 + NN;             // rows of a block of the shared (global) blob
     const double* pp = blob + lane;
+    const double* pg = GB ? gbasis + lane : nullptr;
     FOCT_T(t_l0);
     FOCT_TADD(3, t_g0, t_l0);
     int pass = 0;
-    if (W == 16) {
-      // one 32-point block per iteration: its two 16-point halves are the two points in flight per lane
+    if constexpr (W == 16) {
+      // 32-point blocks: the two 16-point halves of a block are two points in flight per lane; FOCT_UNROLL16 = 4 takes
+      // two blocks per iteration (two warps per scheduler is all the staged profiles leave room for: the instruction-
+      // level parallelism has to come from the loop body)
+#ifndef FOCT_UNROLL16
+#define FOCT_UNROLL16 4
+#endif
+#ifndef FOCT_UNROLL16_GB
+#define FOCT_UNROLL16_GB 2
+#endif
+      constexpr int U16 = NN <= 11 ? (GB ? FOCT_UNROLL16_GB : FOCT_UNROLL16) : 2;
+      if (U16 > 2) {
 #pragma unroll 1
-      for (; pass < P.npass; ++pass, pp += ROWS * 32) sweep_points<NN, MOD, KP, ZI, 2, W>(pp, th1, th2, th3, r3, yg, acc);
+        for (; pass + U16 / 2 <= P.npass; pass += U16 / 2, pp += (U16 / 2) * ROWS * 32, pg += (U16 / 2) * GROWS * 32)
+          sweep_points<NN, MOD, KP, ZI, U16, W, GB>(pp, th1, th2, th3, r3, yg, acc, pg);
+      }
+#pragma unroll 1
+      for (; pass < P.npass; ++pass, pp += ROWS * 32, pg += GROWS * 32)
+        sweep_points<NN, MOD, KP, ZI, 2, W, GB>(pp, th1, th2, th3, r3, yg, acc, pg);
     } else {
       if (UNROLL >= 2) {
 #pragma unroll 1
-        for (; pass + UNROLL <= P.npass; pass += UNROLL, pp += UNROLL * ROWS * 32)
-          sweep_points<NN, MOD, KP, ZI, UNROLL>(pp, th1, th2, th3, r3, yg, acc);
+        for (; pass + UNROLL <= P.npass; pass += UNROLL, pp += UNROLL * ROWS * 32, pg += UNROLL * GROWS * 32)
+          sweep_points<NN, MOD, KP, ZI, UNROLL, W, GB>(pp, th1, th2, th3, r3, yg, acc, pg);
       }
 #pragma unroll 1
-      for (; pass < P.npass; ++pass, pp += ROWS * 32) sweep_points<NN, MOD, KP, ZI, 1>(pp, th1, th2, th3, r3, yg, acc);
+      for (; pass < P.npass; ++pass, pp += ROWS * 32, pg += GROWS * 32)
+        sweep_points<NN, MOD, KP, ZI, 1, W, GB>(pp, th1, th2, th3, r3, yg, acc, pg);
     }
     FOCT_T(t_l1);
     FOCT_TADD(1, t_l0, t_l1);
@@ -537,6 +598,34 @@ __device__ __forceinline__ void stage_blob_tma(double* smem_dst, const double* g
           : "memory");
       off += n;
     }
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mbar_s), "r"(phase)
+        : "memory");
+  }
+  phase ^= 1u;
+}
+
+// Stage only the first `rows` rows (cx | y | w) of every 32-point block of a blob: one bulk copy per block, all
+// completing on the same mbarrier.  Used when the basis rows are shared by the whole batch and read through L1.
+__device__ __forceinline__ void stage_rows_tma(double* smem_dst, const double* gsrc, int nblocks, int src_rows, int rows,
+                                               uint64_t* mbar, uint32_t& phase) {
+  const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
+  if (threadIdx.x == 0) {
+    const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const uint32_t blk = (uint32_t)rows * 32u * (uint32_t)sizeof(double);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(blk * (uint32_t)nblocks) : "memory");
+    for (int j = 0; j < nblocks; ++j)
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s + (uint32_t)j * blk),
+          "l"((const char*)(gsrc + (size_t)j * src_rows * 32)), "r"(blk), "r"(mbar_s)
+          : "memory");
   }
   uint32_t done = 0;
   while (!done) {

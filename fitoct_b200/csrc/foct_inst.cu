@@ -393,9 +393,15 @@ static cudaError_t launch_nuts_mod(int grid, int block, size_t smem, cudaStream_
   cudaError_t e;
   if constexpr (Dims<NN>::D <= 16) {
     if (use_pair<NN>()) {
-      e = cudaFuncSetAttribute(nuts2_kernel<NN, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      nuts2_kernel<NN, MOD><<<grid, block, smem, st>>>(K);
+      if (K.shared_basis) {
+        e = cudaFuncSetAttribute(nuts2_kernel<NN, MOD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        nuts2_kernel<NN, MOD, true><<<grid, block, smem, st>>>(K);
+      } else {
+        e = cudaFuncSetAttribute(nuts2_kernel<NN, MOD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        nuts2_kernel<NN, MOD, false><<<grid, block, smem, st>>>(K);
+      }
       return cudaGetLastError();
     }
   }
@@ -439,19 +445,31 @@ static cudaError_t occupancy_of(KernelT kernel, int block, size_t smem, int* blo
 
 // Launch geometry of the sampling kernel for `chains` chains per profile: threads per CTA, resident CTAs per SM,
 // chains a CTA serves per work item, registers per thread.
+// shared_basis in: the batch has one depth grid; out: whether this kernel reads the basis from global memory (then `smem`
+// must be the size of the cx | y | w part only: the caller passes both sizes).
 template <int NN>
-static cudaError_t nuts_occupancy(int mod, int chains, size_t smem, int* block, int* blocks_per_sm, int* cta_chains, int* regs) {
+static cudaError_t nuts_occupancy(int mod, int chains, size_t smem_full, size_t smem_rows, int* shared_basis, size_t* smem,
+                                  int* block, int* blocks_per_sm, int* cta_chains, int* regs) {
   *block = nuts_block<NN>(chains);
+  *smem = smem_full;
   if constexpr (Dims<NN>::D <= 16) {
     if (use_pair<NN>()) {
       *cta_chains = FOCT_PAIR_CTA_CHAINS;
-      return mod == 0 ? occupancy_of(nuts2_kernel<NN, 0>, *block, smem, blocks_per_sm, regs)
-                      : occupancy_of(nuts2_kernel<NN, 1>, *block, smem, blocks_per_sm, regs);
+      static const bool no_gb = std::getenv("FOCT_NO_SHARED_BASIS") != nullptr;
+      if (*shared_basis && NN > 0 && !no_gb) {
+        *smem = smem_rows;
+        return mod == 0 ? occupancy_of(nuts2_kernel<NN, 0, true>, *block, *smem, blocks_per_sm, regs)
+                        : occupancy_of(nuts2_kernel<NN, 1, true>, *block, *smem, blocks_per_sm, regs);
+      }
+      *shared_basis = 0;
+      return mod == 0 ? occupancy_of(nuts2_kernel<NN, 0, false>, *block, *smem, blocks_per_sm, regs)
+                      : occupancy_of(nuts2_kernel<NN, 1, false>, *block, *smem, blocks_per_sm, regs);
     }
   }
+  *shared_basis = 0;
   *cta_chains = FOCT_CTA_CHAINS;
-  return mod == 0 ? occupancy_of(nuts_kernel<NN, 0>, *block, smem, blocks_per_sm, regs)
-                  : occupancy_of(nuts_kernel<NN, 1>, *block, smem, blocks_per_sm, regs);
+  return mod == 0 ? occupancy_of(nuts_kernel<NN, 0>, *block, *smem, blocks_per_sm, regs)
+                  : occupancy_of(nuts_kernel<NN, 1>, *block, *smem, blocks_per_sm, regs);
 }
 
 #define FOCT_CAT_(a, b) a##b

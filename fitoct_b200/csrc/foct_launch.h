@@ -59,7 +59,8 @@ struct InstEntry {
   int NN;  // 0 = mono-exponential
   cudaError_t (*launch_nuts)(int mod, int grid, int block, size_t smem, cudaStream_t st, const SamplerParams& K);
   cudaError_t (*launch_logp)(int mod, int grid, int block, size_t smem, cudaStream_t st, const LogpParams& K);
-  cudaError_t (*nuts_occupancy)(int mod, int chains, size_t smem, int* block, int* blocks_per_sm, int* cta_chains, int* regs);
+  cudaError_t (*nuts_occupancy)(int mod, int chains, size_t smem_full, size_t smem_rows, int* shared_basis, size_t* smem,
+                                int* block, int* blocks_per_sm, int* cta_chains, int* regs);
   cudaError_t (*launch_map)(int mod, int grid, size_t smem, cudaStream_t st, const MapParams& K);
   cudaError_t (*launch_vb)(int mod, int grid, size_t smem, cudaStream_t st, const VbParams& K);
 };

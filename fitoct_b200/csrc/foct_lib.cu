@@ -4,6 +4,7 @@
 //
 // There is no CPU compute path in this file: every compute entry point needs a CUDA device.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -19,6 +20,11 @@
 #include "foct_summary.cuh"
 
 namespace foct {
+#ifdef FOCT_VARIANT_NNS
+// scripts/build_variant.sh: a small build for kernel A/B runs that carries only Nn = 0 and Nn = 10
+FOCT_DECL_INST(0) FOCT_DECL_INST(10)
+static const InstEntry* inst_for(int NN) { return NN == 0 ? foct_inst_0() : (NN == 10 ? foct_inst_10() : nullptr); }
+#else
 FOCT_DECL_INST(0)
 FOCT_DECL_INST(1)  FOCT_DECL_INST(2)  FOCT_DECL_INST(3)  FOCT_DECL_INST(4)  FOCT_DECL_INST(5)
 FOCT_DECL_INST(6)  FOCT_DECL_INST(7)  FOCT_DECL_INST(8)  FOCT_DECL_INST(9)  FOCT_DECL_INST(10)
@@ -36,6 +42,7 @@ static const InstEntry* inst_for(int NN) {
   if (NN < 0 || NN > FOCT_MAX_NN) return nullptr;
   return table[NN]();
 }
+#endif
 
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -507,6 +514,13 @@ struct foct_plan {
   cudaEvent_t evx0 = nullptr, evx1 = nullptr, evx2 = nullptr;
   float ext_sample_ms = 0.f, ext_summary_ms = 0.f;
   unsigned long long seed = 0;
+  // progress / cancellation: device counter and flag, read and written from a side stream while the kernel runs
+  unsigned long long* d_progress = nullptr;
+  int* d_cancel = nullptr;
+  unsigned long long* h_progress = nullptr;  // pinned
+  cudaStream_t side = nullptr;
+  bool cancelled = false;
+  int shared_basis = 0;
 };
 
 // Copy the post-warm-up draws of the selected profiles into their extension blocks.
@@ -541,6 +555,8 @@ static void plan_free(foct_plan* p) {
   // foct_plan_run is asynchronous: the kernels may still be reading and writing these buffers, and pool_free hands
   // them to the next pool_malloc of any thread without the implicit synchronisation cudaFree would have done
   if (p->stream && p->ran) cudaStreamSynchronize(p->stream);
+  if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); }
+  pool_free(p->d_progress); pool_free(p->d_cancel); pinned_free(p->h_progress);
   pool_free(p->d_invm_init); pool_free(p->d_eps_init); pool_free(p->d_lastq);
   pool_free(p->d_xdraws); pool_free(p->d_xsparams); pool_free(p->d_slot_of); pool_free(p->d_sel); pool_free(p->d_sel_slots);
   if (p->evx0) cudaEventDestroy(p->evx0);
@@ -819,6 +835,11 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
   CUP(cudaEventCreate(&p->evx0));
   CUP(cudaEventCreate(&p->evx1));
   CUP(cudaEventCreate(&p->evx2));
+  CUP(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+  CUP(pool_malloc(&p->d_progress, sizeof(unsigned long long)));
+  CUP(pool_malloc(&p->d_cancel, sizeof(int)));
+  CUP(pinned_malloc(&p->h_progress, 64));
+  *p->h_progress = 0ull;
   tr.mark("stream + events");
   if (int rc = build_device_batch(kind, P, n, spec, device, p->stream, &p->NN, &p->npad, &p->blob_stride, &p->d_blobs, &p->d_probs)) {
     plan_free(p);
@@ -854,9 +875,17 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
   }
   tr.mark("output buffers");
   p->inst = inst_for(p->NN);
-  p->smem = p->blob_stride * sizeof(double);
+  if (!p->inst) { plan_free(p); return fail(FOCT_EINVAL, "this build carries no kernels for Nn=%d", p->NN); }
+  // One depth grid for the whole batch (the profiles of one acquisition: same x after selX, FitOCT.R:85-86) means one
+  // GP basis: the sampling kernel then stages only cx | y | w per profile and reads the basis of blob 0 through L1.
+  int shared_basis = kind == FOCT_EXPGP && n > 1;
+  for (int j = 1; j < n && shared_basis; ++j)
+    shared_basis = P[j].N == P[0].N && P[j].gridType == P[0].gridType && P[j].rho == P[0].rho &&
+                   std::memcmp(P[j].x, P[0].x, (size_t)P[0].N * sizeof(double)) == 0;
   int cta_chains = FOCT_CTA_CHAINS;
-  CUP(p->inst->nuts_occupancy(spec->modulation, cfg->chains, p->smem, &p->block, &p->blocks_per_sm, &cta_chains, &p->regs));
+  CUP(p->inst->nuts_occupancy(spec->modulation, cfg->chains, p->blob_stride * sizeof(double), (size_t)3 * p->npad * sizeof(double),
+                              &shared_basis, &p->smem, &p->block, &p->blocks_per_sm, &cta_chains, &p->regs));
+  p->shared_basis = shared_basis;
   if (p->blocks_per_sm < 1) { plan_free(p); return fail(FOCT_EINVAL, "sampling kernel does not fit an SM (smem %zu B)", p->smem); }
   int n_sm = 0;  // (cudaGetDeviceProperties costs milliseconds; one attribute does not)
   CUP(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
@@ -922,6 +951,7 @@ static void plan_params(const foct_plan* p, unsigned long long seed, SamplerPara
   K.draws = p->d_draws; K.sparams = p->d_sparams; K.stepsize = p->d_stepsize; K.inv_metric = p->d_invm;
   K.n_leapfrog = p->d_nleap; K.n_divergent = p->d_ndiv; K.work_counter = p->d_counter; K.order = p->d_order;
   K.invm_init = p->d_invm_init; K.eps_init = p->d_eps_init; K.last_q = p->d_lastq; K.it_offset = c.iter_offset;
+  K.progress = p->d_progress; K.cancel = p->d_cancel; K.shared_basis = p->shared_basis;
 }
 
 extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
@@ -931,6 +961,9 @@ extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
   plan_params(p, seed, K);
   const foct_sampler_cfg& c = p->cfg;
   CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), p->stream));
+  CU(cudaMemsetAsync(p->d_progress, 0, sizeof(unsigned long long), p->stream));
+  CU(cudaMemsetAsync(p->d_cancel, 0, sizeof(int), p->stream));
+  p->cancelled = false;
   CU(cudaEventRecord(p->ev0, p->stream));
   CU(p->inst->launch_nuts(p->spec.modulation, p->grid, p->block, p->smem, p->stream, K));
   CU(cudaEventRecord(p->ev1, p->stream));
@@ -955,6 +988,7 @@ extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
 static int plan_extend(foct_plan* p) {
   if (!p->extend_pending) return 0;
   p->extend_pending = false;
+  if (p->cancelled) return 0;
   const foct_sampler_cfg& c = p->cfg;
   const int n = p->n, C = c.chains, P_out = p->P_out, D = p->D, n_post = p->n_post;
   CU(cudaStreamSynchronize(p->stream));
@@ -1042,6 +1076,7 @@ extern "C" int foct_plan_sync(foct_plan* p, float* kernel_ms) {
   if (!p) return fail(FOCT_EINVAL, "NULL plan");
   CU(cudaSetDevice(p->device));
   CU(cudaStreamSynchronize(p->stream));
+  if (p->cancelled) return fail(FOCT_ECANCELLED, "the run was cancelled");
   if (int rc = plan_extend(p)) return rc;
   if (kernel_ms) {
     *kernel_ms = 0.f;
@@ -1073,6 +1108,7 @@ extern "C" int foct_plan_fetch(foct_plan* p, foct_result* R) {
   if (!p->ran) return fail(FOCT_EINVAL, "plan has not been run");
   CU(cudaSetDevice(p->device));
   CU(cudaStreamSynchronize(p->stream));
+  if (p->cancelled) return fail(FOCT_ECANCELLED, "the run was cancelled");
   if (int rc = plan_extend(p)) return rc;
   const size_t pc = (size_t)p->n * p->cfg.chains;
   if (p->x_slots > 0 && !p->thinned && p->want_draws && (R->draws || R->sampler_params)) {
@@ -1117,11 +1153,49 @@ extern "C" int foct_plan_fetch(foct_plan* p, foct_result* R) {
   return 0;
 }
 
+extern "C" int foct_plan_query(foct_plan* p, int* done, double* fraction) {
+  if (!p) return fail(FOCT_EINVAL, "NULL plan");
+  CU(cudaSetDevice(p->device));
+  const cudaError_t q = p->ran ? cudaStreamQuery(p->stream) : cudaSuccess;
+  if (q != cudaSuccess && q != cudaErrorNotReady) return fail(FOCT_ECUDA, "cudaStreamQuery failed: %s", cudaGetErrorString(q));
+  if (done) *done = q == cudaSuccess;
+  if (fraction) {
+    *fraction = 0.0;
+    if (p->ran) {
+      CU(cudaMemcpyAsync(p->h_progress, p->d_progress, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->side));
+      CU(cudaStreamSynchronize(p->side));
+      *fraction = (double)*p->h_progress / ((double)p->n * p->cfg.chains * p->cfg.n_iter);
+    }
+  }
+  return 0;
+}
+
+extern "C" int foct_plan_cancel(foct_plan* p) {
+  if (!p) return fail(FOCT_EINVAL, "NULL plan");
+  if (!p->ran) return 0;
+  CU(cudaSetDevice(p->device));
+  static const int one = 1;
+  CU(cudaMemcpyAsync(p->d_cancel, &one, sizeof(int), cudaMemcpyHostToDevice, p->side));
+  CU(cudaStreamSynchronize(p->side));
+  p->cancelled = true;
+  return 0;
+}
+
 extern "C" void foct_plan_destroy(foct_plan* p) { plan_free(p); }
 
 // ------------------------------------------------------------------ ABI: one-shot sampling, sharded over devices
+// What foct_sample_cb's polling thread shares with the per-device workers: the workers publish the chain-iterations their
+// current plan has completed, the caller's thread turns that into a fraction and may raise `cancel`.
+struct SampleJob {
+  std::atomic<long long> finished_iters{0};   // chain-iterations of chunks that are complete
+  std::atomic<long long> running_iters[64];   // ... of the chunk each worker is running now
+  std::atomic<int> extending{0};              // workers inside the rhat_target rounds
+  std::atomic<bool> cancel{false};
+  SampleJob() { for (auto& a : running_iters) a.store(0); }
+};
+
 static int sample_chunk(int device, int kind, const foct_problem* P, int first, int n, const foct_model_spec* spec,
-                        const foct_sampler_cfg* cfg, foct_result* R, int D, int P_out) {
+                        const foct_sampler_cfg* cfg, foct_result* R, int D, int P_out, SampleJob* job, int worker) {
   const int C = cfg->chains;
   const int n_saved = cfg->save_warmup ? cfg->n_iter : cfg->n_iter - cfg->n_warmup;
   foct_plan* p = nullptr;
@@ -1129,11 +1203,30 @@ static int sample_chunk(int device, int kind, const foct_problem* P, int first, 
   const double* invm_slice = cfg->inv_metric_init ? cfg->inv_metric_init + (size_t)first * C * D : nullptr;
   const double* eps_slice = cfg->stepsize_init ? cfg->stepsize_init + (size_t)first * C : nullptr;
   Trace tr("foct_sample");
+  if (job && job->cancel.load()) return fail(FOCT_ECANCELLED, "the run was cancelled");
   int rc = plan_create_on(device, kind, P + first, n, spec, cfg, init_slice, invm_slice, eps_slice,
                           R->draws || R->sampler_params, R->summary != nullptr, &p);
   if (rc) return rc;
   tr.mark("plan (alloc, pack, upload, setup kernel)");
   rc = foct_plan_run(p, cfg->seed);
+  if (!rc && job) {
+    // keep the caller's thread informed while the kernel runs; pass a cancellation on to the device
+    for (;;) {
+      int done = 0;
+      double frac = 0.0;
+      rc = foct_plan_query(p, &done, &frac);
+      if (rc) break;
+      job->running_iters[worker].store((long long)(frac * (double)n * C * cfg->n_iter));
+      if (job->cancel.load() && !p->cancelled) { rc = foct_plan_cancel(p); if (rc) break; }
+      if (done) break;
+      std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
+    if (!rc && p->extend_pending && !p->cancelled) {
+      job->extending.fetch_add(1);
+      rc = foct_plan_sync(p, nullptr);
+      job->extending.fetch_sub(1);
+    }
+  }
   if (!rc && tr.on) { foct_plan_sync(p, nullptr); tr.mark("kernels"); }
   if (!rc) {
     foct_result S = *R;
@@ -1151,6 +1244,10 @@ static int sample_chunk(int device, int kind, const foct_problem* P, int first, 
     tr.mark("fetch");
   }
   plan_free(p);
+  if (job) {
+    job->running_iters[worker].store(0);
+    if (!rc) job->finished_iters.fetch_add((long long)n * C * cfg->n_iter);
+  }
   tr.mark("free");
   return rc;
 }
@@ -1160,7 +1257,7 @@ static int sample_chunk(int device, int kind, const foct_problem* P, int first, 
 // 1e5 profiles are 54 GB of draws; 1e6 would not fit 180 GB.  Chunks are whole multiples of the
 // resident CTA count where possible, so chunking does not add partial waves.
 static int sample_shard(int device, int kind, const foct_problem* P, int first, int n, const foct_model_spec* spec,
-                        const foct_sampler_cfg* cfg, foct_result* R, int D, int P_out) {
+                        const foct_sampler_cfg* cfg, foct_result* R, int D, int P_out, SampleJob* job, int worker) {
   const int n_saved = cfg->save_warmup ? cfg->n_iter : cfg->n_iter - cfg->n_warmup;
   const double per_profile = (double)cfg->chains * std::max(1, n_saved) * (P_out + 6) * sizeof(double);
   double budget = 48.0 * 1024 * 1024 * 1024;
@@ -1170,13 +1267,13 @@ static int sample_shard(int device, int kind, const foct_problem* P, int first, 
   chunk = std::max<long long>(1, std::min<long long>(chunk, n));
   for (int off = 0; off < n; off += (int)chunk) {
     const int m = (int)std::min<long long>(chunk, n - off);
-    if (int rc = sample_chunk(device, kind, P, first + off, m, spec, cfg, R, D, P_out)) return rc;
+    if (int rc = sample_chunk(device, kind, P, first + off, m, spec, cfg, R, D, P_out, job, worker)) return rc;
   }
   return 0;
 }
 
-extern "C" int foct_sample(int kind, const foct_problem* P, int n, const foct_model_spec* spec,
-                           const foct_sampler_cfg* cfg, foct_result* R) {
+static int sample_impl(int kind, const foct_problem* P, int n, const foct_model_spec* spec, const foct_sampler_cfg* cfg,
+                       foct_result* R, foct_progress_fn progress, void* user, int poll_ms) {
   if (int rc = check_device()) return rc;
   if (!P || !spec || !cfg || !R || n < 1) return fail(FOCT_EINVAL, "NULL argument or empty batch");
   if (int rc = validate_cfg(cfg)) return rc;
@@ -1187,23 +1284,58 @@ extern "C" int foct_sample(int kind, const foct_problem* P, int n, const foct_mo
   else { int d = 0; CU(cudaGetDevice(&d)); devs.push_back(d); }
   const int ndev_avail = foct_device_count();
   for (int d : devs) if (d < 0 || d >= ndev_avail) return fail(FOCT_EINVAL, "device %d not present (%d devices)", d, ndev_avail);
-  const int G = (int)std::min<size_t>(devs.size(), (size_t)n);
-  if (G == 1) return sample_shard(devs[0], kind, P, 0, n, spec, cfg, R, D, P_out);
+  const int G = (int)std::min<size_t>(std::min<size_t>(devs.size(), (size_t)n), 64);
+  if (G == 1 && !progress) return sample_shard(devs[0], kind, P, 0, n, spec, cfg, R, D, P_out, nullptr, 0);
   // independent contiguous shards, one host thread per GPU, no collective
+  SampleJob job;
   std::vector<std::thread> th;
   std::vector<int> rcs(G, 0);
   std::vector<std::string> errs(G);
+  std::atomic<int> running{G};
   for (int gidx = 0; gidx < G; ++gidx) {
     const int first = (int)((long long)n * gidx / G), last = (int)((long long)n * (gidx + 1) / G);
     th.emplace_back([&, gidx, first, last]() {
-      rcs[gidx] = sample_shard(devs[gidx], kind, P, first, last - first, spec, cfg, R, D, P_out);
+      rcs[gidx] = sample_shard(devs[gidx], kind, P, first, last - first, spec, cfg, R, D, P_out, progress ? &job : nullptr, gidx);
       if (rcs[gidx]) errs[gidx] = g_err;
+      running.fetch_sub(1);
     });
   }
+  if (progress) {
+    // the callback runs on THIS thread (R's API is single-threaded): poll, report, pass a cancellation on
+    const double total = (double)n * cfg->chains * cfg->n_iter;
+    const auto tick = std::chrono::milliseconds(poll_ms > 0 ? poll_ms : 100);
+    auto next = std::chrono::steady_clock::now() + tick;
+    while (running.load() > 0) {
+      std::this_thread::sleep_for(std::chrono::milliseconds(2));
+      if (std::chrono::steady_clock::now() < next) continue;
+      next += tick;
+      long long it = job.finished_iters.load();
+      for (int g = 0; g < G; ++g) it += job.running_iters[g].load();
+      const double f = std::min(1.0, (double)it / total);
+      // chains advance at similar rates: warm-up is over for all of them once the mean iteration count is past it
+      const char* phase = job.extending.load() > 0 ? "Extending" : (f * cfg->n_iter < cfg->n_warmup ? "Warmup" : "Sampling");
+      if (!job.cancel.load() && progress(f, phase, user)) job.cancel.store(true);
+    }
+  }
   for (auto& t : th) t.join();
+  if (job.cancel.load()) return fail(FOCT_ECANCELLED, "the run was cancelled by the progress callback");
   for (int gidx = 0; gidx < G; ++gidx)
     if (rcs[gidx]) { g_err = errs[gidx]; return rcs[gidx]; }
+  if (progress) progress(1.0, "Sampling", user);
   return 0;
+}
+
+extern "C" int foct_sample(int kind, const foct_problem* P, int n, const foct_model_spec* spec,
+                           const foct_sampler_cfg* cfg, foct_result* R) {
+  return sample_impl(kind, P, n, spec, cfg, R, nullptr, nullptr, 0);
+}
+extern "C" int foct_sample_cb(int kind, const foct_problem* P, int n, const foct_model_spec* spec,
+                              const foct_sampler_cfg* cfg, foct_result* R, foct_progress_fn progress, void* user, int poll_ms) {
+  return sample_impl(kind, P, n, spec, cfg, R, progress, user, poll_ms);
+}
+extern "C" int foct_expgp_logp_grad(const foct_problem* P, int n, const foct_model_spec* spec, const double* q, int n_q,
+                                    double* lp, double* grad, double* chi2) {
+  return foct_logp_grad(FOCT_EXPGP, P, n, spec, q, n_q, lp, grad, chi2);
 }
 
 extern "C" int foct_expgp_sample(const foct_problem* P, int n, const foct_model_spec* spec, const foct_sampler_cfg* cfg,

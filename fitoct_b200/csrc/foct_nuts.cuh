@@ -44,7 +44,23 @@ struct SamplerParams {
   int save_stride;          // saved iterations a profile's draw block holds (0: n_saved of this launch)
   int save_offset;          // first row of this launch inside the block
   const int* slot_of;       // [..] draw block of profile j (nullptr: j)
+  // ---- progress and cancellation (foct_plan_query / foct_plan_cancel / foct_sample_cb; SURVEY §8b: R polls and calls
+  //      R_CheckUserInterrupt between polls, server.R:457-472 scrapes the progress)
+  int shared_basis;              // 1: every profile has the same depth grid; the basis rows are read through L1 from blob 0
+  unsigned long long* progress;  // chain-iterations completed so far, or nullptr
+  const int* cancel;             // != 0: every chain stops at its next iteration boundary, or nullptr
 };
+
+#define FOCT_PROGRESS_EVERY 8
+__device__ __forceinline__ bool cancel_requested(const SamplerParams& K) {
+  return K.cancel && *reinterpret_cast<const volatile int*>(K.cancel) != 0;
+}
+__device__ __forceinline__ void report_progress(const SamplerParams& K, int it_done, bool last, bool leader) {
+  // one atomic per FOCT_PROGRESS_EVERY iterations of a chain, plus the remainder when the chain ends
+  if (!K.progress || !leader) return;
+  if (last) { const int r = it_done % FOCT_PROGRESS_EVERY; if (r) atomicAdd(K.progress, (unsigned long long)r); }
+  else if (it_done % FOCT_PROGRESS_EVERY == 0) atomicAdd(K.progress, (unsigned long long)FOCT_PROGRESS_EVERY);
+}
 
 // Row of (profile, saved iteration, chain) in draws / sampler_params.
 __device__ __forceinline__ size_t save_row(const SamplerParams& K, int prob, int n_saved, int save_idx, int chain) {
@@ -59,7 +75,7 @@ __device__ __forceinline__ double lse_prob(double a, double b, double& prob_b) {
   const double d = b - a;
   const double ad = fabs(d);
   const double e = fexp(-ad);
-  double lse = fmax(a, b) + log1p(e);
+  double lse = fmax(a, b) + flog1p_unit(e);
   prob_b = (d >= 0.0 ? 1.0 : e) * frcp(1.0 + e);  // 1 + e in [1, 2]: the branch-free reciprocal is exact enough
   if (!(ad >= 0.0)) { lse = -CUDART_INF; prob_b = 0.0; }  // both weights zero
   return lse;
@@ -189,7 +205,9 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
   double st_qp[FOCT_STACK_LEVELS], st_gp[FOCT_STACK_LEVELS];
   double st_lsw[FOCT_STACK_LEVELS], st_V[FOCT_STACK_LEVELS], st_c2[FOCT_STACK_LEVELS], st_H[FOCT_STACK_LEVELS];
 
+  int it_done = 0;
   for (int it = 0; it < K.n_iter; ++it) {
+    if (cancel_requested(K)) break;
     // ================================================================ one NUTS transition
     double p = 0.0;
     if (act) {
@@ -348,7 +366,10 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       }
       if (it == K.n_warmup - 1) eps = exp(da_xbar);
     }
+    it_done = it + 1;
+    report_progress(K, it_done, false, lane == 0);
   }
+  report_progress(K, it_done, true, lane == 0);
   const size_t pc = (size_t)prob * K.chains + chain;
   if (lane == 0) {
     if (K.stepsize) K.stepsize[pc] = eps;

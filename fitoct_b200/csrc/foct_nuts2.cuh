@@ -39,9 +39,10 @@ __device__ __forceinline__ bool merge_persists_w(double invM, double i_rho, doub
 
 // lane32 = lane in the warp; this half's chain is `chain` (>= K.chains: the half has no chain and only keeps the other
 // half company in the gradient evaluations).
-template <int NN, int MOD>
+template <int NN, int MOD, bool GB>
 __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const double* __restrict__ blob, int prob,
                          int chain, int lane32) {
+  const double* __restrict__ gbasis = GB ? K.blobs : nullptr;  // blob 0: the basis every profile of the batch shares
   using DM = Dims<NN>;
   constexpr int D = DM::D;
   constexpr int P_OUT = DM::P_OUT;
@@ -70,7 +71,7 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
       else q = 0.0;
     }
   }
-  Eval ev = warp_logp_grad<NN, MOD, W>(blob, P, K.spec, q, lane);
+  Eval ev = warp_logp_grad<NN, MOD, W, GB>(blob, P, K.spec, q, lane, gbasis);
   double g = ev.g, V = -ev.lp, c2 = ev.chi2;
   double invM = 1.0;
   FOCT_PARK double eps = K.stepsize0 > 0.0 ? K.stepsize0 : 1.0;
@@ -148,6 +149,11 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
   for (;;) {
     __syncwarp();
     // ================================================================ PRE
+    if (mode == PM_ITER && cancel_requested(K)) {
+      report_progress(K, it, true, lane == 0);
+      finish_chain();
+      mode = PM_DONE;
+    }
     if (mode == PM_ITER) {
       double p = 0.0;
       if (act) {
@@ -190,7 +196,7 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
     {
       const double ph = fma(0.5 * eps_s, zg, zp);
       zq = fma(eps_s * invM, ph, zq);
-      const Eval e2 = warp_logp_grad<NN, MOD, W>(blob, P, K.spec, zq, lane);
+      const Eval e2 = warp_logp_grad<NN, MOD, W, GB>(blob, P, K.spec, zq, lane, gbasis);
       zp = fma(0.5 * eps_s, e2.g, ph);
       zg = e2.g; zV = -e2.lp; zc2 = e2.chi2;
     }
@@ -331,7 +337,8 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
           } else {
             it = it + 1;
             mode = it < K.n_iter ? PM_ITER : PM_DONE;
-            if (mode == PM_DONE) finish_chain();
+            report_progress(K, it, false, lane == 0);
+            if (mode == PM_DONE) { report_progress(K, it, true, lane == 0); finish_chain(); }
           }
         }
       }
@@ -355,7 +362,8 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
         e_after_window = 0;
         it = it + 1;
         mode = it < K.n_iter ? PM_ITER : PM_DONE;
-        if (mode == PM_DONE) finish_chain();
+        report_progress(K, it, false, lane == 0);
+        if (mode == PM_DONE) { report_progress(K, it, true, lane == 0); finish_chain(); }
       } else {
         mode = PM_ITER;  // the trial before the first transition
       }
@@ -364,14 +372,20 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
 }
 
 // Persistent CTAs of two warps = four chains of one profile (chains 2w + h: warp w, half h).  A work item is
-// (profile, group of <= 4 chains) as in nuts_kernel; four CTAs share an SM (four staged profiles, up to 255 registers
-// per thread).
+// (profile, group of <= 4 chains) as in nuts_kernel.  GB = false: the whole blob is staged, four CTAs share an SM (four
+// staged profiles, up to 255 registers per thread).  GB = true (every profile of the batch has the same depth grid, hence
+// the same basis): only cx | y | w are staged (12 KB), the basis rows come through L1 from one blob in global memory, and
+// the number of resident CTAs is set by the registers instead of the shared memory.
 #define FOCT_PAIR_CTA_CHAINS 4
 #ifndef FOCT_PAIR_MINB
 #define FOCT_PAIR_MINB 4
 #endif
-template <int NN, int MOD>
-__global__ void __launch_bounds__(16 * FOCT_PAIR_CTA_CHAINS, FOCT_PAIR_MINB) nuts2_kernel(const SamplerParams K) {
+#ifndef FOCT_PAIR_MINB_GB
+#define FOCT_PAIR_MINB_GB 6
+#endif
+template <int NN, int MOD, bool GB>
+__global__ void __launch_bounds__(16 * FOCT_PAIR_CTA_CHAINS, GB ? FOCT_PAIR_MINB_GB : FOCT_PAIR_MINB)
+nuts2_kernel(const SamplerParams K) {
   extern __shared__ __align__(128) double smem[];
   __shared__ uint64_t mbar;
   __shared__ int s_next;
@@ -389,10 +403,11 @@ __global__ void __launch_bounds__(16 * FOCT_PAIR_CTA_CHAINS, FOCT_PAIR_MINB) nut
     const int j = K.order ? K.order[w / groups] : w / groups;
     const int chain = (w % groups) * FOCT_PAIR_CTA_CHAINS + 2 * warp + (lane >> 4);
     if (threadIdx.x == 0) s_prob = K.probs[j];
-    stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase);
+    if (GB) stage_rows_tma(smem, K.blobs + (size_t)j * K.blob_stride, K.npad / 32, 3 + NN, 3, &mbar, phase);
+    else stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase);
     __syncthreads();
     // a warp runs if at least its first half has a chain
-    if ((w % groups) * FOCT_PAIR_CTA_CHAINS + 2 * warp < K.chains) run_pair<NN, MOD>(K, s_prob, smem, j, chain, lane);
+    if ((w % groups) * FOCT_PAIR_CTA_CHAINS + 2 * warp < K.chains) run_pair<NN, MOD, GB>(K, s_prob, smem, j, chain, lane);
     __syncthreads();
   }
 }

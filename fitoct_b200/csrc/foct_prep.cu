@@ -652,7 +652,19 @@ extern "C" int foct_pipeline(const foct_problem* P, int n, const foct_pipeline_c
   // 2. fitMonoExp MAP (FitOCT.R:95) with the estimated uy
   std::vector<foct_problem> Q(P, P + n);
   size_t off = 0;
-  for (int j = 0; j < n; ++j) { Q[j].uy = out->uy + off; Q[j].Nn = 0; off += (size_t)P[j].N; }
+  std::vector<double> ones;  // a profile whose noise fit failed (uy not finite / not positive) still rides along in the MAP batch
+  for (int j = 0; j < n; ++j) {
+    Q[j].uy = out->uy + off; Q[j].Nn = 0;
+    bool ok = true;
+    for (int i = 0; i < P[j].N && ok; ++i) ok = out->uy[off + i] > 0.0 && std::isfinite(out->uy[off + i]);
+    if (!ok) {
+      int maxN = 0;
+      for (int k = 0; k < n; ++k) maxN = std::max(maxN, P[k].N);
+      if (ones.empty()) ones.assign((size_t)maxN, 1.0);
+      Q[j].uy = ones.data();  // flagged FOCT_PIPE_SKIPPED in step 4 (which looks at out->uy)
+    }
+    off += (size_t)P[j].N;
+  }
   foct_model_spec sm;
   foct_model_spec_default(&sm, FOCT_MONOEXP);
   if (int rc = foct_monoexp_map(Q.data(), n, &sm, nullptr, out->mono_theta, out->mono_hessian, out->mono_br, out->mono_status)) return rc;
@@ -660,16 +672,52 @@ extern "C" int foct_pipeline(const foct_problem* P, int n, const foct_pipeline_c
   if (int rc = gate_prior(FOCT_MONOEXP, Q.data(), n, &sm, pc->prior_type, out->mono_theta, out->mono_hessian, pc->ru_theta,
                           out->mono_br, out->br_ci, out->alert, out->theta0, out->Sigma0, out->ru))
     return rc;
-  // 4. fitExpGP on the profiles the gate lets through (FitOCT.R:110-124)
+  // 4. fitExpGP on the profiles the gate lets through (FitOCT.R:110-124).  Failures are handled PER PROFILE: a MonoExp
+  //    fit that did not converge has a large Birge ratio, so it is exactly what the gate forwards, and its Hessian may be
+  //    singular or indefinite (Sigma0 = NaN) — one such profile must not abort the whole directory.
+  auto finite3 = [](const double* v, int k) { for (int i = 0; i < k; ++i) if (!std::isfinite(v[i])) return false; return true; };
+  auto spd3 = [](const double* S) {  // Cholesky of a symmetric 3 x 3
+    if (!(S[0] > 0.0)) return false;
+    const double l10 = S[3] / std::sqrt(S[0]), l20 = S[6] / std::sqrt(S[0]);
+    const double d1 = S[4] - l10 * l10;
+    if (!(d1 > 0.0)) return false;
+    const double l21 = (S[7] - l20 * l10) / std::sqrt(d1);
+    return S[8] - l20 * l20 - l21 * l21 > 0.0;
+  };
   std::vector<foct_problem> G;
+  size_t uoff = 0;
   for (int j = 0; j < n; ++j) {
+    const size_t u0 = uoff;
+    uoff += (size_t)P[j].N;
+    if (out->status) out->status[j] = FOCT_PIPE_GATED;
     if (pc->gate && !out->alert[j]) continue;
+    double* th0 = out->theta0 + 3 * (size_t)j;
+    double* S0 = out->Sigma0 + 9 * (size_t)j;
+    const double* thm = out->mono_theta + 3 * (size_t)j;
+    int stj = FOCT_PIPE_SAMPLED;
+    bool uy_ok = true;
+    for (int i = 0; i < P[j].N && uy_ok; ++i) uy_ok = out->uy[u0 + i] > 0.0 && std::isfinite(out->uy[u0 + i]);
+    if (!uy_ok || !finite3(thm, 3) || !(thm[2] != 0.0)) {
+      if (out->status) out->status[j] = FOCT_PIPE_SKIPPED;
+      continue;
+    }
+    if (!finite3(th0, 3) || !finite3(S0, 9) || !spd3(S0)) {
+      for (int k = 0; k < 9; ++k) S0[k] = 0.0;
+      for (int k = 0; k < 3; ++k) {
+        th0[k] = thm[k];
+        const double sd = pc->ru_theta * std::fabs(thm[k]);
+        S0[4 * k] = sd > 0.0 ? sd * sd : 1.0;
+      }
+      if (out->ru) out->ru[j] = pc->ru_theta;
+      stj = FOCT_PIPE_PRIOR_REPAIRED;
+    }
+    if (out->status) out->status[j] = stj;
     foct_problem g = Q[j];
     g.Nn = pc->Nn; g.gridType = pc->gridType;
     g.rho = pc->rho_scale == 0.0 ? 1.0 / pc->Nn : pc->rho_scale;
     g.lambda_rate = pc->lambda_rate; g.prior_PD = 0;
-    std::memcpy(g.theta0, out->theta0 + 3 * (size_t)j, sizeof(g.theta0));
-    std::memcpy(g.Sigma0, out->Sigma0 + 9 * (size_t)j, sizeof(g.Sigma0));
+    std::memcpy(g.theta0, th0, sizeof(g.theta0));
+    std::memcpy(g.Sigma0, S0, sizeof(g.Sigma0));
     out->expgp_index[G.size()] = j;
     G.push_back(g);
   }

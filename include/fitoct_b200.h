@@ -34,6 +34,7 @@ extern "C" {
 #define FOCT_ENODEV (-2)  /* no CUDA device / driver: the product has no CPU path */
 #define FOCT_ECUDA (-3)   /* CUDA runtime error */
 #define FOCT_ENOMEM (-4)
+#define FOCT_ECANCELLED (-5) /* the caller asked the run to stop (foct_plan_cancel, a progress callback returning non-zero) */
 
 /* model kinds */
 #define FOCT_EXPGP 0   /* replaces FitOCTLib::fitExpGP   (FitOCT.R:110-124, priPost.R:2-16, server.R:408-426) */
@@ -146,11 +147,23 @@ int foct_expgp_basis(const foct_problem* P, const foct_model_spec* spec, double*
  * log_prob + reverse-mode gradient (SURVEY a-4, a-5). */
 int foct_logp_grad(int kind, const foct_problem* P, int n_problems, const foct_model_spec* spec,
                    const double* q, int n_q, double* lp, double* grad, double* chi2);
+/* The same for kind = FOCT_EXPGP under the name SURVEY §8(b) gives the parity hook. */
+int foct_expgp_logp_grad(const foct_problem* P, int n_problems, const foct_model_spec* spec, const double* q, int n_q,
+                         double* lp, double* grad, double* chi2);
 
 /* One-shot batched NUTS: upload, sample on device, (optionally) summarise on device, download.
  * Replaces FitOCTLib::fitExpGP(method='sample') -> rstan::sampling (FitOCT.R:110-124) for a whole batch. */
 int foct_sample(int kind, const foct_problem* P, int n_problems, const foct_model_spec* spec,
                 const foct_sampler_cfg* cfg, foct_result* R);
+/* The same call for a host that must stay responsive (the R shim polls, prints rstan-style progress lines
+ * for ShinyInterface/server.R:457-472 and calls R_CheckUserInterrupt between polls).  The sampling runs on worker
+ * threads, one per device; `progress` is called ON THE CALLING THREAD every poll_ms milliseconds (and once at the end)
+ * with the fraction of chain-iterations completed and the phase ("Warmup" until every chain can have left warm-up,
+ * then "Sampling", then "Extending" during the rhat_target rounds).  A non-zero return cancels the run: every chain
+ * stops at its next iteration boundary, all buffers are released, and the call returns FOCT_ECANCELLED. */
+typedef int (*foct_progress_fn)(double fraction, const char* phase, void* user);
+int foct_sample_cb(int kind, const foct_problem* P, int n_problems, const foct_model_spec* spec,
+                   const foct_sampler_cfg* cfg, foct_result* R, foct_progress_fn progress, void* user, int poll_ms);
 /* Named as SURVEY §8(b) lists them. */
 int foct_expgp_sample(const foct_problem* P, int n_problems, const foct_model_spec* spec,
                       const foct_sampler_cfg* cfg, foct_result* R);
@@ -186,6 +199,11 @@ int foct_plan_create(int kind, const foct_problem* P, int n_problems, const foct
 int foct_plan_run(foct_plan* plan, unsigned long long seed); /* async on the plan's stream */
 int foct_plan_sync(foct_plan* plan, float* kernel_ms /* CUDA-event time of the sampling kernel, may be NULL */);
 int foct_plan_fetch(foct_plan* plan, foct_result* R);
+/* Non-blocking: *done = 1 once the kernels of the last foct_plan_run have finished; *fraction = chain-iterations
+ * completed / total (either pointer may be NULL).  foct_plan_cancel asks the running kernels to stop at the next
+ * iteration boundary of every chain; foct_plan_sync / foct_plan_fetch then return FOCT_ECANCELLED. */
+int foct_plan_query(foct_plan* plan, int* done, double* fraction);
+int foct_plan_cancel(foct_plan* plan);
 /* CUDA-event durations of the last run (sampling kernel; summary kernel) and the launch geometry of the
  * sampling kernel — what bench.py's roofline is computed from.  Any pointer may be NULL. */
 int foct_plan_timing(foct_plan* plan, float* sample_ms, float* summary_ms, int* grid, int* block,
@@ -250,7 +268,16 @@ typedef struct foct_pipeline_out {
   int n_expgp;           /* out: number of profiles passed to fitExpGP */
   int* expgp_index;      /* [n]: profile index of ExpGP fit k, k < n_expgp */
   foct_result expgp;     /* buffers sized for n problems by the caller; the first n_expgp entries are filled */
+  /* ABI 2: what happened to profile j ([n], may be NULL).  A failed or degenerate MonoExp fit (constant signal, singular
+   * Hessian) is exactly what the Birge-ratio gate forwards to fitExpGP, and one such profile must not abort a directory
+   * of 1e5: its prior is repaired or the profile is skipped, and the call goes on. */
+  int* status;           /* FOCT_PIPE_* */
 } foct_pipeline_out;
+#define FOCT_PIPE_SAMPLED 0        /* fitExpGP ran with estimateExpPrior's prior */
+#define FOCT_PIPE_GATED 1          /* MonoExp fit OK (printBr raised no alert): fitExpGP not needed (FitOCT.R:100) */
+#define FOCT_PIPE_PRIOR_REPAIRED 2 /* Sigma0 was not finite / positive definite: fitExpGP ran with the diagonal prior
+                                      diag((ru_theta theta_MAP)^2) (priorType 'mono' without the Hessian's correlations) */
+#define FOCT_PIPE_SKIPPED 3        /* no usable MonoExp fit (non-finite theta or uy): nothing to centre a prior on */
 int foct_pipeline(const foct_problem* P, int n_problems, const foct_pipeline_cfg* pc, const foct_model_spec* spec_gp,
                   const foct_sampler_cfg* cfg, foct_pipeline_out* out);
 

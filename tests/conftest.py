@@ -54,3 +54,15 @@ def case_to_batch(case):
 def grad_tol_ok(g, g_ref, abs_terms, rtol):
     """|g - g_ref| <= rtol * (|g_ref| + sum_i |summand_i|): relative to the conditioning of each sum."""
     return np.all(np.abs(np.asarray(g) - np.asarray(g_ref)) <= rtol * (np.abs(g_ref) + abs_terms))
+
+
+def record_metric(name, **values):
+    """Append measured parity figures (worst errors, not just pass/fail) to gpurun_out/parity_metrics.jsonl so that the
+    numbers behind the tolerances can be copied into profiles/ after a GPU run."""
+    d = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_metrics.jsonl"), "a") as fh:
+            fh.write(json.dumps(dict(test=name, **{k: (float(v) if np.isscalar(v) else v) for k, v in values.items()})) + "\n")
+    except OSError:
+        pass

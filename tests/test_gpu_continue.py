@@ -43,7 +43,7 @@ def test_split_run_is_bit_identical_to_the_unsplit_run(L, Nn):
     D = Nn + 5
     last = full["draws"][:, -1, :, :D].copy()
     last[..., Nn + 3:] = np.log(last[..., Nn + 3:])
-    np.testing.assert_allclose(full["last_q"], last, rtol=1e-14)
+    np.testing.assert_allclose(full["last_q"], last, rtol=1e-13, atol=1e-15)
 
 
 def test_continuation_builds_the_same_trees_as_the_oracle(L, O):
@@ -61,38 +61,36 @@ def test_continuation_builds_the_same_trees_as_the_oracle(L, O):
     np.testing.assert_array_equal(out["stepsize"], first["stepsize"])
 
 
-@pytest.mark.parametrize("Nn,n_warmup", [(10, 150), (10, 40), (15, 40)])
+@pytest.mark.parametrize("Nn,n_warmup", [(10, 150), (10, 40), (15, 150)])
 def test_adaptation_windows_match_the_oracle(L, O, Nn, n_warmup):
-    """Deterministic comparison ACROSS the metric windows (tree identity stopped at transition 6).
-    Shallow trees (max_treedepth 3) keep the floating-point chaos of the trajectories small enough for the GPU and
-    the CPU restatement to stay on the same path through init_buffer, every metric window (regularised Welford
-    variance, step-size re-initialisation, dual-averaging restart) and the final exp(x_bar)."""
+    """Deterministic comparison ACROSS the metric windows (tree identity stopped at transition 6, before
+    any window closed).  Shallow trees (max_treedepth 3) and a cautious step size (adapt_delta 0.95) keep the floating-
+    point chaos of the trajectories small — on the CPU restatement a 1e-15 perturbation of the data grows to 1e-11 over
+    these 160 transitions — so the GPU and the oracle stay on ONE path through init_buffer, the metric window
+    (regularised Welford variance), the step-size re-initialisation, the dual-averaging restart and the final
+    exp(x_bar), and every output can be compared directly."""
     _, b = batch_of(2, Nn, first_id=5)
     spec = abi.default_spec()
     n_iter = n_warmup + 10
-    cfg = abi.default_cfg(n_warmup=n_warmup, n_iter=n_iter, seed=31, save_warmup=1, max_treedepth=3)
+    cfg = abi.default_cfg(n_warmup=n_warmup, n_iter=n_iter, seed=31, save_warmup=1, max_treedepth=3, adapt_delta=0.95)
     out = L.sample(0, b, 2, spec, cfg)
     ref = O.sample(0, b, 2, spec, cfg)
     sp, spr = out["sampler_params"], ref["sampler_params"]
-    same = np.all(sp[..., 2:5] == spr[..., 2:5], axis=(0, 2, 3))
-    first_diff = int(np.argmin(same)) if not same.all() else n_iter
-    # window schedule for this n_warmup (Stan: 75/25/50, or 15 % / 75 % / 10 % below 150 iterations)
-    if n_warmup >= 150:
-        closes = [99]          # 75 + 25 - 1; the next window would end inside term_buffer, so it is stretched to 99
-    else:
-        closes = [int(0.15 * n_warmup) + (n_warmup - int(0.15 * n_warmup) - int(0.1 * n_warmup)) - 1]
-    assert first_diff > closes[-1] + 5, f"trees diverge at transition {first_diff}, before the window close {closes}"
-    upto = min(first_diff, n_iter)
-    # step size used at every transition (column 1): identical path through dual averaging and both restarts
-    np.testing.assert_allclose(sp[:, :upto, :, 1], spr[:, :upto, :, 1], rtol=1e-6)
-    # the step size jumps at the window close (re-initialised from the new metric), on both sides at the same place
-    c = closes[-1]
-    assert np.all(sp[:, c + 1, :, 1] != sp[:, c, :, 1])
-    np.testing.assert_allclose(out["draws"][:, :upto], ref["draws"][:, :upto], rtol=1e-6, atol=1e-8)
-    if first_diff == n_iter:
-        np.testing.assert_allclose(out["inv_metric"], ref["inv_metric"], rtol=1e-6)
-        np.testing.assert_allclose(out["stepsize"], ref["stepsize"], rtol=1e-6)
-    assert np.all(out["inv_metric"] != 1.0)   # the metric was adapted
+    # window schedule (Stan: 75 / 25 / 50; 15 % / 75 % / 10 % below 150 warm-up iterations): one window, closing here
+    close = 99 if n_warmup >= 150 else int(0.15 * n_warmup) + (n_warmup - int(0.15 * n_warmup) - int(0.1 * n_warmup)) - 1
+    np.testing.assert_array_equal(sp[..., 2:5], spr[..., 2:5])                         # depth, n_leapfrog, divergent
+    np.testing.assert_allclose(sp[..., 1], spr[..., 1], rtol=1e-7)                     # step size of every transition
+    np.testing.assert_allclose(sp[..., [0, 5]], spr[..., [0, 5]], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(out["draws"], ref["draws"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(out["inv_metric"], ref["inv_metric"], rtol=1e-7)
+    np.testing.assert_allclose(out["stepsize"], ref["stepsize"], rtol=1e-7)
+    # the comparison did cross what it claims to cross: the metric left the unit matrix at the window close, where the
+    # step size was re-initialised (a jump by a power of two from init_stepsize, not a dual-averaging step), and the
+    # sampling phase runs at exp(x_bar)
+    assert np.all(out["inv_metric"] != 1.0)
+    jump = sp[:, close + 1, :, 1] / sp[:, close, :, 1]
+    assert np.all(np.abs(np.log(jump)) > 0.05)
+    np.testing.assert_array_equal(sp[:, n_warmup:, :, 1], np.broadcast_to(out["stepsize"][:, None, :], sp[:, n_warmup:, :, 1].shape))
 
 
 def test_run_until_converged(L, O):
@@ -141,3 +139,34 @@ def test_rhat_target_needs_the_summary(L):
     cfg.rhat_target = 0.9
     with pytest.raises(L.FitOCTError, match="rhat_target"):
         L.sample(0, b, 1, abi.default_spec(), cfg)
+
+
+def test_progress_callback_and_cancel(L):
+    """foct_sample_cb: the callback runs on the calling thread while the kernels run; a truthy return cancels."""
+    _, b = batch_of(40, 10, first_id=300)
+    spec = abi.default_spec()
+    cfg = abi.default_cfg(n_warmup=200, n_iter=500, seed=3)
+    seen = []
+    out = L.sample(0, b, 40, spec, cfg, draws=False, progress=lambda f, ph: seen.append((f, ph)) and False, poll_ms=2)
+    ref = L.sample(0, b, 40, spec, cfg, draws=False)
+    np.testing.assert_array_equal(out["summary"], ref["summary"])          # polling does not change the result
+    fr = [f for f, _ in seen]
+    assert len(fr) >= 3 and fr == sorted(fr) and fr[-1] == 1.0 and 0.0 <= fr[0] < 1.0
+    assert seen[0][1] == "Warmup" and seen[-1][1] == "Sampling"
+    calls = []
+    with pytest.raises(L.FitOCTError) as ei:
+        L.sample(0, b, 40, spec, abi.default_cfg(n_warmup=2000, n_iter=6000, seed=3), draws=False,
+                 progress=lambda f, ph: calls.append(f) or len(calls) >= 3, poll_ms=2)
+    assert ei.value.code == -5 and len(calls) == 3 and calls[-1] < 0.5
+    again = L.sample(0, b, 40, spec, cfg, draws=False)                     # the library is fine after a cancelled run
+    np.testing.assert_array_equal(again["summary"], ref["summary"])
+    # the plan-level form
+    plan = L.Plan(0, b, 40, spec, abi.default_cfg(n_warmup=2000, n_iter=6000, seed=3), want_draws=False, want_summary=True)
+    plan.run()
+    done, f0 = plan.query()
+    assert not done and 0.0 <= f0 < 1.0
+    plan.cancel()
+    with pytest.raises(L.FitOCTError) as ei:
+        plan.sync()
+    assert ei.value.code == -5
+    plan.close()

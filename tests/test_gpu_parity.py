@@ -7,7 +7,7 @@ implementations still follow the same trajectory; posterior summaries within 3-4
 import numpy as np
 import pytest
 
-from conftest import case_to_batch, grad_tol_ok
+from conftest import case_to_batch, grad_tol_ok, record_metric
 from fitoct_b200 import _abi as abi
 from fitoct_b200 import synth
 
@@ -28,28 +28,40 @@ def rand_q(rng, theta0, Nn, n_q, wide=False):
 
 @pytest.mark.parametrize("idx", range(7))
 def test_logp_grad_vs_golden(L, O, golden, idx):
+    """FROM RAW INPUTS (x, y, uy, q): the device builds its own grid and GP basis, and log density, gradient and chi2 must
+    match the 50-digit restatement to 1e-12 (round 1 allowed 2e-8 here and reached 1e-12 only with the device basis
+    substituted into the oracle; Kgg + jitter I has a condition number of ~40, not 1e9, so no allowance is needed)."""
     case = golden[idx]
     batch, spec = case_to_batch(case)
     q = np.array(case["q"])[None]
     lp, g, chi2 = L.logp_grad(case["kind"], batch, 1, spec, q)
-    # golden values were computed with the double-rounded exact basis; the device builds its own basis, so the
-    # golden comparison allows for cond(Kgg)*eps in B, and the 1e-12 check is done against the oracle fed the
-    # device basis (test_logp_grad_vs_oracle_random).
-    loose = 1e-12 if case["kind"] == 1 or case["prior_PD"] else 2e-8
-    for k, e in enumerate(case["expected"]):
-        assert abs(lp[0, k] - float(e["lp"])) <= loose * abs(float(e["lp"]))
+    lp_ref = np.array([float(e["lp"]) for e in case["expected"]])
+    g_ref = np.array([[float(v) for v in e["grad"]] for e in case["expected"]])
+    err_lp = np.abs(lp[0] - lp_ref) / np.abs(lp_ref)
+    assert np.all(err_lp <= RTOL)
+    err_B = 0.0
     if case["kind"] == 0:
         B = L.basis(batch, 0, spec)
-        assert np.abs(B - np.array(case["basis"])).max() <= 2e-7 * np.abs(np.array(case["basis"])).max()
-        lpo, go, c2o, at = O.logp_grad(0, batch, 0, spec, q[0], B=B, want_abs=True)
+        Bg = np.array(case["basis"])
+        err_B = np.abs(B - Bg).max() / np.abs(Bg).max()
+        assert err_B <= 1e-13
+        lpo, go, c2o, at = O.logp_grad(0, batch, 0, spec, q[0], want_abs=True)      # the oracle's own basis
     else:
         lpo, go, c2o, at = O.logp_grad(1, batch, 0, spec, q[0], want_abs=True)
+    # gradient against the 50-digit value: conditioning-relative bound, and the plain relative error on record
+    assert grad_tol_ok(g[0], g_ref, at, RTOL)
+    rel_plain = np.abs(g[0] - g_ref) / np.abs(g_ref)
+    assert rel_plain.max() <= 1e-9          # (a component is a cancelling sum of ~500 terms; see `at`)
     assert np.all(np.abs(lp[0] - lpo) <= RTOL * np.abs(lpo))
     assert grad_tol_ok(g[0], go, at, RTOL)
     if not case["prior_PD"]:
-        assert np.all(np.abs(chi2[0] - c2o) <= RTOL * c2o)
+        c2_ref = np.array([float(e["chi2"]) for e in case["expected"]])
+        assert np.all(np.abs(chi2[0] - c2_ref) <= RTOL * c2_ref)
     else:
         assert np.all(np.isnan(chi2[0]))
+    record_metric("logp_grad_vs_golden", case=case["name"], rel_err_lp=err_lp.max(), rel_err_basis=err_B,
+                  worst_plain_rel_err_grad=rel_plain.max(),
+                  worst_conditioned_err_grad=(np.abs(g[0] - g_ref) / (np.abs(g_ref) + at)).max())
 
 
 @pytest.mark.parametrize("Nn", [1, 5, 10, 11, 12, 15, 20, 25])
@@ -67,13 +79,17 @@ def test_logp_grad_vs_oracle_random(L, O, Nn, mod):
     for j in range(n):
         B = L.basis(b, j, spec)
         Bo = O.basis(b, j, spec)
-        assert np.abs(B - Bo).max() <= 1e-6 * np.abs(Bo).max()
-        lpo, go, c2o, at = O.logp_grad(0, b, j, spec, q[j], B=B, want_abs=True)
+        err_B = np.abs(B - Bo).max() / np.abs(Bo).max()
+        assert err_B <= 1e-12                  # cond(Kgg) grows with Nn at fixed rho: ~1e4 at Nn = 25, rho = 0.06
+        lpo, go, c2o, at = O.logp_grad(0, b, j, spec, q[j], want_abs=True)   # raw inputs on both sides
         ok = np.isfinite(lpo)
         assert np.array_equal(np.isfinite(lp[j]), ok)
         assert np.all(np.abs(lp[j][ok] - lpo[ok]) <= RTOL * np.abs(lpo[ok]))
         assert grad_tol_ok(g[j][ok], go[ok], at[ok], RTOL)
         assert np.all(np.abs(chi2[j][ok] - c2o[ok]) <= RTOL * c2o[ok])
+        rel_plain = np.abs(g[j][ok] - go[ok]) / np.maximum(np.abs(go[ok]), 1e-300)
+        record_metric("logp_grad_vs_oracle_random", Nn=Nn, mod=mod, profile=j, rel_err_basis=err_B,
+                      rel_err_lp=(np.abs(lp[j][ok] - lpo[ok]) / np.abs(lpo[ok])).max(), worst_plain_rel_err_grad=rel_plain.max())
 
 
 def test_logp_adversarial_points(L, O):
@@ -93,8 +109,7 @@ def test_logp_adversarial_points(L, O):
     q = base.copy(); q[2] = -300.0; qs.append(q)                # negative decay length => overflow
     q = np.array(qs)[None]
     lp, g, chi2 = L.logp_grad(0, b, 1, spec, q)
-    B = L.basis(b, 0, spec)
-    lpo, go, c2o, at = O.logp_grad(0, b, 0, spec, q[0], B=B, want_abs=True)
+    lpo, go, c2o, at = O.logp_grad(0, b, 0, spec, q[0], want_abs=True)
     fin = np.isfinite(lpo)
     assert np.array_equal(np.isfinite(lp[0]), fin)               # non-finite states agree (=> divergent, H7)
     assert fin.sum() >= 4 and (~fin).sum() >= 1
@@ -116,7 +131,7 @@ def test_ragged_batch_and_empty_errors(L, O):
     q = np.stack([rand_q(rng, S["theta0"][j], 6, 2) for j in range(4)])
     lp, g, chi2 = L.logp_grad(0, b, 4, spec, q)
     for j in range(4):
-        lpo, go, c2o, at = O.logp_grad(0, b, j, spec, q[j], B=L.basis(b, j, spec), want_abs=True)
+        lpo, go, c2o, at = O.logp_grad(0, b, j, spec, q[j], want_abs=True)
         assert np.all(np.abs(lp[j] - lpo) <= RTOL * np.abs(lpo))
         assert grad_tol_ok(g[j], go, at, RTOL)
     # error behaviour: empty batch, mixed Nn, bad dataType, non-positive uy, too few points
@@ -333,7 +348,7 @@ def test_size_edges(L, O):
         Nn = c["Nn"]
         q = rand_q(rng, th0, Nn, 3)[None]
         lp, g, chi2 = L.logp_grad(0, b, 1, abi.default_spec(), q)
-        lpo, go, c2o, at = O.logp_grad(0, b, 0, abi.default_spec(), q[0], B=L.basis(b, 0, abi.default_spec()), want_abs=True)
+        lpo, go, c2o, at = O.logp_grad(0, b, 0, abi.default_spec(), q[0], want_abs=True)
         assert np.all(np.abs(lp[0] - lpo) <= RTOL * np.abs(lpo))
         assert grad_tol_ok(g[0], go, at, RTOL)
         cfg = abi.default_cfg(n_warmup=20, n_iter=30, seed=4, save_warmup=1, chains=2)
