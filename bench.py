@@ -13,7 +13,14 @@ barrier and the max-over-ranks timing.
              vs the DFMA peak measured in this run (MEASURED_PEAKS.json has no fp64 figure)
   cpu_baseline / --impl reference
              the CPU oracle (Stan's algorithm, analytic gradient — NOT rstan, which cannot run here:
-             BASELINE.md §3) on a bounded sample of the same workload, all host cores.
+             BASELINE.md §3) on a bounded sample of the same workload, all host cores; its TIMING build
+             (-O3, AVX2 + FMA: oracle/Makefile), not the separately-rounded parity build.
+  quality    every profile is sampled until its largest split R-hat is below 1.01 (north_star): the profiles still
+             above it after the configured iterations are continued on the device (rhat_target / max_extend); the
+             cost of those rounds is inside `value` and `e2e`, and `fixed_length` gives the figure without them.
+  inlib      (N > 1) the product's own multi-GPU path: rank 0 alone hands all N x profiles to ONE foct_sample()
+             call with devices = 0..N-1 (one host thread per GPU inside the library) while the other ranks wait.
+  c5         (N = 8, or --c5) BASELINE configs[4]: 100,000 profiles x 4 chains through that same call.
 """
 from __future__ import annotations
 
@@ -146,7 +153,7 @@ def run_reference(args, rank, world):
     for s in range(args.warmup + args.steps):
         cfg.seed = args.seed + s
         t0 = time.perf_counter()
-        out = O.sample(abi.FOCT_EXPGP, b, n, spec, cfg, draws=True, summary=True, n_threads=cores)
+        out = O.sample(abi.FOCT_EXPGP, b, n, spec, cfg, draws=True, summary=True, n_threads=cores, fast=True)
         dt = time.perf_counter() - t0
         threads = out["threads"]
         if s >= args.warmup:
@@ -156,14 +163,16 @@ def run_reference(args, rank, world):
     n_post = args.n_iter - args.n_warmup
     val = ess * len(times) / T
     dps = n * chains * n_post * len(times) / T
-    sample = f"{n} of {args.profiles} profiles x {chains} chains, full {args.n_warmup}/{n_post} iterations per step"
+    sample = (f"{n} of {args.profiles} profiles x {chains} chains, full {args.n_warmup}/{n_post} iterations per step, fixed length "
+              f"(no run-until-converged rounds)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic (synthData.R-shaped)", "draws_per_s": dps,
-        "config": dict(workload_config(args, args.profiles), cpu_sample_profiles=n),
+        "config": workload_config(args, args.profiles),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "draws_per_s": dps,
+                         "build": "oracle/libfoct_oracle_fast.so: gcc -O3 -march=x86-64-v3 (AVX2 + FMA), OpenMP over chains",
                          "note": "CPU restatement (Stan algorithm, analytic gradient) - not rstan (R absent, BASELINE.md s3)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -175,6 +184,7 @@ def workload_config(args, n):
                         f"warmup {args.n_warmup} + {args.n_iter - args.n_warmup} draws (BASELINE configs[2])",
             "profiles_per_gpu": n, "chains": 4, "Nn": args.nn, "N": 481, "n_warmup": args.n_warmup,
             "n_iter": args.n_iter, "adapt_delta": 0.8, "max_treedepth": 10,
+            "rhat_target": args.rhat_target, "max_extend": args.max_extend,
             "l2": "flushed between steps (256 MiB memset)", "parallelism": "independent profile shards, no collective"}
 
 
@@ -190,6 +200,11 @@ def main():
     ap.add_argument("--n-iter", type=int, default=1500)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--cpu-waves", type=int, default=3, help="CPU sample = cores/4 * waves profiles")
+    ap.add_argument("--rhat-target", type=float, default=1.01, help="continue profiles until split R-hat < this (0: off)")
+    ap.add_argument("--max-extend", type=int, default=12, help="continuation rounds of (n_iter - n_warmup) / 4 draws")
+    ap.add_argument("--c5", action="store_true", help="also run BASELINE configs[4] (100k profiles) on all N GPUs from rank 0")
+    ap.add_argument("--c5-profiles", type=int, default=100000)
+    ap.add_argument("--no-inlib", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -219,89 +234,150 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from fitoct_b200 import shard
+
     chains = 4
     n = args.profiles
     n_post = args.n_iter - args.n_warmup
     S, batch = make_batch(n, rank * n, args.nn)
     spec = abi.default_spec()
-    cfg = abi.default_cfg(n_warmup=args.n_warmup, n_iter=args.n_iter, seed=args.seed, chains=chains)
-    cfg.n_devices = 1
     import ctypes as C
     dev_arr = (C.c_int * 1)(local_rank)
-    cfg.devices = C.cast(dev_arr, C.POINTER(C.c_int))
 
+    def make_cfg(extend=True):
+        c = abi.default_cfg(n_warmup=args.n_warmup, n_iter=args.n_iter, seed=args.seed, chains=chains)
+        c.n_devices = 1
+        c.devices = C.cast(dev_arr, C.POINTER(C.c_int))
+        if extend and args.rhat_target > 0:
+            c.rhat_target, c.max_extend = args.rhat_target, args.max_extend   # rounds of n_post / 4 draws (extend_iter = 0)
+        return c
+
+    cfg = make_cfg()
+    dist_or_none = dist if world > 1 else None
     peak_tf, _ = L.fp64_peak(local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    # ---------------- value: device-resident inputs, CUDA-event timing
-    plan = L.Plan(abi.FOCT_EXPGP, batch, n, spec, cfg, want_draws=False, want_summary=True)
-    for s in range(args.warmup):
-        flush.zero_()
-        plan.run(args.seed + s)
-        plan.sync()
-    clocks = ClockSampler(local_rank)
-    barrier()
-    clocks.start()
-    step_ms, samp_ms, summ_ms, ess_sum, leap = [], [], [], 0.0, 0.0
-    t_wall0 = time.perf_counter()
-    for s in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        plan.run(args.seed + args.warmup + s)
-        plan.sync()
-        tm = plan.timing()
-        samp_ms.append(tm["sample_ms"]); summ_ms.append(tm["summary_ms"])
-        step_ms.append(tm["sample_ms"] + tm["summary_ms"])
-        out = plan.fetch()
-        ess_sum += min_ess_sum(out["summary"], args.nn)
-        leap += float(out["n_leapfrog"].sum())
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clk = clocks.stop()
-    tm = plan.timing()
-    rhat_max = float(np.nanmax(out["summary"][:, : args.nn + 5, 9]))
-    rhat_q99 = float(np.nanquantile(np.nanmax(out["summary"][:, : args.nn + 5, 9], axis=1), 0.99))
-    n_div = float(out["n_divergent"].sum())
-    plan.close()
+    def timed_plan(cfg_, steps, warmup, sample_clocks):
+        """`steps` timed fits with device-resident inputs; CUDA-event times of the kernels on the plan's stream."""
+        plan = L.Plan(abi.FOCT_EXPGP, batch, n, spec, cfg_, want_draws=False, want_summary=True)
+        for s in range(warmup):
+            flush.zero_()
+            plan.run(args.seed + s)
+            plan.sync()
+        clocks = ClockSampler(local_rank) if sample_clocks else None
+        barrier()
+        if clocks:
+            clocks.start()
+        r = dict(step_ms=[], samp_ms=[], summ_ms=[], ess=0.0, leap=0.0, launches=0, extended=0.0)
+        t0 = time.perf_counter()
+        for s in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            plan.run(args.seed + args.warmup + s)
+            plan.sync()
+            tm = plan.timing()
+            r["samp_ms"].append(tm["sample_ms"]); r["summ_ms"].append(tm["summary_ms"])
+            r["step_ms"].append(tm["sample_ms"] + tm["summary_ms"])
+            out = plan.fetch()
+            r["ess"] += min_ess_sum(out["summary"], args.nn)
+            r["leap"] += float(out["n_leapfrog"].sum())
+            r["launches"] += plan.launches()
+            r["extended"] += float((out["n_extend"] > 0).sum())
+        barrier()
+        r["wall"] = time.perf_counter() - t0
+        r["clk"] = clocks.stop() if clocks else None
+        r["tm"], r["out"] = plan.timing(), out
+        plan.close()
+        return r
 
-    T = float(np.sum(step_ms)) * 1e-3  # device time of the timed steps on this rank
-    stats = np.array([T, ess_sum, leap, float(np.sum(samp_ms)) * 1e-3], dtype=np.float64)
-    if world > 1:
-        tt = torch.from_numpy(stats.copy())
-        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        T_max, ess_all, leap_all, Ts_max = float(mx[0]), float(sm[1]), float(sm[2]), float(mx[3])
-    else:
-        T_max, ess_all, leap_all, Ts_max = stats[0], stats[1], stats[2], stats[3]
+    # ---------------- value: device-resident inputs, CUDA-event timing
+    R = timed_plan(cfg, args.steps, args.warmup, True)
+    out, tm, clk, t_wall = R["out"], R["tm"], R["clk"], R["wall"]
+    rh = np.nanmax(out["summary"][:, : args.nn + 5, 9], axis=1)
+    rhat_max, rhat_q99 = float(np.nanmax(rh)), float(np.nanquantile(rh, 0.99))
+    n_div = float(out["n_divergent"].sum())
+    T = float(np.sum(R["step_ms"])) * 1e-3  # device time of the timed steps on this rank
+    mx, sm = shard.aggregate([T, float(np.sum(R["samp_ms"])) * 1e-3], [R["ess"], R["leap"], R["extended"], float((rh < 1.01).sum())],
+                             dist_or_none)
+    T_max, Ts_max = float(mx[0]), float(mx[1])
+    ess_all, leap_all, ext_all, conv_all = (float(v) for v in sm)
     value = ess_all / T_max
     draws_per_s = world * n * chains * n_post * args.steps / T_max
 
+    # ---------------- the same without the run-until-converged rounds (what round 1 measured)
+    fixed = None
+    if args.rhat_target > 0:
+        F = timed_plan(make_cfg(False), 1, 1, False)
+        rhf = np.nanmax(F["out"]["summary"][:, : args.nn + 5, 9], axis=1)
+        mxf, smf = shard.aggregate([float(np.sum(F["step_ms"])) * 1e-3], [F["ess"], float((rhf < 1.01).sum())], dist_or_none)
+        fixed = {"value": float(smf[0]) / float(mxf[0]), "unit": UNIT, "ms_per_step": 1e3 * float(mxf[0]),
+                 "rhat_max": float(np.nanmax(rhf)), "profiles_below_1.01": float(smf[1]) / (world * n)}
+
     # ---------------- e2e: host buffers through foct_sample (H2D + D2H inside the timed region)
-    e2e = None
+    e2e = e2e_draws = None
     if not args.no_e2e:
-        L.sample(abi.FOCT_EXPGP, batch, min(n, 64), spec, cfg, draws=False, summary=True)  # warm the path
-        barrier()
-        t0 = time.perf_counter()
-        e_ess = 0.0
-        for s in range(args.steps):
-            cfg.seed = args.seed + args.warmup + s
-            o2 = L.sample(abi.FOCT_EXPGP, batch, n, spec, cfg, draws=False, summary=True)
-            e_ess += min_ess_sum(o2["summary"], args.nn)
-        barrier()
-        Te = time.perf_counter() - t0
-        cfg.seed = args.seed
-        es = np.array([Te, e_ess])
-        if world > 1:
-            a = torch.from_numpy(es.copy()); m2 = a.clone(); dist.all_reduce(m2, op=dist.ReduceOp.MAX)
-            s2 = a.clone(); dist.all_reduce(s2, op=dist.ReduceOp.SUM)
-            Te, e_all = float(m2[0]), float(s2[1])
-        else:
-            e_all = e_ess
         D, P_out = abi.dims(abi.FOCT_EXPGP, args.nn)
         h2d = n * (3 * 481 * 8 + 200)
-        d2h = n * (P_out * abi.FOCT_N_SUMMARY_COLS * 8 + chains * 8 * (1 + D + 2 + 1))
+        d2h = n * (P_out * abi.FOCT_N_SUMMARY_COLS * 8 + chains * 8 * (1 + D + 2 + 1 + D) + 4)
+
+        def timed_e2e(steps, draws):
+            L.sample(abi.FOCT_EXPGP, batch, min(n, 64), spec, cfg, draws=draws, summary=True)  # warm the path
+            barrier()
+            t0 = time.perf_counter()
+            e_ess = 0.0
+            for s in range(steps):
+                cfg.seed = args.seed + args.warmup + s
+                o2 = L.sample(abi.FOCT_EXPGP, batch, n, spec, cfg, draws=draws, summary=True)
+                e_ess += min_ess_sum(o2["summary"], args.nn)
+            barrier()
+            Te = time.perf_counter() - t0
+            cfg.seed = args.seed
+            m2, s2 = shard.aggregate([Te], [e_ess], dist_or_none)
+            return float(m2[0]), float(s2[0])
+
+        Te, e_all = timed_e2e(args.steps, False)
         e2e = {"value": e_all / Te, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "draws_per_s": world * n * chains * n_post * args.steps / Te, "ms_per_step": 1e3 * Te / args.steps}
+        # the reference contract returns the draws (plotExpGP.R:44-47): the same call shipping them and the sampler
+        # parameters to the host as well
+        Td, d_all = timed_e2e(1, True)
+        e2e_draws = {"value": d_all / Td, "unit": UNIT, "ms_per_step": 1e3 * Td, "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h + n * chains * n_post * (P_out + 6) * 8}
+
+    # ---------------- the product's own multi-GPU path: one foct_sample(devices = 0..N-1) issued by rank 0
+    inlib = c5 = None
+    run_c5 = args.c5 or world == 8
+    if world > 1 and (not args.no_inlib or run_c5):
+        barrier()
+        if rank == 0:
+            devs = list(range(world))
+            if not args.no_inlib:
+                _, ball = make_batch(world * n, 0, args.nn)
+                ci = make_cfg()
+                L.sample(abi.FOCT_EXPGP, ball, min(world * n, 64 * world), spec, ci, draws=False, summary=True, devices=devs)
+                t0 = time.perf_counter()
+                oi = L.sample(abi.FOCT_EXPGP, ball, world * n, spec, ci, draws=False, summary=True, devices=devs)
+                Ti = time.perf_counter() - t0
+                inlib = {"value": min_ess_sum(oi["summary"], args.nn) / Ti, "unit": UNIT, "ms_per_step": 1e3 * Ti, "n_gpus": world,
+                         "profiles": world * n, "how": "ONE foct_sample() call from rank 0 with devices=0..N-1, host buffers, wall clock",
+                         "rhat_max": float(np.nanmax(oi["summary"][:, : args.nn + 5, 9]))}
+                del ball, oi
+            if run_c5:
+                n5 = args.c5_profiles
+                _, b5 = make_batch(n5, 0, args.nn)
+                c5cfg = make_cfg()
+                t0 = time.perf_counter()
+                o5 = L.sample(abi.FOCT_EXPGP, b5, n5, spec, c5cfg, draws=False, summary=True, devices=devs)
+                T5 = time.perf_counter() - t0
+                rh5 = np.nanmax(o5["summary"][:, : args.nn + 5, 9], axis=1)
+                c5 = {"workload": f"{n5} profiles x {chains} chains, Nn={args.nn}, {args.n_warmup}+{n_post} iterations, ONE foct_sample() "
+                                  f"call over {world} GPUs (BASELINE configs[4], strong scaling)",
+                      "seconds": T5, "value": min_ess_sum(o5["summary"], args.nn) / T5, "unit": UNIT,
+                      "draws_per_s": n5 * chains * n_post / T5, "grad_per_s": float(o5["n_leapfrog"].sum()) / T5,
+                      "rhat_max": float(np.nanmax(rh5)), "profiles_below_1.01": float((rh5 < 1.01).mean()),
+                      "profiles_continued": float((o5["n_extend"] > 0).mean()), "divergent_post_warmup": float(o5["n_divergent"].sum())}
+                del b5, o5
+        barrier()
 
     # ---------------- cpu baseline (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
@@ -310,12 +386,14 @@ def main():
         cores = host_cores()
         nc = max(1, min(n, max(1, cores // chains) * args.cpu_waves))
         _, bc = make_batch(nc, 0, args.nn)
+        cpu_cfg = abi.default_cfg(n_warmup=args.n_warmup, n_iter=args.n_iter, seed=args.seed, chains=chains)
         t0 = time.perf_counter()
-        oc = O.sample(abi.FOCT_EXPGP, bc, nc, spec, cfg, draws=True, summary=True, n_threads=cores)
+        oc = O.sample(abi.FOCT_EXPGP, bc, nc, spec, cpu_cfg, draws=True, summary=True, n_threads=cores, fast=True)
         dt = time.perf_counter() - t0
         cpu = {"value": min_ess_sum(oc["summary"], args.nn) / dt, "unit": UNIT, "cores": oc["threads"], "kind": "port",
                "sample": f"{nc} of {n} profiles x {chains} chains, full {args.n_warmup}/{n_post} iterations, {dt:.1f} s",
                "draws_per_s": nc * chains * n_post / dt, "grad_per_s": float(oc["n_leapfrog"].sum()) / dt,
+               "build": "oracle/libfoct_oracle_fast.so: gcc -O3 -march=x86-64-v3 (AVX2 + FMA), OpenMP over chains",
                "note": "CPU restatement (Stan algorithm, analytic gradient) - not rstan (R absent, BASELINE.md s3)"}
 
     if rank == 0:
@@ -333,16 +411,24 @@ def main():
                          "algorithmic_bytes_per_launch": n * ((3 + args.nn) * 512 * 8 + chains * n_post * (args.nn + 7) * 8),
                          "peak_source": "DFMA-chain microbenchmark measured in this run (foct_fp64_peak); "
                                         "MEASURED_PEAKS.json has no fp64 figure",
-                         "kernel": "foct::nuts_kernel", "algorithmic_flop_per_grad": f_grad(481, args.nn),
+                         "kernel": "foct::nuts2_kernel" if args.nn <= 11 else "foct::nuts_kernel",
+                         "algorithmic_flop_per_grad": f_grad(481, args.nn),
                          "leapfrogs_per_step": leap_all / world / args.steps,
                          "hbm_writeback_gbs": (n * chains * n_post * (args.nn + 7) * 8 * args.steps / Ts_max) / 1e9,
                          "launch": {k: tm[k] for k in ("grid", "block", "blocks_per_sm", "regs", "smem_bytes")}},
-            "kernel_ms": {"sample": float(np.mean(samp_ms)), "summary": float(np.mean(summ_ms))},
+            "kernel_ms": {"sample": float(np.mean(R["samp_ms"])), "summary": float(np.mean(R["summ_ms"]))},
             "quality": {"rhat_max": rhat_max, "rhat_q99_of_profile_max": rhat_q99, "divergent_post_warmup": n_div,
+                        "profiles_below_1.01": conv_all / (world * n),
+                        "profiles_continued_per_step": ext_all / (world * args.steps),
                         "mean_min_bulk_ess_per_profile": ess_all / (world * n * args.steps)},
-            "clocks": clk, "e2e": e2e, "gpu_launches": 2 * args.steps,
+            "fixed_length": fixed,
+            "clocks": clk, "e2e": e2e, "e2e_with_draws": e2e_draws, "gpu_launches": int(R["launches"]),
             "wall_s_timed_region": t_wall,
         }
+        if inlib is not None:
+            line["inlib"] = inlib
+        if c5 is not None:
+            line["c5"] = c5
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -84,6 +84,7 @@ class SamplerCfg(C.Structure):
         ("iter_offset", C.c_int),
         ("rhat_target", C.c_double),
         ("max_extend", C.c_int),
+        ("extend_iter", C.c_int),
     ]
 
 

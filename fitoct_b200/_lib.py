@@ -24,7 +24,7 @@ EXPORTS = (
     "foct_plan_sync", "foct_plan_timing", "foct_plan_fetch", "foct_plan_destroy", "foct_fp64_peak",
     "foct_estimate_noise", "foct_birge_ci", "foct_print_br", "foct_estimate_exp_prior", "foct_pipeline_cfg_default",
     "foct_pipeline", "foct_vb_cfg_default", "foct_vb", "foct_release_cache",
-    "foct_sample_cb", "foct_plan_query", "foct_plan_cancel", "foct_expgp_logp_grad",
+    "foct_sample_cb", "foct_plan_query", "foct_plan_cancel", "foct_expgp_logp_grad", "foct_plan_launches",
 )
 
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_double, C.c_char_p, C.c_void_p)
@@ -64,6 +64,7 @@ def lib():
         L.foct_expgp_logp_grad.argtypes = [PP, C.c_int, MS, dp, C.c_int, dp, dp, dp]
         L.foct_plan_query.argtypes = [C.c_void_p, ip, dp]
         L.foct_plan_cancel.argtypes = [C.c_void_p]
+        L.foct_plan_launches.argtypes = [C.c_void_p]
         for name in ("foct_expgp_sample", "foct_monoexp_sample"):
             getattr(L, name).argtypes = [PP, C.c_int, MS, SC, RS]
         L.foct_monoexp_map.argtypes = [PP, C.c_int, MS, dp, dp, dp, dp, ip]
@@ -163,7 +164,7 @@ def continuation_cfg(cfg: abi.SamplerCfg, prev: dict, n_more: int, iters_done: i
     c.init_mode, c.init = 2, abi.as_ptr(init)
     c.inv_metric_init, c.stepsize_init = abi.as_ptr(invm), abi.as_ptr(eps)
     c.iter_offset = int(iters_done)
-    c.rhat_target, c.max_extend = 0.0, 0
+    c.rhat_target, c.max_extend, c.extend_iter = 0.0, 0, 0
     return c
 
 
@@ -225,6 +226,9 @@ class Plan:
 
     def cancel(self):
         check(lib().foct_plan_cancel(self._h))
+
+    def launches(self) -> int:
+        return int(lib().foct_plan_launches(self._h))
 
     def fetch(self):
         out, R = alloc_result(self.kind, self.n, self.Nn, self.cfg, self.want_draws, self.want_summary)

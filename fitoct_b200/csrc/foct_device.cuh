@@ -283,6 +283,9 @@ struct Dims {
 // carries the lane index inside the group): the points are the two 16-point halves of consecutive 32-point blocks.
 // GB: the basis rows are not in the staged block (which then holds cx | y | w only) but read through L1 from `pg`, a
 // blob in global memory that every profile of the batch shares (same depth grid => same basis).
+#ifndef FOCT_PAIR_LDS128
+#define FOCT_PAIR_LDS128 1
+#endif
 template <int NN, int MOD, int KP, int ZI, int U, int W = 32, bool GB = false>
 __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, double th1, double th2, double th3, double r3,
                                              const double (&yg)[NN > 0 ? NN : 1], double (&acc)[KP],
@@ -296,20 +299,49 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
   double dl0[U], dl1[U], s[U], cx[U], y[U], ws[U], r[U], t[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) { dl0[u] = 1.0; dl1[u] = 0.0; }  // s = 1 + dL: the 1 rides in the first partial sum
+#if FOCT_PAIR_LDS128
+  if constexpr (W == 16) {
+    // Half-warp groups: lane l takes the NEIGHBOURING points 2l, 2l+1 of a 32-point block (pp carries 2l), so one
+    // 128-bit load per row serves both points in flight.  An LDS.64 costs ~2.6 issue cycles next to the fp64 stream,
+    // an LDS.128 ~1.6 for twice the data (scripts/micro/issue_cost.cu): the loads were a quarter of the sweep's issue time.
 #pragma unroll
-  for (int k = 0; k < NN; ++k) {
+    for (int k = 0; k < NN; ++k) {
+#pragma unroll
+      for (int v = 0; v < U / 2; ++v) {
+        const double2 bb = GB ? __ldg(reinterpret_cast<const double2*>(pg + v * (3 + NN) * 32 + (3 + k) * 32))
+                              : *reinterpret_cast<const double2*>(pp + v * SROWS * 32 + (3 + k) * 32);
+        b[2 * v][k] = bb.x; b[2 * v + 1][k] = bb.y;
+        if (k & 1) { dl1[2 * v] = fma(bb.x, yg[k], dl1[2 * v]); dl1[2 * v + 1] = fma(bb.y, yg[k], dl1[2 * v + 1]); }
+        else { dl0[2 * v] = fma(bb.x, yg[k], dl0[2 * v]); dl0[2 * v + 1] = fma(bb.y, yg[k], dl0[2 * v + 1]); }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < U / 2; ++v) {
+      const double2 c2 = *reinterpret_cast<const double2*>(pp + v * SROWS * 32);
+      const double2 y2 = *reinterpret_cast<const double2*>(pp + v * SROWS * 32 + 32);
+      const double2 w2 = *reinterpret_cast<const double2*>(pp + v * SROWS * 32 + 64);
+      cx[2 * v] = c2.x; cx[2 * v + 1] = c2.y; y[2 * v] = y2.x; y[2 * v + 1] = y2.y; ws[2 * v] = w2.x; ws[2 * v + 1] = w2.y;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) s[u] = dl0[u] + dl1[u];
+  } else
+#endif
+  {
+#pragma unroll
+    for (int k = 0; k < NN; ++k) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        b[u][k] = GB ? __ldg(pg + FOCT_PTG(u) + (3 + k) * 32) : pp[FOCT_PT(u) + (3 + k) * 32];
+        if (k & 1) dl1[u] = fma(b[u][k], yg[k], dl1[u]); else dl0[u] = fma(b[u][k], yg[k], dl0[u]);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      b[u][k] = GB ? __ldg(pg + FOCT_PTG(u) + (3 + k) * 32) : pp[FOCT_PT(u) + (3 + k) * 32];
-      if (k & 1) dl1[u] = fma(b[u][k], yg[k], dl1[u]); else dl0[u] = fma(b[u][k], yg[k], dl0[u]);
+      s[u] = dl0[u] + dl1[u];
+      cx[u] = pp[FOCT_PT(u)];
+      y[u] = pp[FOCT_PT(u) + 32];
+      ws[u] = pp[FOCT_PT(u) + 64];  // 1/uy; the 1/sigma^2 common to every sum is applied once after the reduction
     }
-  }
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    s[u] = dl0[u] + dl1[u];
-    cx[u] = pp[FOCT_PT(u)];
-    y[u] = pp[FOCT_PT(u) + 32];
-    ws[u] = pp[FOCT_PT(u) + 64];  // 1/uy; the 1/sigma^2 common to every sum is applied once after the reduction
   }
   // reciprocal of the local decay length (length modulation with a GP); otherwise r3 is hoisted
   if (MOD == 0 && NN > 0) {
@@ -512,8 +544,10 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
     const double r3 = frcp(th3);  // (a full division drags its exponent-range slow path into every leaf)
     constexpr int ROWS = GB ? 3 : 3 + NN;     // rows of a staged block
     constexpr int GROWS = 3 + NN;             // rows of a block of the shared (global) blob
-    const double* pp = blob + lane;
-    const double* pg = GB ? gbasis + lane : nullptr;
+    // (half-warp groups with 128-bit loads: lane l owns the neighbouring points 2l, 2l+1 of each block)
+    const int lane_off = (W == 16 && FOCT_PAIR_LDS128) ? 2 * lane : lane;
+    const double* pp = blob + lane_off;
+    const double* pg = GB ? gbasis + lane_off : nullptr;
     FOCT_T(t_l0);
     FOCT_TADD(3, t_g0, t_l0);
     int pass = 0;

@@ -455,8 +455,11 @@ static cudaError_t nuts_occupancy(int mod, int chains, size_t smem_full, size_t 
   if constexpr (Dims<NN>::D <= 16) {
     if (use_pair<NN>()) {
       *cta_chains = FOCT_PAIR_CTA_CHAINS;
-      static const bool no_gb = std::getenv("FOCT_NO_SHARED_BASIS") != nullptr;
-      if (*shared_basis && NN > 0 && !no_gb) {
+      // measured (profiles/r2_kernel_experiments.txt): with the basis read through L1 six CTAs fit an SM instead of four.
+      // With 64-bit loads that bought nothing (2.58e8 vs 2.61e8 gradients/s at full waves: twice the L1 requests of the
+      // staged variant's LDS); with one 128-bit load per row and point pair it is 3.06e8.  FOCT_NO_SHARED_BASIS=1: A/B.
+      static const bool use_gb = std::getenv("FOCT_NO_SHARED_BASIS") == nullptr;
+      if (*shared_basis && NN > 0 && use_gb) {
         *smem = smem_rows;
         return mod == 0 ? occupancy_of(nuts2_kernel<NN, 0, true>, *block, *smem, blocks_per_sm, regs)
                         : occupancy_of(nuts2_kernel<NN, 1, true>, *block, *smem, blocks_per_sm, regs);

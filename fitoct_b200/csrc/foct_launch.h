@@ -68,6 +68,7 @@ struct InstEntry {
 // shared by the host translation units (defined in foct_lib.cu)
 int fail(int code, const char* fmt, ...);  // records the thread-local message behind foct_last_error(), returns code
 int check_device();
+int sm_count();  // SMs of the current device
 // cached device / pinned-host buffers (foct_lib.cu): freed blocks are kept for later calls, see foct_release_cache()
 cudaError_t device_cache_alloc(void** p, size_t bytes);
 void device_cache_free(void* p);

@@ -507,7 +507,7 @@ struct foct_plan {
   double *d_invm_init = nullptr, *d_eps_init = nullptr, *d_lastq = nullptr;
   // run until converged (cfg.rhat_target): extension blocks of the profiles that were continued
   bool extend_pending = false, thinned = false;
-  int x_cap = 0, x_slots = 0;
+  int x_cap = 0, x_slots = 0, x_ext = 0;
   double *d_xdraws = nullptr, *d_xsparams = nullptr;
   int *d_slot_of = nullptr, *d_sel = nullptr, *d_sel_slots = nullptr;
   std::vector<int> n_extend, slot_of;
@@ -521,6 +521,7 @@ struct foct_plan {
   cudaStream_t side = nullptr;
   bool cancelled = false;
   int shared_basis = 0;
+  int launches = 0;  // kernels of the last run
 };
 
 // Copy the post-warm-up draws of the selected profiles into their extension blocks.
@@ -532,19 +533,22 @@ __global__ void gather_blocks_kernel(const double* __restrict__ src, size_t src_
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
   }
 }
-// Thin an extension block back into the profile's post-warm-up rows: row t <- row (t + 1) * step - 1.
+// Thin an extension block back into the profile's post-warm-up rows: row t <- row floor((t + 1) total / n_post) - 1 of
+// the block, total = n_post + n_extend * ext draws.
 __global__ void thin_blocks_kernel(const double* __restrict__ xsrc, size_t x_stride, double* __restrict__ dst, size_t dst_stride,
-                                   size_t dst_off, int n_post, size_t row_len, const int* __restrict__ slot_of,
+                                   size_t dst_off, int n_post, int ext, size_t row_len, const int* __restrict__ slot_of,
                                    const int* __restrict__ n_extend, int n) {
   for (int j = blockIdx.y; j < n; j += gridDim.y) {
     const int e = n_extend[j];
     if (e <= 0) continue;
+    const long long total = (long long)n_post + (long long)e * ext;
     const double* a = xsrc + (size_t)slot_of[j] * x_stride;
     double* b = dst + (size_t)j * dst_stride + dst_off;
     const size_t tot = (size_t)n_post * row_len;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
       const size_t t = i / row_len, c = i % row_len;
-      b[i] = a[((t + 1) * (size_t)(e + 1) - 1) * row_len + c];
+      const size_t src = (size_t)(((long long)(t + 1) * total) / n_post - 1);
+      b[i] = a[src * row_len + c];
     }
   }
 }
@@ -570,6 +574,19 @@ static void plan_free(foct_plan* p) {
   if (p->ev2) cudaEventDestroy(p->ev2);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
+}
+
+// Streaming multiprocessors of the current device (grids are sized in multiples of it; 148 on B200).
+int foct::sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    cached_dev = dev; cached = n;
+  }
+  return cached;
 }
 
 int foct::check_device() {
@@ -649,7 +666,7 @@ static int build_device_batch(int kind, const foct_problem* P, int n, const foct
     CUB(cudaMemcpyAsync(d_up, h_up, total * sizeof(double), cudaMemcpyHostToDevice, st));
     CUB(cudaMemcpyAsync(d_meta, h_meta, (size_t)n * sizeof(HostMeta), cudaMemcpyHostToDevice, st));
     CUB(cudaMemsetAsync(d_status, 0, sizeof(int), st));
-    const int grid = std::min(n, 148 * 8);
+    const int grid = std::min(n, sm_count() * 8);
     setup_kernel<<<grid, 128, 0, st>>>(d_up, d_meta, n, NN, npad, stride, *d_blobs, *d_probs, spec->kernel, spec->jitter,
                                        spec->br_ndf, d_status);
     CUB(cudaGetLastError());
@@ -753,7 +770,7 @@ extern "C" int foct_logp_grad(int kind, const foct_problem* P, int n, const foct
       K.width = (wenv && std::atoi(wenv) == 32) ? 32 : 16;
     }
     const InstEntry* inst = inst_for(NN);
-    CUB(inst->launch_logp(spec->modulation, std::min(n, 148 * 4), 128, stride * sizeof(double), 0, K));
+    CUB(inst->launch_logp(spec->modulation, std::min(n, sm_count() * 4), 128, stride * sizeof(double), 0, K));
     CUB(cudaDeviceSynchronize());
     CUB(cudaMemcpy(lp, d_lp, nq * sizeof(double), cudaMemcpyDeviceToHost));
     CUB(cudaMemcpy(grad, d_g, nq * D * sizeof(double), cudaMemcpyDeviceToHost));
@@ -785,7 +802,7 @@ extern "C" int foct_predict(int kind, const foct_problem* P, const foct_model_sp
     CUB(pool_malloc(&d_r, tot * sizeof(double)));
     CUB(pool_malloc(&d_dl, tot * sizeof(double)));
     CUB(cudaMemcpy(d_dr, draws, (size_t)n_draws * P_out * sizeof(double), cudaMemcpyHostToDevice));
-    predict_kernel<<<(int)std::min<size_t>((tot + 255) / 256, 148 * 16), 256>>>(d_blobs, npad, P->N, NN, spec->modulation, P_out,
+    predict_kernel<<<(int)std::min<size_t>((tot + 255) / 256, (size_t)sm_count() * 16), 256>>>(d_blobs, npad, P->N, NN, spec->modulation, P_out,
                                                                                 d_dr, n_draws, d_m, d_r, d_dl);
     CUB(cudaGetLastError());
     CUB(cudaDeviceSynchronize());
@@ -808,6 +825,7 @@ static int validate_cfg(const foct_sampler_cfg* c) {
   if (c->iter_offset < 0) return fail(FOCT_EINVAL, "iter_offset=%d < 0", c->iter_offset);
   if (c->rhat_target > 0.0 && (c->max_extend < 0 || c->max_extend > 64)) return fail(FOCT_EINVAL, "max_extend=%d outside 0..64", c->max_extend);
   if (c->rhat_target > 0.0 && !(c->rhat_target > 1.0)) return fail(FOCT_EINVAL, "rhat_target=%g must exceed 1", c->rhat_target);
+  if (c->extend_iter < 0) return fail(FOCT_EINVAL, "extend_iter=%d < 0", c->extend_iter);
   return 0;
 }
 
@@ -973,6 +991,7 @@ extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
   }
   CU(cudaEventRecord(p->ev2, p->stream));
   p->ran = true;
+  p->launches = 1 + (p->want_summary && p->n_post >= 2 ? 1 : 0);
   p->seed = seed;
   p->thinned = false;
   p->ext_sample_ms = p->ext_summary_ms = 0.f;
@@ -1013,7 +1032,9 @@ static int plan_extend(foct_plan* p) {
   if (sel.empty()) return 0;
   // extension blocks: one per profile selected in the first round
   const int m0 = (int)sel.size();
-  p->x_cap = (c.max_extend + 1) * n_post;
+  const int ext = c.extend_iter > 0 ? c.extend_iter : std::max(50, (n_post + 3) / 4);
+  p->x_ext = ext;
+  p->x_cap = n_post + c.max_extend * ext;
   p->x_slots = m0;
   p->slot_of.assign(n, -1);
   for (int k = 0; k < m0; ++k) p->slot_of[sel[k]] = k;
@@ -1042,15 +1063,17 @@ static int plan_extend(foct_plan* p) {
         gather_blocks_kernel<<<grid, 256, 0, p->stream>>>(p->d_sparams, (size_t)p->n_saved * C * 6, (size_t)off * C * 6, p->d_xsparams,
                                                           (size_t)p->x_cap * C * 6, (size_t)n_post * C * 6, p->d_sel, p->d_sel_slots, m);
       CU(cudaGetLastError());
+      p->launches += p->d_xsparams ? 2 : 1;
     }
+    p->launches += 2;
     SamplerParams K;
     plan_params(p, p->seed, K);
     K.n_problems = m; K.order = p->d_sel;
-    K.n_warmup = 0; K.n_iter = n_post; K.save_warmup = 0;
+    K.n_warmup = 0; K.n_iter = ext; K.save_warmup = 0;
     K.init_mode = 2; K.init = p->d_lastq; K.invm_init = p->d_invm; K.eps_init = p->d_stepsize;
-    K.it_offset = c.iter_offset + c.n_iter + (e - 1) * n_post;
+    K.it_offset = c.iter_offset + c.n_iter + (e - 1) * ext;
     K.draws = p->d_xdraws; K.sparams = p->d_xsparams; K.slot_of = p->d_slot_of;
-    K.save_stride = p->x_cap; K.save_offset = e * n_post; K.accumulate = 1;
+    K.save_stride = p->x_cap; K.save_offset = n_post + (e - 1) * ext; K.accumulate = 1;
     CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), p->stream));
     cudaEvent_t a0, a1, a2;
     CU(cudaEventCreate(&a0)); CU(cudaEventCreate(&a1)); CU(cudaEventCreate(&a2));
@@ -1058,7 +1081,7 @@ static int plan_extend(foct_plan* p) {
     const int grid = (int)std::min<long long>((long long)m * p->groups, (long long)p->n_sm * p->blocks_per_sm);
     CU(p->inst->launch_nuts(p->spec.modulation, grid, p->block, p->smem, p->stream, K));
     CU(cudaEventRecord(a1, p->stream));
-    CU(launch_summary(p->d_xdraws, m, p->x_cap, 0, (e + 1) * n_post, C, P_out, p->d_summary, p->stream, p->d_sel_slots, p->d_sel));
+    CU(launch_summary(p->d_xdraws, m, p->x_cap, 0, n_post + e * ext, C, P_out, p->d_summary, p->stream, p->d_sel_slots, p->d_sel));
     CU(cudaEventRecord(a2, p->stream));
     CU(cudaMemcpyAsync(rh.data(), p->d_summary, rh.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
@@ -1120,10 +1143,10 @@ extern "C" int foct_plan_fetch(foct_plan* p, foct_result* R) {
     const size_t row = (size_t)C * p->P_out;
     const dim3 grid(32, std::min(p->n, 65535));
     thin_blocks_kernel<<<grid, 256, 0, p->stream>>>(p->d_xdraws, (size_t)p->x_cap * row, p->d_draws, (size_t)p->n_saved * row,
-                                                    (size_t)off * row, p->n_post, row, p->d_slot_of, d_next, p->n);
+                                                    (size_t)off * row, p->n_post, p->x_ext, row, p->d_slot_of, d_next, p->n);
     if (p->d_xsparams)
       thin_blocks_kernel<<<grid, 256, 0, p->stream>>>(p->d_xsparams, (size_t)p->x_cap * C * 6, p->d_sparams, (size_t)p->n_saved * C * 6,
-                                                      (size_t)off * C * 6, p->n_post, (size_t)C * 6, p->d_slot_of, d_next, p->n);
+                                                      (size_t)off * C * 6, p->n_post, p->x_ext, (size_t)C * 6, p->d_slot_of, d_next, p->n);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
     pool_free(d_next);
@@ -1181,6 +1204,7 @@ extern "C" int foct_plan_cancel(foct_plan* p) {
   return 0;
 }
 
+extern "C" int foct_plan_launches(foct_plan* p) { return p ? p->launches : 0; }
 extern "C" void foct_plan_destroy(foct_plan* p) { plan_free(p); }
 
 // ------------------------------------------------------------------ ABI: one-shot sampling, sharded over devices
@@ -1263,7 +1287,11 @@ static int sample_shard(int device, int kind, const foct_problem* P, int first, 
   double budget = 48.0 * 1024 * 1024 * 1024;
   if (const char* env = std::getenv("FOCT_DRAW_BUDGET_MB")) budget = std::atof(env) * 1024 * 1024;
   long long chunk = (long long)(budget / per_profile);
-  if (chunk >= 2048) chunk -= chunk % 592;  // whole waves of resident CTAs where the chunk is many waves anyway (4 per SM x 148)
+  {  // whole waves of resident CTAs where the chunk is many waves anyway (~4-6 CTAs per SM)
+    cudaSetDevice(device);
+    const long long wave = (long long)sm_count() * 4;
+    if (chunk >= 4 * wave) chunk -= chunk % wave;
+  }
   chunk = std::max<long long>(1, std::min<long long>(chunk, n));
   for (int off = 0; off < n; off += (int)chunk) {
     const int m = (int)std::min<long long>(chunk, n - off);
@@ -1414,7 +1442,7 @@ extern "C" int foct_expgp_map(const foct_problem* P, int n, const foct_model_spe
     K.blobs = d_blobs; K.blob_stride = stride; K.npad = npad; K.probs = d_probs; K.n_problems = n;
     K.spec = dev_spec(*spec); K.init = d_init; K.par = d_par; K.hessian = d_H; K.status = d_st; K.max_iter = 1000;
     const InstEntry* inst = inst_for(NN);
-    CUB(inst->launch_map(spec->modulation, std::min(n, 148 * 4), stride * sizeof(double), 0, K));
+    CUB(inst->launch_map(spec->modulation, std::min(n, sm_count() * 4), stride * sizeof(double), 0, K));
     CUB(cudaDeviceSynchronize());
     CUB(cudaMemcpy(par, d_par, (size_t)n * P_out * sizeof(double), cudaMemcpyDeviceToHost));
     if (hessian) CUB(cudaMemcpy(hessian, d_H, (size_t)n * D * D * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1475,7 +1503,7 @@ extern "C" int foct_vb(int kind, const foct_problem* P, int n, const foct_model_
     K.init = d_init; K.mean = d_mean; K.draws = d_draws; K.mu = d_mu; K.omega = d_om; K.elbo = d_elbo; K.eta_out = d_eta;
     K.iters = d_it; K.status = d_st;
     const InstEntry* inst = inst_for(NN);
-    CUB(inst->launch_vb(spec->modulation, std::min(n, 148 * 8), stride * sizeof(double), 0, K));
+    CUB(inst->launch_vb(spec->modulation, std::min(n, sm_count() * 8), stride * sizeof(double), 0, K));
     CUB(cudaDeviceSynchronize());
     CUB(cudaMemcpy(R->mean, d_mean, (size_t)n * P_out * sizeof(double), cudaMemcpyDeviceToHost));
     CUB(cudaMemcpy(R->mu, d_mu, (size_t)n * D * sizeof(double), cudaMemcpyDeviceToHost));

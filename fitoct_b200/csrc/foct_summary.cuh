@@ -295,12 +295,12 @@ static cudaError_t launch_summary(const double* d_draws, int n_problems, int n_s
   if (bytes <= 200 * 1024) {
     e = cudaFuncSetAttribute(summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    const int grid = n_items < 148 * 64 ? n_items : 148 * 64;
+    const int grid = n_items < sm_count() * 64 ? n_items : sm_count() * 64;
     summary_kernel<<<grid, SUM_THREADS, bytes, st>>>(d_draws, n_saved, off, n_post, C, P_out, Spad, n_items, d_summary, nullptr, in_slot, out_row);
     return cudaGetLastError();
   }
   double* gwork = nullptr;
-  const int grid = n_items < 148 * 4 ? n_items : 148 * 4;
+  const int grid = n_items < sm_count() * 4 ? n_items : sm_count() * 4;
   e = cudaMallocAsync((void**)&gwork, bytes * (size_t)grid, st);
   if (e != cudaSuccess) return e;
   summary_kernel<<<grid, SUM_THREADS, 0, st>>>(d_draws, n_saved, off, n_post, C, P_out, Spad, n_items, d_summary, gwork, in_slot, out_row);

@@ -102,11 +102,13 @@ typedef struct foct_sampler_cfg {
   int iter_offset;
   /* Run until converged (BASELINE north_star: "sampled to R-hat < 1.01"): after the n_iter iterations, every profile
    * whose largest split R-hat over the sampled parameters is >= rhat_target is continued on the device — same adapted
-   * metric and step size, no new warm-up — for another n_iter - n_warmup draws, at most max_extend times.  The summary
-   * then covers ALL post-warm-up draws of the profile; the returned post-warm-up draws / sampler_params keep their shape
-   * and hold every (1 + n_extend)-th draw.  rhat_target <= 0: off.  Needs the summary output. */
+   * metric and step size, no new warm-up — for another extend_iter draws, at most max_extend times.  The summary then
+   * covers ALL post-warm-up draws of the profile; the returned post-warm-up draws / sampler_params keep their shape and
+   * are thinned evenly out of them (row t <- draw floor((t + 1) total / n_post) - 1).  rhat_target <= 0: off.  Needs
+   * the summary output. */
   double rhat_target;
   int max_extend;
+  int extend_iter; /* draws per continuation round; 0 => a quarter of n_iter - n_warmup (at least 50) */
 } foct_sampler_cfg;
 
 /* Caller-allocated outputs; any pointer may be NULL to skip that output.
@@ -208,6 +210,8 @@ int foct_plan_cancel(foct_plan* plan);
  * sampling kernel — what bench.py's roofline is computed from.  Any pointer may be NULL. */
 int foct_plan_timing(foct_plan* plan, float* sample_ms, float* summary_ms, int* grid, int* block,
                      int* blocks_per_sm, int* regs, int* smem_bytes);
+/* Kernels the last foct_plan_run launched so far (sampling, summary, and those of the continuation rounds). */
+int foct_plan_launches(foct_plan* plan);
 void foct_plan_destroy(foct_plan* plan);
 
 /* ---- the steps either side of the sampling path (MODEL_SPEC §11-13) ---------------------------

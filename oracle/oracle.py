@@ -17,6 +17,20 @@ sys.path.insert(0, os.path.dirname(_HERE))
 from fitoct_b200 import _abi as abi  # noqa: E402  (struct definitions only)
 
 _LIB = None
+_FAST = None
+
+
+def fast_lib():
+    """The TIMING build (-O3, AVX2 + FMA; oracle/Makefile): same entry points, used only by bench.py's CPU legs."""
+    global _FAST
+    if _FAST is None:
+        path = os.path.join(_HERE, "libfoct_oracle_fast.so")
+        if not os.path.exists(path):
+            build()
+        _FAST = C.CDLL(path)
+        _FAST.foct_oracle_sample.argtypes = [C.c_int, C.POINTER(abi.Problem), C.c_int, C.POINTER(abi.ModelSpec),
+                                             C.POINTER(abi.SamplerCfg), C.POINTER(abi.Result), C.c_int]
+    return _FAST
 
 
 def build() -> str:
@@ -125,11 +139,12 @@ def alloc_result(kind, n_problems, Nn, cfg: abi.SamplerCfg, draws=True, summary=
     return out, R
 
 
-def sample(kind, batch: abi.ProblemBatch, n_problems, spec, cfg, draws=True, summary=True, n_threads=0):
+def sample(kind, batch: abi.ProblemBatch, n_problems, spec, cfg, draws=True, summary=True, n_threads=0, fast=False):
     Nn = batch.array[0].Nn if kind == abi.FOCT_EXPGP else 0
     out, R = alloc_result(kind, n_problems, Nn, cfg, draws, summary)
-    used = _check(lib().foct_oracle_sample(kind, batch.array, n_problems, C.byref(spec), C.byref(cfg), C.byref(R),
-                                           n_threads), "sample")
+    L = fast_lib() if fast else lib()
+    used = _check(L.foct_oracle_sample(kind, batch.array, n_problems, C.byref(spec), C.byref(cfg), C.byref(R),
+                                       n_threads), "sample")
     out["threads"] = used
     return out
 

@@ -70,6 +70,7 @@ static void fill_cfg(foct_sampler_cfg* cfg, SEXP ctl) {
   cfg->init_mode = (int)get_num(ctl, "init_mode", 0);
   cfg->rhat_target = get_num(ctl, "rhat_target", 0.0);
   cfg->max_extend = (int)get_num(ctl, "max_extend", 0);
+  cfg->extend_iter = (int)get_num(ctl, "extend_iter", 0);
   cfg->save_warmup = (int)get_num(ctl, "save_warmup", 1); /* traceplot(inc_warmup = TRUE), plotExpGP.R:46 */
 }
 /* theta0 (3) / Sigma0 (9) of problem j from a vector (one profile) or a 3 x n / 9 x n matrix; a zero-length vector is

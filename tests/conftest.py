@@ -63,6 +63,6 @@ def record_metric(name, **values):
     try:
         os.makedirs(d, exist_ok=True)
         with open(os.path.join(d, "parity_metrics.jsonl"), "a") as fh:
-            fh.write(json.dumps(dict(test=name, **{k: (float(v) if np.isscalar(v) else v) for k, v in values.items()})) + "\n")
+            fh.write(json.dumps(dict(test=name, **{k: (float(v) if isinstance(v, (int, float, np.integer, np.floating)) else v) for k, v in values.items()})) + "\n")
     except OSError:
         pass

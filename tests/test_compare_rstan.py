@@ -85,7 +85,7 @@ def test_posterior_parity_32_profiles(tmp_path, L, O):
     ref = O.sample(0, batch(S, n, Nn), n, abi.default_spec(), abi.default_cfg(n_warmup=500, n_iter=1500, seed=4321))
     write_rstan_standin(tmp_path / "out", ref, Nn)
     rows, verdict = CR.compare(str(tmp_path / "in"), str(tmp_path / "out"), Nn=Nn, n_warmup=500, n_sample=1000, seed=77,
-                               rhat_target=1.01, max_extend=4)
+                               rhat_target=1.01, max_extend=12)
     print(verdict)
     assert verdict["tests"] == 1920
     assert verdict["rhat_max_gpu"] < 1.01, verdict

@@ -102,7 +102,7 @@ def test_run_until_converged(L, O):
     rh0 = np.nanmax(plain["summary"][:, :15, 9], axis=1)
     target = float(np.sort(rh0)[n // 2])           # half of the profiles are above the target after the plain run
     cfg = abi.default_cfg(**base)
-    cfg.rhat_target, cfg.max_extend = target, 3
+    cfg.rhat_target, cfg.max_extend, cfg.extend_iter = target, 3, 40
     out = L.sample(0, b, n, spec, cfg)
     ne = out["n_extend"]
     rh = np.nanmax(out["summary"][:, :15, 9], axis=1)
@@ -114,15 +114,17 @@ def test_run_until_converged(L, O):
     same = ne == 0
     np.testing.assert_array_equal(out["draws"][same], plain["draws"][same])
     np.testing.assert_array_equal(out["summary"][same], plain["summary"][same])
-    # a continued profile: its returned draws are every (1 + e)-th draw of (plain run ++ explicit continuation), and its
+    # a continued profile: its returned draws are thinned evenly out of (plain run ++ explicit continuation), and its
     # summary is the summary of all of them
     j = int(np.argmax(ne))
     e = int(ne[j])
     keep = []
-    cfg2 = L.continuation_cfg(abi.default_cfg(**base), plain, n_more=100 * e, iters_done=250, keep=keep)
+    cfg2 = L.continuation_cfg(abi.default_cfg(**base), plain, n_more=40 * e, iters_done=250, keep=keep)
     cont = L.sample(0, b, n, spec, cfg2)
     allj = np.concatenate([plain["draws"][j], cont["draws"][j]], axis=0)
-    np.testing.assert_array_equal(out["draws"][j], allj[e::e + 1])
+    total = 100 + 40 * e
+    rows = ((np.arange(100) + 1) * total) // 100 - 1
+    np.testing.assert_array_equal(out["draws"][j], allj[rows])
     np.testing.assert_allclose(out["summary"][j], O.summary(allj), rtol=1e-9, atol=1e-12)
     np.testing.assert_array_equal(out["last_q"][j], cont["last_q"][j])
     # leapfrog counts accumulate over the rounds

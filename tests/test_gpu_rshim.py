@@ -39,7 +39,7 @@ def test_shim_batch_progress_interrupt_pipeline(tmp_path, L):
     for a, b, c, rh in means:   # synthData.R truth (1000, 2000, 300), 5 % priors
         assert abs(float(a) - 1000) < 30 and abs(float(b) - 2000) < 120 and abs(float(c) - 300) < 30 and float(rh) < 1.2
     # 2. progress lines in rstan's format; the Shiny scraper's arithmetic on the last line gives ~100 %
-    lines = re.findall(r"Chain (\d+): Iteration:\s+(\d+) / (\d+) \[\s*(\d+)%\]\s+\((Warmup|Sampling|Extending)\)", out.split("INTERRUPT")[0])
+    lines = re.findall(r"Chain (\d+): Iteration:\s+(\d+) / (\d+) \[\s*(\d+)%\]\s+\((Warmup|Sampling|Extending)\)", out.split("BATCH draws_len")[0])
     assert len(lines) >= 2
     chain, it, n_iter, pct, _ = lines[-1]
     assert int(n_iter) == 200 and ((int(chain) - 1) * 100 + int(pct)) / 4 >= 99
