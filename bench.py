@@ -15,9 +15,11 @@ barrier and the max-over-ranks timing.
              the CPU oracle (Stan's algorithm, analytic gradient — NOT rstan, which cannot run here:
              BASELINE.md §3) on a bounded sample of the same workload, all host cores; its TIMING build
              (-O3, AVX2 + FMA: oracle/Makefile), not the separately-rounded parity build.
-  quality    every profile is sampled until its largest split R-hat is below 1.01 (north_star): the profiles still
-             above it after the configured iterations are continued on the device (rhat_target / max_extend); the
-             cost of those rounds is inside `value` and `e2e`, and `fixed_length` gives the figure without them.
+  value/e2e  the fixed-length workload BASELINE configs[2] names (500 + 1000 iterations), the same work the CPU arm does.
+  until_converged
+             north_star's "sampled to R-hat < 1.01": the same fit with rhat_target = 1.01 — the profiles still above it
+             after the configured iterations are continued on the device (rhat_target / max_extend / extend_iter) and
+             re-summarised; one extra timed step, reported next to the headline with its own R-hat figures.
   inlib      (N > 1) the product's own multi-GPU path: rank 0 alone hands all N x profiles to ONE foct_sample()
              call with devices = 0..N-1 (one host thread per GPU inside the library) while the other ranks wait.
   c5         (N = 8, or --c5) BASELINE configs[4]: 100,000 profiles x 4 chains through that same call.
@@ -184,7 +186,6 @@ def workload_config(args, n):
                         f"warmup {args.n_warmup} + {args.n_iter - args.n_warmup} draws (BASELINE configs[2])",
             "profiles_per_gpu": n, "chains": 4, "Nn": args.nn, "N": 481, "n_warmup": args.n_warmup,
             "n_iter": args.n_iter, "adapt_delta": 0.8, "max_treedepth": 10,
-            "rhat_target": args.rhat_target, "max_extend": args.max_extend,
             "l2": "flushed between steps (256 MiB memset)", "parallelism": "independent profile shards, no collective"}
 
 
@@ -244,7 +245,7 @@ def main():
     import ctypes as C
     dev_arr = (C.c_int * 1)(local_rank)
 
-    def make_cfg(extend=True):
+    def make_cfg(extend=False):
         c = abi.default_cfg(n_warmup=args.n_warmup, n_iter=args.n_iter, seed=args.seed, chains=chains)
         c.n_devices = 1
         c.devices = C.cast(dev_arr, C.POINTER(C.c_int))
@@ -304,14 +305,17 @@ def main():
     value = ess_all / T_max
     draws_per_s = world * n * chains * n_post * args.steps / T_max
 
-    # ---------------- the same without the run-until-converged rounds (what round 1 measured)
-    fixed = None
+    # ---------------- the same fit run until every profile is below the R-hat target (north_star), one timed step
+    conv = None
     if args.rhat_target > 0:
-        F = timed_plan(make_cfg(False), 1, 1, False)
+        F = timed_plan(make_cfg(True), 1, 1, False)
         rhf = np.nanmax(F["out"]["summary"][:, : args.nn + 5, 9], axis=1)
-        mxf, smf = shard.aggregate([float(np.sum(F["step_ms"])) * 1e-3], [F["ess"], float((rhf < 1.01).sum())], dist_or_none)
-        fixed = {"value": float(smf[0]) / float(mxf[0]), "unit": UNIT, "ms_per_step": 1e3 * float(mxf[0]),
-                 "rhat_max": float(np.nanmax(rhf)), "profiles_below_1.01": float(smf[1]) / (world * n)}
+        mxf, smf = shard.aggregate([float(np.sum(F["step_ms"])) * 1e-3, float(np.nanmax(rhf))],
+                                   [F["ess"], float((rhf < args.rhat_target).sum()), F["extended"], F["leap"]], dist_or_none)
+        conv = {"value": float(smf[0]) / float(mxf[0]), "unit": UNIT, "ms_per_step": 1e3 * float(mxf[0]),
+                "rhat_target": args.rhat_target, "max_extend": args.max_extend, "rhat_max": float(mxf[1]),
+                "profiles_below_target": float(smf[1]) / (world * n), "profiles_continued": float(smf[2]) / world,
+                "grad_per_s": float(smf[3]) / float(mxf[0]), "gpu_launches": int(F["launches"])}
 
     # ---------------- e2e: host buffers through foct_sample (H2D + D2H inside the timed region)
     e2e = e2e_draws = None
@@ -365,7 +369,7 @@ def main():
             if run_c5:
                 n5 = args.c5_profiles
                 _, b5 = make_batch(n5, 0, args.nn)
-                c5cfg = make_cfg()
+                c5cfg = make_cfg(True)   # north_star: sampled to R-hat < 1.01
                 t0 = time.perf_counter()
                 o5 = L.sample(abi.FOCT_EXPGP, b5, n5, spec, c5cfg, draws=False, summary=True, devices=devs)
                 T5 = time.perf_counter() - t0
@@ -421,7 +425,7 @@ def main():
                         "profiles_below_1.01": conv_all / (world * n),
                         "profiles_continued_per_step": ext_all / (world * args.steps),
                         "mean_min_bulk_ess_per_profile": ess_all / (world * n * args.steps)},
-            "fixed_length": fixed,
+            "until_converged": conv,
             "clocks": clk, "e2e": e2e, "e2e_with_draws": e2e_draws, "gpu_launches": int(R["launches"]),
             "wall_s_timed_region": t_wall,
         }

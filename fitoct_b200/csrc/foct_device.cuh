@@ -81,7 +81,13 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
   unsigned long long a = (((unsigned long long)hi << 32) | lo) >> 11;
   return ((double)a + 0.5) * 0x1.0p-53;
 }
+// (one copy of log / cos / sqrt per kernel instead of one per call site when FOCT_NORMAL_NOINLINE: the sampling kernels are
+// sensitive to their code size, see foct_nuts2.cuh)
+#ifdef FOCT_NORMAL_NOINLINE
+static __device__ __noinline__ double normal_from(const uint32_t (&r)[4]) {
+#else
 __device__ __forceinline__ double normal_from(const uint32_t (&r)[4]) {
+#endif
   double u0 = u53(r[0], r[1]), u1 = u53(r[2], r[3]);
   return sqrt(-2.0 * log(u0)) * cos(6.283185307179586476925286766559 * u1);
 }
@@ -281,12 +287,14 @@ struct Dims {
 // Raw sums go to acc[] (theta2 / theta3 factors are applied once, after the reduction).
 // W = 32: point u of the iteration sits one pass block further (pp + u * block); W = 16 (half-warp lane groups, pp
 // carries the lane index inside the group): the points are the two 16-point halves of consecutive 32-point blocks.
-// GB: the basis rows are not in the staged block (which then holds cx | y | w only) but read through L1 from `pg`, a
-// blob in global memory that every profile of the batch shares (same depth grid => same basis).
+// GB != 0: the basis rows are not in the staged block (which then holds cx | y | w only) because every profile of the batch
+// shares them (same depth grid => same basis).  GB = 1: read through L1 from `pg`, a whole blob in global
+// memory (rows cx | y | w | B_0.. per block).  GB = 2: `pg` is a copy of the basis rows alone (NN rows per block) in shared
+// memory that the sub-CTAs of one CTA share (nuts2_kernel).
 #ifndef FOCT_PAIR_LDS128
 #define FOCT_PAIR_LDS128 1
 #endif
-template <int NN, int MOD, int KP, int ZI, int U, int W = 32, bool GB = false>
+template <int NN, int MOD, int KP, int ZI, int U, int W = 32, int GB = 0>
 __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, double th1, double th2, double th3, double r3,
                                              const double (&yg)[NN > 0 ? NN : 1], double (&acc)[KP],
                                              const double* __restrict__ pg = nullptr) {
@@ -295,6 +303,7 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
   const double* __restrict__ pp = pp0;
 #define FOCT_PT(u) (W == 32 ? (u) * SROWS * 32 : ((u) >> 1) * SROWS * 32 + ((u) & 1) * 16)
 #define FOCT_PTG(u) (W == 32 ? (u) * (3 + NN) * 32 : ((u) >> 1) * (3 + NN) * 32 + ((u) & 1) * 16)
+  static_assert(GB != 2 || (W == 16 && FOCT_PAIR_LDS128), "the shared-memory basis copy is read by the half-warp point-pair path only");
   double b[U][NN > 0 ? NN : 1];
   double dl0[U], dl1[U], s[U], cx[U], y[U], ws[U], r[U], t[U];
 #pragma unroll
@@ -308,8 +317,9 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
     for (int k = 0; k < NN; ++k) {
 #pragma unroll
       for (int v = 0; v < U / 2; ++v) {
-        const double2 bb = GB ? __ldg(reinterpret_cast<const double2*>(pg + v * (3 + NN) * 32 + (3 + k) * 32))
-                              : *reinterpret_cast<const double2*>(pp + v * SROWS * 32 + (3 + k) * 32);
+        const double2 bb = GB == 1 ? __ldg(reinterpret_cast<const double2*>(pg + v * (3 + NN) * 32 + (3 + k) * 32))
+                           : GB == 2 ? *reinterpret_cast<const double2*>(pg + v * NN * 32 + k * 32)
+                                     : *reinterpret_cast<const double2*>(pp + v * SROWS * 32 + (3 + k) * 32);
         b[2 * v][k] = bb.x; b[2 * v + 1][k] = bb.y;
         if (k & 1) { dl1[2 * v] = fma(bb.x, yg[k], dl1[2 * v]); dl1[2 * v + 1] = fma(bb.y, yg[k], dl1[2 * v + 1]); }
         else { dl0[2 * v] = fma(bb.x, yg[k], dl0[2 * v]); dl0[2 * v + 1] = fma(bb.y, yg[k], dl0[2 * v + 1]); }
@@ -458,7 +468,7 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
 // in flight per warp (the fp64 pipe was latency-, not throughput-bound with one: profiles/r1_*v1*).
 // W = 32: one chain per warp.  W = 16: one chain per half-warp — `lane` is then the index inside the half, both halves
 // must call together (full-mask shuffles of width 16) and walk the same profile, so every LDS is a 16-word broadcast.
-template <int NN, int MOD, int W = 32, bool GB = false>
+template <int NN, int MOD, int W = 32, int GB = 0>
 __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, const DevProblem& P, const DevSpec& S,
                                                double qd, int lane, const double* __restrict__ gbasis = nullptr) {
   static_assert(W == 32 || Dims<NN>::D <= 16, "a half-warp holds at most 16 components");
@@ -543,7 +553,7 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
   if (!P.prior_PD) {
     const double r3 = frcp(th3);  // (a full division drags its exponent-range slow path into every leaf)
     constexpr int ROWS = GB ? 3 : 3 + NN;     // rows of a staged block
-    constexpr int GROWS = 3 + NN;             // rows of a block of the shared (global) blob
+    constexpr int GROWS = GB == 2 ? NN : 3 + NN;  // rows of a block of the shared basis (whole blob in global / basis rows in smem)
     // (half-warp groups with 128-bit loads: lane l owns the neighbouring points 2l, 2l+1 of each block)
     const int lane_off = (W == 16 && FOCT_PAIR_LDS128) ? 2 * lane : lane;
     const double* pp = blob + lane_off;
@@ -616,9 +626,9 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
 // Stage one profile blob (contiguous in global memory) into shared memory with a TMA bulk copy
 // (cp.async.bulk, SASS UBLKCP) completed on an mbarrier.  Called by all threads of the CTA.
 __device__ __forceinline__ void stage_blob_tma(double* smem_dst, const double* gsrc, uint32_t bytes, uint64_t* mbar,
-                                               uint32_t& phase) {
+                                               uint32_t& phase, bool leader) {
   const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
-  if (threadIdx.x == 0) {
+  if (leader) {
     const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(bytes) : "memory");
     // chunks of <= 64 KB keep every copy well inside any per-instruction limit
@@ -649,9 +659,9 @@ __device__ __forceinline__ void stage_blob_tma(double* smem_dst, const double* g
 // Stage only the first `rows` rows (cx | y | w) of every 32-point block of a blob: one bulk copy per block, all
 // completing on the same mbarrier.  Used when the basis rows are shared by the whole batch and read through L1.
 __device__ __forceinline__ void stage_rows_tma(double* smem_dst, const double* gsrc, int nblocks, int src_rows, int rows,
-                                               uint64_t* mbar, uint32_t& phase) {
+                                               uint64_t* mbar, uint32_t& phase, bool leader) {
   const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
-  if (threadIdx.x == 0) {
+  if (leader) {
     const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(smem_dst);
     const uint32_t blk = (uint32_t)rows * 32u * (uint32_t)sizeof(double);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(blk * (uint32_t)nblocks) : "memory");

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(128) logp_kernel(const LogpParams K) {
   uint32_t phase = 0;
   for (int j = blockIdx.x; j < K.n_problems; j += gridDim.x) {
     if (threadIdx.x == 0) s_prob = K.probs[j];
-    stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase);
+    stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase, threadIdx.x == 0);
     __syncthreads();
     if constexpr (D <= 16) {
       if (K.width == 16) {
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(32) map_bfgs_kernel(const MapParams K) {
   uint32_t phase = 0;
   for (int j = blockIdx.x; j < K.n_problems; j += gridDim.x) {
     if (lane == 0) s_prob = K.probs[j];
-    stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase);
+    stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase, threadIdx.x == 0);
     __syncthreads();
     const DevProblem& P = s_prob;
     // objective f = -(lp - Jacobian); jac_d = 1 on the log-lambda / log-sigma lanes
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(32) vb_kernel(const VbParams K) {
   uint32_t phase_bit = 0;
   for (int j = blockIdx.x; j < K.n_problems; j += gridDim.x) {
     if (lane == 0) s_prob = K.probs[j];
-    stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase_bit);
+    stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase_bit, threadIdx.x == 0);
     __syncthreads();
     const DevProblem& P = s_prob;
     Rng rng;
@@ -374,17 +374,22 @@ static cudaError_t launch_map(int mod, int grid, size_t smem, cudaStream_t st, c
   return cudaGetLastError();
 }
 
-// Nn <= 11 (D <= 16) and the mono-exponential run two chains per warp (foct_nuts2.cuh); FOCT_NO_PAIR=1 forces the
-// one-chain-per-warp kernel for A/B runs.
+// Two sampling kernels.  Nn <= 11 (D <= 16) and the mono-exponential can run two chains per warp (foct_nuts2.cuh): more
+// gradients per second on a full GPU (3.0e8 against 2.3e8 at Nn = 10), but a chain advances at 60-70 % of the speed it has
+// with a warp of its own.  So the one-chain-per-warp kernel serves the batches that fit the GPU in one go (measured, B200,
+// 500 + 1000 iterations: 1 profile 1.44 s against 1.98 s, 148 profiles 1.70 against 2.54 s, 444 profiles 2.21 against
+// 3.02 s; profiles/r2_kernel_experiments.txt) and the continuation rounds of a few unconverged profiles.
+// FOCT_NO_PAIR=1 / FOCT_FORCE_PAIR=1 pin the choice (A/B runs, tests of the time slicing on small batches).
 template <int NN>
-static bool use_pair() {
-  if (Dims<NN>::D > 16) return false;
-  static const bool off = std::getenv("FOCT_NO_PAIR") != nullptr;
-  return !off;
+static bool pair_capable() { return Dims<NN>::D <= 16; }
+static int pair_env() {
+  if (std::getenv("FOCT_NO_PAIR")) return 0;
+  if (std::getenv("FOCT_FORCE_PAIR")) return 1;
+  return -1;
 }
 template <int NN>
-static int nuts_block(int chains) {
-  if (use_pair<NN>()) return 32 * ((std::min(chains, FOCT_PAIR_CTA_CHAINS) + 1) / 2);
+static int nuts_block(int chains, bool pair) {
+  if (pair) return 32 * ((std::min(chains, FOCT_PAIR_CTA_CHAINS) + 1) / 2);
   return 32 * std::min(chains, FOCT_CTA_CHAINS);
 }
 
@@ -392,15 +397,19 @@ template <int NN, int MOD>
 static cudaError_t launch_nuts_mod(int grid, int block, size_t smem, cudaStream_t st, const SamplerParams& K) {
   cudaError_t e;
   if constexpr (Dims<NN>::D <= 16) {
-    if (use_pair<NN>()) {
-      if (K.shared_basis) {
-        e = cudaFuncSetAttribute(nuts2_kernel<NN, MOD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (K.pair_kernel) {
+      if (K.shared_basis == 2) {
+        e = cudaFuncSetAttribute(nuts2_kernel<NN, MOD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        nuts2_kernel<NN, MOD, true><<<grid, block, smem, st>>>(K);
+        nuts2_kernel<NN, MOD, 2><<<grid, block, smem, st>>>(K);
+      } else if (K.shared_basis == 1) {
+        e = cudaFuncSetAttribute(nuts2_kernel<NN, MOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        nuts2_kernel<NN, MOD, 1><<<grid, block, smem, st>>>(K);
       } else {
-        e = cudaFuncSetAttribute(nuts2_kernel<NN, MOD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(nuts2_kernel<NN, MOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        nuts2_kernel<NN, MOD, false><<<grid, block, smem, st>>>(K);
+        nuts2_kernel<NN, MOD, 0><<<grid, block, smem, st>>>(K);
       }
       return cudaGetLastError();
     }
@@ -448,31 +457,68 @@ static cudaError_t occupancy_of(KernelT kernel, int block, size_t smem, int* blo
 // shared_basis in: the batch has one depth grid; out: whether this kernel reads the basis from global memory (then `smem`
 // must be the size of the cx | y | w part only: the caller passes both sizes).
 template <int NN>
-static cudaError_t nuts_occupancy(int mod, int chains, size_t smem_full, size_t smem_rows, int* shared_basis, size_t* smem,
-                                  int* block, int* blocks_per_sm, int* cta_chains, int* regs) {
-  *block = nuts_block<NN>(chains);
+static cudaError_t nuts_occupancy(int mod, int chains, long long n_items, int n_sm, size_t smem_full, size_t smem_rows,
+                                  int* shared_basis, size_t* smem, int* block, int* blocks_per_sm, int* cta_chains, int* regs,
+                                  size_t* slice_bytes, int* pair_kernel, int* subs) {
   *smem = smem_full;
+  *subs = 1;  // independent two-warp sub-CTAs per CTA, each working through items (nuts2_kernel, basis mode 2)
+  *slice_bytes = 0;  // per work item: saved state of a CTA's warps (time slicing); 0 = this kernel runs items to completion
+  *pair_kernel = 0;
+  *cta_chains = FOCT_CTA_CHAINS;
+  // geometry of the one-chain-per-warp kernel: what a batch must exceed to be worth two chains per warp
+  *block = nuts_block<NN>(chains, false);
+  int one_bpsm = 0, one_regs = 0;
+  cudaError_t e = mod == 0 ? occupancy_of(nuts_kernel<NN, 0>, *block, *smem, &one_bpsm, &one_regs)
+                           : occupancy_of(nuts_kernel<NN, 1>, *block, *smem, &one_bpsm, &one_regs);
+  if (e != cudaSuccess) {
+    // (a profile too long for its blob to be staged whole can still run on the shared-basis kernel)
+    if (!pair_capable<NN>()) return e;
+    cudaGetLastError();
+    one_bpsm = 0;
+  }
   if constexpr (Dims<NN>::D <= 16) {
-    if (use_pair<NN>()) {
+    const int env = pair_env();
+    const long long groups = (chains + FOCT_CTA_CHAINS - 1) / FOCT_CTA_CHAINS;
+    // (measured crossover: 600 profiles still finish sooner in two ragged waves of the one-chain kernel, 3.45 s against 3.65 s)
+    const bool pair = one_bpsm < 1 || (env >= 0 ? env == 1 : 10 * n_items * groups > 16 * (long long)n_sm * one_bpsm);
+    if (pair) {
+      *pair_kernel = 1;
+      *block = nuts_block<NN>(chains, true);
       *cta_chains = FOCT_PAIR_CTA_CHAINS;
-      // measured (profiles/r2_kernel_experiments.txt): with the basis read through L1 six CTAs fit an SM instead of four.
-      // With 64-bit loads that bought nothing (2.58e8 vs 2.61e8 gradients/s at full waves: twice the L1 requests of the
-      // staged variant's LDS); with one 128-bit load per row and point pair it is 3.06e8.  FOCT_NO_SHARED_BASIS=1: A/B.
-      static const bool use_gb = std::getenv("FOCT_NO_SHARED_BASIS") == nullptr;
+      *slice_bytes = (size_t)(FOCT_PAIR_CTA_CHAINS / 2) * FOCT_PAIR_STATE_DOUBLES * 32 * sizeof(double);
+      // One depth grid for the batch = one GP basis for every profile: only cx | y | w are staged per item, and twelve
+      // warps fit an SM instead of eight.  Mode 2: the basis rows sit once per CTA in shared memory, shared by
+      // FOCT_PAIR_SUBS sub-CTAs; mode 1 (the fallback when that copy does not fit, FOCT_BASIS_MODE=1 for A/B runs): read
+      // through L1 from blob 0.  Measured in profiles/r2_kernel_experiments.txt.
+      const bool use_gb = std::getenv("FOCT_NO_SHARED_BASIS") == nullptr;  // (read per plan: tests flip it)
       if (*shared_basis && NN > 0 && use_gb) {
+        const char* bm = std::getenv("FOCT_BASIS_MODE");
+        if (!bm || std::atoi(bm) == 2) {
+          const size_t smem2 = smem_rows / 3 * NN + (size_t)FOCT_PAIR_SUBS * smem_rows;
+          int b2 = 0, r2 = 0;
+          const int block2 = *block * FOCT_PAIR_SUBS;
+          cudaError_t e2 = mod == 0 ? occupancy_of(nuts2_kernel<NN, 0, 2>, block2, smem2, &b2, &r2)
+                                    : occupancy_of(nuts2_kernel<NN, 1, 2>, block2, smem2, &b2, &r2);
+          if (e2 == cudaSuccess && b2 >= 1) {
+            *shared_basis = 2; *smem = smem2; *block = block2; *blocks_per_sm = b2; *regs = r2; *subs = FOCT_PAIR_SUBS;
+            return cudaSuccess;
+          }
+          cudaGetLastError();
+        }
+        *shared_basis = 1;
         *smem = smem_rows;
-        return mod == 0 ? occupancy_of(nuts2_kernel<NN, 0, true>, *block, *smem, blocks_per_sm, regs)
-                        : occupancy_of(nuts2_kernel<NN, 1, true>, *block, *smem, blocks_per_sm, regs);
+        return mod == 0 ? occupancy_of(nuts2_kernel<NN, 0, 1>, *block, *smem, blocks_per_sm, regs)
+                        : occupancy_of(nuts2_kernel<NN, 1, 1>, *block, *smem, blocks_per_sm, regs);
       }
       *shared_basis = 0;
-      return mod == 0 ? occupancy_of(nuts2_kernel<NN, 0, false>, *block, *smem, blocks_per_sm, regs)
-                      : occupancy_of(nuts2_kernel<NN, 1, false>, *block, *smem, blocks_per_sm, regs);
+      return mod == 0 ? occupancy_of(nuts2_kernel<NN, 0, 0>, *block, *smem, blocks_per_sm, regs)
+                      : occupancy_of(nuts2_kernel<NN, 1, 0>, *block, *smem, blocks_per_sm, regs);
     }
   }
   *shared_basis = 0;
-  *cta_chains = FOCT_CTA_CHAINS;
-  return mod == 0 ? occupancy_of(nuts_kernel<NN, 0>, *block, *smem, blocks_per_sm, regs)
-                  : occupancy_of(nuts_kernel<NN, 1>, *block, *smem, blocks_per_sm, regs);
+  *blocks_per_sm = one_bpsm;
+  *regs = one_regs;
+  return cudaSuccess;
 }
 
 #define FOCT_CAT_(a, b) a##b

@@ -522,6 +522,17 @@ struct foct_plan {
   bool cancelled = false;
   int shared_basis = 0;
   int launches = 0;  // kernels of the last run
+  // time slicing of the work items (nuts2_kernel): saved chain state, ring queue, per-warp done flags
+  double* d_slice_state = nullptr;
+  unsigned long long* d_slice_queue = nullptr;
+  int* d_slice_done = nullptr;
+  int slice_ticks = 0;
+  // which sampling kernel (foct_inst.cu: two chains per warp for batches larger than the GPU holds at once), and the
+  // geometry of the one-chain-per-warp kernel for continuation rounds of few profiles
+  int pair_kernel = 0;
+  int alt_block = 0, alt_blocks_per_sm = 0;
+  int subs = 1;  // two-warp sub-CTAs per CTA (nuts2_kernel with the basis copy in shared memory): items a CTA works on at once
+  size_t alt_smem = 0;
 };
 
 // Copy the post-warm-up draws of the selected profiles into their extension blocks.
@@ -569,6 +580,7 @@ static void plan_free(foct_plan* p) {
   pool_free(p->d_blobs); pool_free(p->d_draws); pool_free(p->d_sparams); pool_free(p->d_summary);
   pool_free(p->d_stepsize); pool_free(p->d_invm); pool_free(p->d_nleap); pool_free(p->d_ndiv); pool_free(p->d_init);
   pool_free(p->d_probs); pool_free(p->d_counter); pool_free(p->d_order);
+  pool_free(p->d_slice_state); pool_free(p->d_slice_queue); pool_free(p->d_slice_done);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   if (p->ev2) cudaEventDestroy(p->ev2);
@@ -877,7 +889,7 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
   CUP(pool_malloc(&p->d_invm, pc * p->D * sizeof(double)));
   CUP(pool_malloc(&p->d_nleap, pc * 2 * sizeof(double)));
   CUP(pool_malloc(&p->d_ndiv, pc * sizeof(double)));
-  CUP(pool_malloc(&p->d_counter, sizeof(int)));
+  CUP(pool_malloc(&p->d_counter, 4 * sizeof(int)));  // work counter; with time slicing: tickets | pushes | finished
   if (cfg->init_mode == 2) {
     CUP(pool_malloc(&p->d_init, pc * p->D * sizeof(double)));
     CUP(cudaMemcpy(p->d_init, init_slice, pc * p->D * sizeof(double), cudaMemcpyHostToDevice));
@@ -901,22 +913,48 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
     shared_basis = P[j].N == P[0].N && P[j].gridType == P[0].gridType && P[j].rho == P[0].rho &&
                    std::memcmp(P[j].x, P[0].x, (size_t)P[0].N * sizeof(double)) == 0;
   int cta_chains = FOCT_CTA_CHAINS;
-  CUP(p->inst->nuts_occupancy(spec->modulation, cfg->chains, p->blob_stride * sizeof(double), (size_t)3 * p->npad * sizeof(double),
-                              &shared_basis, &p->smem, &p->block, &p->blocks_per_sm, &cta_chains, &p->regs));
-  p->shared_basis = shared_basis;
-  if (p->blocks_per_sm < 1) { plan_free(p); return fail(FOCT_EINVAL, "sampling kernel does not fit an SM (smem %zu B)", p->smem); }
+  size_t slice_bytes = 0;
   int n_sm = 0;  // (cudaGetDeviceProperties costs milliseconds; one attribute does not)
   CUP(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+  CUP(p->inst->nuts_occupancy(spec->modulation, cfg->chains, n, n_sm, p->blob_stride * sizeof(double), (size_t)3 * p->npad * sizeof(double),
+                              &shared_basis, &p->smem, &p->block, &p->blocks_per_sm, &cta_chains, &p->regs, &slice_bytes, &p->pair_kernel, &p->subs));
+  p->shared_basis = shared_basis;
+  if (p->blocks_per_sm < 1) { plan_free(p); return fail(FOCT_EINVAL, "sampling kernel does not fit an SM (smem %zu B)", p->smem); }
+  if (p->pair_kernel) {
+    // (n_items = 0: the geometry of the one-chain-per-warp kernel, if the blob fits an SM at all)
+    int sb = 0, cc = 0, rg = 0, pk = 0, su = 0;
+    size_t sl = 0;
+    if (p->inst->nuts_occupancy(spec->modulation, cfg->chains, 0, n_sm, p->blob_stride * sizeof(double), (size_t)3 * p->npad * sizeof(double),
+                                &sb, &p->alt_smem, &p->alt_block, &p->alt_blocks_per_sm, &cc, &rg, &sl, &pk, &su) != cudaSuccess || pk) {
+      cudaGetLastError();
+      p->alt_blocks_per_sm = 0;
+    }
+  }
   const int groups = (cfg->chains + cta_chains - 1) / cta_chains;
   p->groups = groups; p->n_sm = n_sm;
-  p->grid = (int)std::min<long long>((long long)n * groups, (long long)n_sm * p->blocks_per_sm);
+  p->grid = (int)std::min<long long>(((long long)n * groups + p->subs - 1) / p->subs, (long long)n_sm * p->blocks_per_sm);
+  if (const char* env = std::getenv("FOCT_MAX_GRID")) p->grid = std::max(1, std::min(p->grid, std::atoi(env)));  // tests: few CTAs
+  const long long resident = (long long)p->grid * p->subs;  // work items in flight at once
+  // More work items than resident CTAs: the CTAs share them in time slices (nuts2_kernel) instead of running each to
+  // completion, so that the last fits of the batch do not run alone.  FOCT_SLICE_TICKS=0 turns it off (A/B runs).
+  if (slice_bytes > 0 && (long long)n * groups > resident) {
+    int ticks = 4096;  // gradient evaluations per slice: ~1 % of a fit, ~50 ms; a state round trip is 160 KB per item
+    if (const char* env = std::getenv("FOCT_SLICE_TICKS")) ticks = std::atoi(env);
+    if (ticks > 0) {
+      const size_t items = (size_t)n * groups;
+      CUP(pool_malloc(&p->d_slice_state, items * slice_bytes));
+      CUP(pool_malloc(&p->d_slice_queue, items * sizeof(unsigned long long)));
+      CUP(pool_malloc(&p->d_slice_done, items * (size_t)(cta_chains / 2) * sizeof(int)));
+      p->slice_ticks = ticks;
+    }
+  }
   // Longest-processing-time-first scheduling.  Fits differ in cost by up to 4x (an unmodulated profile needs a third of
   // the leapfrogs of a strongly modulated one), and with more work items than resident CTAs the order in which the
   // persistent CTAs claim them decides how long the last ones run alone.  The Birge ratio of a mono-exponential MAP fit
   // (map_kernel on the blobs already on the device, ~0.2 ms per 1000 profiles) ranks the fits by expected cost (Spearman
   // 0.9 against the leapfrog count); the result of a fit does not depend on when it runs (per-profile Philox keys).
   tr.mark("occupancy + device properties");
-  if (kind == FOCT_EXPGP && n * groups > p->grid && !std::getenv("FOCT_NO_LPT")) {
+  if (kind == FOCT_EXPGP && (long long)n * groups > resident && !std::getenv("FOCT_NO_LPT")) {
     double *d_th = nullptr, *d_br = nullptr;
     int* d_st = nullptr;
     CUP(pool_malloc(&d_th, (size_t)n * 3 * sizeof(double)));
@@ -970,6 +1008,9 @@ static void plan_params(const foct_plan* p, unsigned long long seed, SamplerPara
   K.n_leapfrog = p->d_nleap; K.n_divergent = p->d_ndiv; K.work_counter = p->d_counter; K.order = p->d_order;
   K.invm_init = p->d_invm_init; K.eps_init = p->d_eps_init; K.last_q = p->d_lastq; K.it_offset = c.iter_offset;
   K.progress = p->d_progress; K.cancel = p->d_cancel; K.shared_basis = p->shared_basis;
+  K.slice_state = p->d_slice_state; K.slice_queue = p->d_slice_queue; K.slice_done = p->d_slice_done;
+  K.slice_ctl = reinterpret_cast<unsigned*>(p->d_counter); K.slice_ticks = p->slice_ticks;
+  K.pair_kernel = p->pair_kernel;
 }
 
 extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
@@ -978,7 +1019,8 @@ extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
   SamplerParams K;
   plan_params(p, seed, K);
   const foct_sampler_cfg& c = p->cfg;
-  CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), p->stream));
+  CU(cudaMemsetAsync(p->d_counter, 0, 4 * sizeof(int), p->stream));
+  if (p->d_slice_queue) CU(cudaMemsetAsync(p->d_slice_queue, 0xff, (size_t)p->n * p->groups * sizeof(unsigned long long), p->stream));
   CU(cudaMemsetAsync(p->d_progress, 0, sizeof(unsigned long long), p->stream));
   CU(cudaMemsetAsync(p->d_cancel, 0, sizeof(int), p->stream));
   p->cancelled = false;
@@ -1074,12 +1116,18 @@ static int plan_extend(foct_plan* p) {
     K.it_offset = c.iter_offset + c.n_iter + (e - 1) * ext;
     K.draws = p->d_xdraws; K.sparams = p->d_xsparams; K.slot_of = p->d_slot_of;
     K.save_stride = p->x_cap; K.save_offset = n_post + (e - 1) * ext; K.accumulate = 1;
-    CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), p->stream));
+    CU(cudaMemsetAsync(p->d_counter, 0, 4 * sizeof(int), p->stream));
+    if ((long long)m * p->groups <= (long long)p->n_sm * p->blocks_per_sm * p->subs) K.slice_state = nullptr;  // every item has a CTA
+    else if (p->d_slice_queue) CU(cudaMemsetAsync(p->d_slice_queue, 0xff, (size_t)m * p->groups * sizeof(unsigned long long), p->stream));
     cudaEvent_t a0, a1, a2;
     CU(cudaEventCreate(&a0)); CU(cudaEventCreate(&a1)); CU(cudaEventCreate(&a2));
     CU(cudaEventRecord(a0, p->stream));
-    const int grid = (int)std::min<long long>((long long)m * p->groups, (long long)p->n_sm * p->blocks_per_sm);
-    CU(p->inst->launch_nuts(p->spec.modulation, grid, p->block, p->smem, p->stream, K));
+    // few profiles left: a warp per chain (a chain advances ~1.5x faster than with half a warp, and the GPU is not full)
+    const bool one_chain = p->pair_kernel && p->alt_blocks_per_sm > 0 && (long long)m * p->groups <= (long long)p->n_sm * p->alt_blocks_per_sm;
+    if (one_chain) { K.pair_kernel = 0; K.shared_basis = 0; K.slice_state = nullptr; }
+    const int bpsm = one_chain ? p->alt_blocks_per_sm : p->blocks_per_sm, subs = one_chain ? 1 : p->subs;
+    const int grid = (int)std::min<long long>(((long long)m * p->groups + subs - 1) / subs, (long long)p->n_sm * bpsm);
+    CU(p->inst->launch_nuts(p->spec.modulation, grid, one_chain ? p->alt_block : p->block, one_chain ? p->alt_smem : p->smem, p->stream, K));
     CU(cudaEventRecord(a1, p->stream));
     CU(launch_summary(p->d_xdraws, m, p->x_cap, 0, n_post + e * ext, C, P_out, p->d_summary, p->stream, p->d_sel_slots, p->d_sel));
     CU(cudaEventRecord(a2, p->stream));

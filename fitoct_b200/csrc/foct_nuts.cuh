@@ -46,9 +46,16 @@ struct SamplerParams {
   const int* slot_of;       // [..] draw block of profile j (nullptr: j)
   // ---- progress and cancellation (foct_plan_query / foct_plan_cancel / foct_sample_cb; SURVEY §8b: R polls and calls
   //      R_CheckUserInterrupt between polls, server.R:457-472 scrapes the progress)
-  int shared_basis;              // 1: every profile has the same depth grid; the basis rows are read through L1 from blob 0
+  int shared_basis;              // every profile has the same depth grid: 1 = basis rows read through L1 from blob 0, 2 = from the CTA's copy in shared memory
   unsigned long long* progress;  // chain-iterations completed so far, or nullptr
   const int* cancel;             // != 0: every chain stops at its next iteration boundary, or nullptr
+  // ---- time slicing of the work items (nuts2_kernel; all nullptr / 0: off)
+  double* slice_state;              // [n_items][warps per CTA][FOCT_PAIR_STATE_DOUBLES][32]
+  int* slice_done;                  // [n_items][warps per CTA] != 0: the chains of this warp have finished
+  unsigned long long* slice_queue;  // [n_items] ring of suspended items, (ticket << 32 | item)
+  unsigned* slice_ctl;              // tickets handed out | pushes | items finished
+  int slice_ticks;                  // gradient evaluations per slice
+  int pair_kernel;                  // host: 1 = nuts2_kernel (two chains per warp), 0 = nuts_kernel
 };
 
 #define FOCT_PROGRESS_EVERY 8
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(32 * FOCT_CTA_CHAINS, NutsBounds<NN>::MINB) nu
     if (w >= n_items) break;
     const int j = K.order ? K.order[w / groups] : w / groups, chain = (w % groups) * FOCT_CTA_CHAINS + warp;
     if (threadIdx.x == 0) s_prob = K.probs[j];
-    stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase);
+    stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase, threadIdx.x == 0);
     __syncthreads();
     if (chain < K.chains) run_chain<NN, MOD>(K, s_prob, smem, j, chain, lane);
     __syncthreads();

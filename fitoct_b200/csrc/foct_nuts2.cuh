@@ -21,7 +21,7 @@
 
 namespace foct {
 
-enum PairMode { PM_ITER = 0, PM_DOUBLE = 1, PM_LEAF = 2, PM_EPS = 3, PM_EPS_EVAL = 4, PM_DONE = 5 };
+enum PairMode { PM_ITER = 0, PM_DOUBLE = 1, PM_LEAF = 2, PM_EPS = 3, PM_EPS_EVAL = 4, PM_DONE = 5, PM_INIT = 6 };
 
 template <int W>
 __device__ __forceinline__ bool merge_persists_w(double invM, double i_rho, double i_pbeg, double i_pend, double f_rho,
@@ -37,12 +37,28 @@ __device__ __forceinline__ bool merge_persists_w(double invM, double i_rho, doub
   return __all_sync(mask, s > 0.0);
 }
 
+// Everything a half-warp carries from one tick to the next, in the order it is saved (time slicing, see nuts2_kernel).
+#define FOCT_PAIR_DOUBLES(X)                                                                                              \
+  X(q) X(g) X(V) X(c2) X(invM) X(eps) X(w_n) X(w_mean) X(w_m2) X(da_mu) X(da_counter) X(da_sbar) X(da_xbar) X(nlf_warm)  \
+  X(nlf_samp) X(ndiv) X(fq) X(fp) X(fg) X(bq) X(bp) X(bg) X(sq) X(sg) X(sV) X(sc2) X(sH) X(rho) X(lsw) X(u_top)          \
+  X(old_end_p) X(other_end_p) X(e_H0) X(zq) X(zp) X(zg) X(zV) X(zc2) X(eps_s) X(H0) X(sum_metro)
+#define FOCT_PAIR_INTS(X)                                                                                                 \
+  X(a_counter) X(a_wsize) X(a_next) X(depth) X(fwd_i) X(divergent_i) X(it) X(e_attempt) X(e_direction) X(e_after_window) \
+  X(e_site) X(n_leap) X(n) X(n_leaves) X(mode)
+#define FOCT_PAIR_N_DOUBLES 41
+#define FOCT_PAIR_N_INTS 15
+// doubles per lane of a saved warp: the scalars above, the ints packed two to a double, nine stack arrays
+#define FOCT_PAIR_STATE_DOUBLES (FOCT_PAIR_N_DOUBLES + (FOCT_PAIR_N_INTS + 1) / 2 + 9 * FOCT_STACK_LEVELS)
+
 // lane32 = lane in the warp; this half's chain is `chain` (>= K.chains: the half has no chain and only keeps the other
 // half company in the gradient evaluations).
-template <int NN, int MOD, bool GB>
-__device__ void run_pair(const SamplerParams& K, const DevProblem& P, const double* __restrict__ blob, int prob,
-                         int chain, int lane32) {
-  const double* __restrict__ gbasis = GB ? K.blobs : nullptr;  // blob 0: the basis every profile of the batch shares
+// Time slicing: `sv` (nullptr: off) is this warp's block of FOCT_PAIR_STATE_DOUBLES x 32 doubles in global memory.  With
+// `resume` the state is loaded from it instead of being initialised; after K.slice_ticks gradient evaluations, if other
+// work items are waiting for a CTA, the state is stored there and the function returns false (true: both chains finished).
+template <int NN, int MOD, int GB>
+__device__ bool run_pair(const SamplerParams& K, const DevProblem& P, const double* __restrict__ blob, int prob,
+                         int chain, int lane32, double* __restrict__ sv, bool resume, int n_items,
+                         const double* __restrict__ gbasis) {  // GB = 1: blob 0 (global); GB = 2: the CTA's copy of the basis rows
   using DM = Dims<NN>;
   constexpr int D = DM::D;
   constexpr int P_OUT = DM::P_OUT;
@@ -55,31 +71,9 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
   Rng rng;
   rng.seed(K.seed, P.id, chain);
   uint32_t rb[4];
-
-  // ---- initial point (MODEL_SPEC §7 init_mode)
-  double q = 0.0;
-  if (act) {
-    rng.block(0, SITE_INIT, 0, (uint32_t)lane, 0, rb);
-    if (K.init_mode == 2 && K.init && have) {
-      q = K.init[((size_t)prob * K.chains + chain) * D + lane];
-    } else if (K.init_mode == 1) {
-      q = -2.0 + 4.0 * u53(rb[0], rb[1]);
-    } else {
-      if (lane < 3) q = P.theta0[lane];
-      else if (lane < 3 + NN) q = 0.01 * normal_from(rb);
-      else if (lane == 3 + NN) q = log(0.1);
-      else q = 0.0;
-    }
-  }
-  Eval ev = warp_logp_grad<NN, MOD, W, GB>(blob, P, K.spec, q, lane, gbasis);
-  double g = ev.g, V = -ev.lp, c2 = ev.chi2;
-  double invM = 1.0;
-  FOCT_PARK double eps = K.stepsize0 > 0.0 ? K.stepsize0 : 1.0;
-  if (have && K.invm_init && act) invM = K.invm_init[((size_t)prob * K.chains + chain) * D + lane];
-  if (have && K.eps_init) eps = K.eps_init[(size_t)prob * K.chains + chain];
   const uint32_t it0 = (uint32_t)K.it_offset;
 
-  // ---- adaptation state (Stan windowed_adaptation / welford_var_estimator / stepsize_adaptation)
+  // ---- adaptation constants (Stan windowed_adaptation / welford_var_estimator / stepsize_adaptation)
   int a_num_warmup, a_init_buffer, a_term_buffer, a_base_window;
   {
     int ib = K.init_buffer > 0 ? K.init_buffer : 75, tb = K.term_buffer > 0 ? K.term_buffer : 50;
@@ -91,20 +85,23 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
       a_num_warmup = nw; a_init_buffer = ib; a_term_buffer = tb; a_base_window = bw;
     }
   }
-  FOCT_PARK int a_counter = 0, a_wsize = a_base_window, a_next = a_init_buffer + a_base_window - 1;
-  FOCT_PARK double w_n = 0.0, w_mean = 0.0, w_m2 = 0.0;
   const double da_delta = K.adapt_delta > 0.0 ? K.adapt_delta : 0.8;
   const double da_gamma = K.gamma > 0.0 ? K.gamma : 0.05, da_kappa = K.kappa > 0.0 ? K.kappa : 0.75;
   const double da_t0 = K.t0 > 0.0 ? K.t0 : 10.0;
-  FOCT_PARK double da_mu = log(10.0 * eps), da_counter = 0.0, da_sbar = 0.0, da_xbar = 0.0;
   const int max_depth = K.max_depth > 0 ? (K.max_depth <= FOCT_STACK_LEVELS + 1 ? K.max_depth : FOCT_STACK_LEVELS + 1) : 10;
   const double log08 = log(0.8);
-  FOCT_PARK double nlf_warm = 0.0, nlf_samp = 0.0, ndiv = 0.0;
   const int n_saved = K.save_warmup ? K.n_iter : K.n_iter - K.n_warmup;
 
-  // ---- per-iteration state (parked: touched once per iteration or per doubling)
-  FOCT_PARK double fq = q, fp = 0.0, fg = g, bq = q, bp = 0.0, bg = g;
-  FOCT_PARK double sq = q, sg = g, sV = V, sc2 = c2, sH = 0.0;
+  // ---- chain state.  FOCT_PARK (volatile): touched once per iteration or per doubling, kept out of the registers
+  double q = 0.0, g = 0.0, V = 0.0, c2 = 0.0, invM = 1.0;
+  FOCT_PARK double eps = K.stepsize0 > 0.0 ? K.stepsize0 : 1.0;
+  FOCT_PARK int a_counter = 0, a_wsize = a_base_window, a_next = a_init_buffer + a_base_window - 1;
+  FOCT_PARK double w_n = 0.0, w_mean = 0.0, w_m2 = 0.0;
+  FOCT_PARK double da_mu = 0.0, da_counter = 0.0, da_sbar = 0.0, da_xbar = 0.0;
+  FOCT_PARK double nlf_warm = 0.0, nlf_samp = 0.0, ndiv = 0.0;
+  // ---- per-iteration state
+  FOCT_PARK double fq = 0.0, fp = 0.0, fg = 0.0, bq = 0.0, bp = 0.0, bg = 0.0;
+  FOCT_PARK double sq = 0.0, sg = 0.0, sV = 0.0, sc2 = 0.0, sH = 0.0;
   FOCT_PARK double rho = 0.0, lsw = 0.0, u_top = 0.0, old_end_p = 0.0, other_end_p = 0.0;
   FOCT_PARK int depth = 0, fwd_i = 1, divergent_i = 0;
   FOCT_PARK int it = 0;
@@ -113,15 +110,61 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
   FOCT_PARK uint32_t e_site = it0;
   FOCT_PARK double e_H0 = 0.0;
   // ---- state of the running subtree / integrator (live across the gradient evaluation)
-  double zq = q, zp = 0.0, zg = g, zV = V, zc2 = c2;
-  double eps_s = eps, H0 = 0.0, sum_metro = 0.0;
+  double zq = 0.0, zp = 0.0, zg = 0.0, zV = 0.0, zc2 = 0.0;
+  double eps_s = 0.0, H0 = 0.0, sum_metro = 0.0;
   int n_leap = 0;
   uint32_t n = 0, n_leaves = 1;
+  int mode = PM_DONE;
 
   // pending "init" subtrees, one slot per level (local memory; touched only at merges)
   double st_rho[FOCT_STACK_LEVELS], st_pbeg[FOCT_STACK_LEVELS], st_pend[FOCT_STACK_LEVELS];
   double st_qp[FOCT_STACK_LEVELS], st_gp[FOCT_STACK_LEVELS];
   double st_lsw[FOCT_STACK_LEVELS], st_V[FOCT_STACK_LEVELS], st_c2[FOCT_STACK_LEVELS], st_H[FOCT_STACK_LEVELS];
+
+#ifndef FOCT_TEST_NO_RESUME
+  if (resume) {
+    // (L2 loads: the block may have been written by another SM since this one last read it)
+    const double* s = sv + lane32;
+#define X(v) v = __ldcg(s); s += 32;
+    FOCT_PAIR_DOUBLES(X)
+#undef X
+    const int* si = reinterpret_cast<const int*>(sv + FOCT_PAIR_N_DOUBLES * 32) + lane32;
+#define X(v) v = __ldcg(si); si += 32;
+    FOCT_PAIR_INTS(X)
+#undef X
+    s = sv + (FOCT_PAIR_N_DOUBLES + (FOCT_PAIR_N_INTS + 1) / 2) * 32 + lane32;
+#pragma unroll 1
+    for (int k = 0; k < FOCT_STACK_LEVELS; ++k, s += 9 * 32) {
+      st_rho[k] = __ldcg(s); st_pbeg[k] = __ldcg(s + 32); st_pend[k] = __ldcg(s + 64); st_qp[k] = __ldcg(s + 96);
+      st_gp[k] = __ldcg(s + 128); st_lsw[k] = __ldcg(s + 160); st_V[k] = __ldcg(s + 192); st_c2[k] = __ldcg(s + 224);
+      st_H[k] = __ldcg(s + 256);
+    }
+  } else
+#endif
+  {
+    // ---- initial point (MODEL_SPEC §7 init_mode)
+    if (act) {
+      rng.block(0, SITE_INIT, 0, (uint32_t)lane, 0, rb);
+      if (K.init_mode == 2 && K.init && have) {
+        q = K.init[((size_t)prob * K.chains + chain) * D + lane];
+      } else if (K.init_mode == 1) {
+        q = -2.0 + 4.0 * u53(rb[0], rb[1]);
+      } else {
+        if (lane < 3) q = P.theta0[lane];
+        else if (lane < 3 + NN) q = 0.01 * normal_from(rb);
+        else if (lane == 3 + NN) q = log(0.1);
+        else q = 0.0;
+      }
+    }
+    // The gradient at the initial point is taken by the first tick of the loop below (mode PM_INIT: a leapfrog step of
+    // length zero leaves q where it is), so that the kernel carries ONE inlined copy of the sweep: with a second one for
+    // this evaluation the code outgrew the instruction cache (7.8 k instructions = 125 KB ran 4-5 % slower than 7.6 k,
+    // profiles/r2_kernel_experiments.txt).
+    if (have && K.invm_init && act) invM = K.invm_init[((size_t)prob * K.chains + chain) * D + lane];
+    if (have && K.eps_init) eps = K.eps_init[(size_t)prob * K.chains + chain];
+    zq = q; zp = 0.0; zg = 0.0; eps_s = 0.0;
+    mode = have ? PM_INIT : PM_DONE;
+  }
 
   const size_t pc = (size_t)prob * K.chains + chain;
   auto finish_chain = [&]() {
@@ -137,17 +180,36 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
     if (K.last_q && act) K.last_q[pc * D + lane] = q;
   };
 
-  int mode;
-  if (!have) {
-    mode = PM_DONE;
-  } else if (K.n_warmup > 0 && eps > 0.0 && !(eps > 1e7)) {
-    mode = PM_EPS;  // Stan's init_stepsize before the first transition
-  } else {
-    mode = PM_ITER;
-  }
-
+  int ticks = 0;
   for (;;) {
     __syncwarp();
+#ifndef FOCT_TEST_NO_SUSPEND
+    if (sv && ticks >= K.slice_ticks) {
+      // end of the slice: give the CTA up only if a work item is waiting for one
+      const unsigned head = *reinterpret_cast<const volatile unsigned*>(K.slice_ctl);
+      const unsigned pushed = *reinterpret_cast<const volatile unsigned*>(K.slice_ctl + 1);
+      if (head < (unsigned)n_items + pushed) {
+        double* s = sv + lane32;
+#define X(v) __stcg(s, (double)v); s += 32;
+        FOCT_PAIR_DOUBLES(X)
+#undef X
+        int* si = reinterpret_cast<int*>(sv + FOCT_PAIR_N_DOUBLES * 32) + lane32;
+#define X(v) __stcg(si, (int)v); si += 32;
+        FOCT_PAIR_INTS(X)
+#undef X
+        s = sv + (FOCT_PAIR_N_DOUBLES + (FOCT_PAIR_N_INTS + 1) / 2) * 32 + lane32;
+#pragma unroll 1
+        for (int k = 0; k < FOCT_STACK_LEVELS; ++k, s += 9 * 32) {
+          __stcg(s, st_rho[k]); __stcg(s + 32, st_pbeg[k]); __stcg(s + 64, st_pend[k]); __stcg(s + 96, st_qp[k]);
+          __stcg(s + 128, st_gp[k]); __stcg(s + 160, st_lsw[k]); __stcg(s + 192, st_V[k]); __stcg(s + 224, st_c2[k]);
+          __stcg(s + 256, st_H[k]);
+        }
+        return false;
+      }
+      ticks = 0;
+    }
+    ++ticks;
+#endif
     // ================================================================ PRE
     if (mode == PM_ITER && cancel_requested(K)) {
       report_progress(K, it, true, lane == 0);
@@ -190,7 +252,7 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
       mode = PM_EPS_EVAL;
     }
     __syncwarp();
-    if (__all_sync(FOCT_FULL, mode == PM_DONE)) break;
+    if (__all_sync(FOCT_FULL, mode == PM_DONE)) return true;
 
     // ================================================================ one leapfrog step, both chains together
     {
@@ -342,6 +404,11 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
           }
         }
       }
+    } else if (mode == PM_INIT) {
+      g = zg; V = zV; c2 = zc2;
+      da_mu = log(10.0 * eps);
+      mode = (K.n_warmup > 0 && eps > 0.0 && !(eps > 1e7)) ? PM_EPS   // Stan's init_stepsize before the first transition
+                                                            : PM_ITER;
     } else if (mode == PM_EPS_EVAL) {
       const double dH = e_H0 - h;
       bool finished = false;
@@ -376,6 +443,20 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
 // staged profiles, up to 255 registers per thread).  GB = true (every profile of the batch has the same depth grid, hence
 // the same basis): only cx | y | w are staged (12 KB), the basis rows come through L1 from one blob in global memory, and
 // the number of resident CTAs is set by the registers instead of the shared memory.
+//
+// TIME SLICING (K.slice_state != nullptr; the host turns it on when there are more work items than resident CTAs).  A fit
+// is ~3e5 gradient evaluations long and cannot be split, so with a plain work counter the last items of a batch run
+// alone on a mostly idle GPU: 1000 profiles on 888 resident CTAs took as long as 1250 (profiles/r2_kernel_experiments.txt).
+// Here a CTA gives its item up after K.slice_ticks gradient evaluations if another item is waiting: the warps store their
+// chain state (FOCT_PAIR_STATE_DOUBLES x 32 doubles per warp) to global memory, the item goes to the back of a ring queue
+// and the CTA takes the item at the front.  All items advance at the same rate (round robin), the GPU stays full until
+// fewer items than CTAs are left, and what is left then is the same small remainder of every long fit.  The result of
+// a fit does not depend on where or when its slices run (per-profile Philox keys; the state is saved and restored bit for
+// bit), which tests/test_gpu_parity.py checks against the unsliced kernel.
+//   ctl[0] tickets handed out; tickets < n_items are the items themselves (in K.order), ticket n_items + p is the p-th push
+//   ctl[1] pushes so far       ctl[2] items finished
+//   queue[p % n_items] = (ticket << 32 | item): a slot cannot be reused before it is consumed, because the items between
+//   two pushes into the same slot would have to be n_items + 1 different ones
 #define FOCT_PAIR_CTA_CHAINS 4
 #ifndef FOCT_PAIR_MINB
 #define FOCT_PAIR_MINB 4
@@ -383,32 +464,127 @@ __device__ void run_pair(const SamplerParams& K, const DevProblem& P, const doub
 #ifndef FOCT_PAIR_MINB_GB
 #define FOCT_PAIR_MINB_GB 6
 #endif
-template <int NN, int MOD, bool GB>
-__global__ void __launch_bounds__(16 * FOCT_PAIR_CTA_CHAINS, GB ? FOCT_PAIR_MINB_GB : FOCT_PAIR_MINB)
+// GB = 2: a CTA is FOCT_PAIR_SUBS independent sub-CTAs of two warps.  Each works through items exactly like a CTA of
+// the other variants (own staged cx | y | w rows, own mbarrier, named barrier 1 + sub); what they share is ONE copy of the
+// basis rows in shared memory, loaded once per CTA, so that the sweep's basis loads are LDS instead of LDG through L1
+// (the L1 path was the co-bottleneck of the GB = 1 kernel: doubling its loads cost 18 %, profiles/r2_kernel_experiments.txt)
+// while twelve warps still share an SM: 2 CTAs x (NN x Npad x 8 + 3 x 12 KB) = 152 KB at Nn = 10, N = 481.
+#ifndef FOCT_PAIR_SUBS
+#define FOCT_PAIR_SUBS 3
+#endif
+#ifndef FOCT_PAIR_MINB_GS
+#define FOCT_PAIR_MINB_GS 2
+#endif
+
+__device__ __forceinline__ void sub_sync(int sub, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(sub + 1), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ int sub_sync_and(int sub, int nthreads, int pred) {
+  int r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.s32 p, %1, 0;\n\t"
+      "bar.red.and.pred q, %2, %3, p;\n\t"
+      "selp.s32 %0, 1, 0, q;\n\t}"
+      : "=r"(r)
+      : "r"(pred), "r"(sub + 1), "r"(nthreads)
+      : "memory");
+  return r;
+}
+
+template <int NN, int MOD, int GB>
+__global__ void __launch_bounds__(16 * FOCT_PAIR_CTA_CHAINS * (GB == 2 ? FOCT_PAIR_SUBS : 1),
+                                  GB == 2 ? FOCT_PAIR_MINB_GS : (GB == 1 ? FOCT_PAIR_MINB_GB : FOCT_PAIR_MINB))
 nuts2_kernel(const SamplerParams K) {
-  extern __shared__ __align__(128) double smem[];
-  __shared__ uint64_t mbar;
-  __shared__ int s_next;
-  __shared__ DevProblem s_prob;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int SUBS = GB == 2 ? FOCT_PAIR_SUBS : 1;
+  const int SUB_THREADS = (int)blockDim.x / SUBS;  // 64, or 32 when a profile has at most two chains
+  extern __shared__ __align__(128) double smem_all[];
+  __shared__ uint64_t mbar[SUBS + 1];
+  __shared__ int s_next[SUBS], s_resume[SUBS];
+  __shared__ DevProblem s_prob[SUBS];
+  const int sub = GB == 2 ? (int)threadIdx.x / SUB_THREADS : 0;
+  const int tid = (int)threadIdx.x - sub * SUB_THREADS;
+  const int lane = tid & 31, warp = tid >> 5;
+  const bool leader = tid == 0;
   const int groups = (K.chains + FOCT_PAIR_CTA_CHAINS - 1) / FOCT_PAIR_CTA_CHAINS;
   const int n_items = K.n_problems * groups;
-  mbar_init(&mbar);
+  const bool sliced = K.slice_state != nullptr;
+  constexpr int CTA_WARPS = FOCT_PAIR_CTA_CHAINS / 2;
+  // shared memory: [basis rows, NN x npad (GB = 2 only)] [sub 0: staged rows / blob] [sub 1] ...
+  const double* gbasis = GB == 1 ? K.blobs : nullptr;
+  double* smem = smem_all;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i <= SUBS; ++i) {
+      const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(&mbar[i]);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (GB == 2) {
+    // the basis rows of blob 0 (rows 3 .. 3 + NN of every 32-point block), once per CTA
+    uint32_t ph = 0;
+    stage_rows_tma(smem_all, K.blobs + 3 * 32, K.npad / 32, 3 + NN, NN, &mbar[SUBS], ph, threadIdx.x == 0);
+    gbasis = smem_all;
+    smem = smem_all + (size_t)NN * K.npad + (size_t)sub * 3 * K.npad;
+    __syncthreads();
+  }
   uint32_t phase = 0;
   for (;;) {
-    if (threadIdx.x == 0) s_next = atomicAdd(K.work_counter, 1);
-    __syncthreads();
-    const int w = s_next;
-    if (w >= n_items) break;
+    if (leader) {
+      int w = -1, res = 0;
+      if (!sliced) {
+        w = atomicAdd(K.work_counter, 1);
+        if (w >= n_items) w = -1;
+      } else {
+        const unsigned t = atomicAdd(K.slice_ctl, 1u);
+        if (t < (unsigned)n_items) {
+          w = (int)t;
+        } else {
+          // wait for the push this ticket stands for, or for the last item to finish
+          const volatile unsigned long long* slot = K.slice_queue + (t - (unsigned)n_items) % (unsigned)n_items;
+          for (;;) {
+            const unsigned long long v = *slot;
+            if ((unsigned)(v >> 32) == t) { w = (int)(v & 0xffffffffu); res = 1; break; }
+            if (*reinterpret_cast<const volatile unsigned*>(K.slice_ctl + 2) >= (unsigned)n_items) break;
+            __nanosleep(2000);
+          }
+          __threadfence();
+        }
+      }
+      s_next[sub] = w; s_resume[sub] = res;
+    }
+    sub_sync(sub, SUB_THREADS);
+    const int w = s_next[sub];
+    const bool resume = s_resume[sub] != 0;
+    if (w < 0) break;
     const int j = K.order ? K.order[w / groups] : w / groups;
     const int chain = (w % groups) * FOCT_PAIR_CTA_CHAINS + 2 * warp + (lane >> 4);
-    if (threadIdx.x == 0) s_prob = K.probs[j];
-    if (GB) stage_rows_tma(smem, K.blobs + (size_t)j * K.blob_stride, K.npad / 32, 3 + NN, 3, &mbar, phase);
-    else stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase);
-    __syncthreads();
+    if (leader) s_prob[sub] = K.probs[j];
+    if (GB) stage_rows_tma(smem, K.blobs + (size_t)j * K.blob_stride, K.npad / 32, 3 + NN, 3, &mbar[sub], phase, leader);
+    else stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar[sub], phase, leader);
+    sub_sync(sub, SUB_THREADS);
     // a warp runs if at least its first half has a chain
-    if ((w % groups) * FOCT_PAIR_CTA_CHAINS + 2 * warp < K.chains) run_pair<NN, MOD, GB>(K, s_prob, smem, j, chain, lane);
-    __syncthreads();
+    bool fin = true;
+    if ((w % groups) * FOCT_PAIR_CTA_CHAINS + 2 * warp < K.chains) {
+      double* sv = sliced ? K.slice_state + ((size_t)w * CTA_WARPS + warp) * (FOCT_PAIR_STATE_DOUBLES * 32) : nullptr;
+      int* wdone = sliced ? K.slice_done + (size_t)w * CTA_WARPS + warp : nullptr;
+      if (!(resume && __ldcg(wdone) != 0)) {
+        fin = run_pair<NN, MOD, GB>(K, s_prob[sub], smem, j, chain, lane, sv, resume, n_items, gbasis);
+        if (sliced && lane == 0) __stcg(wdone, fin ? 1 : 0);
+      }
+    }
+    const int all_fin = sub_sync_and(sub, SUB_THREADS, fin ? 1 : 0);
+    if (sliced && leader) {
+      if (all_fin) {
+        atomicAdd(K.slice_ctl + 2, 1u);
+      } else {
+        __threadfence();  // the state stored by this sub-CTA's warps before the barrier is visible before the queue entry is
+        const unsigned p = atomicAdd(K.slice_ctl + 1, 1u);
+        *reinterpret_cast<volatile unsigned long long*>(K.slice_queue + p % (unsigned)n_items) =
+            ((unsigned long long)((unsigned)n_items + p) << 32) | (unsigned)w;
+      }
+    }
   }
 }
 

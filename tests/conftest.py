@@ -39,6 +39,18 @@ def L():
     return _lib
 
 
+@pytest.fixture(params=["auto", "pair"])
+def sampling_kernel(request, monkeypatch):
+    """The library picks the sampling kernel by batch size (foct_inst.cu: one chain per warp while the batch fits the GPU
+    in one go, two chains per warp above that).  The parity tests use small batches, so they run twice: as shipped, and
+    with the two-chains-per-warp kernel forced — the one the BASELINE-size batches run on."""
+    if request.param == "pair":
+        monkeypatch.setenv("FOCT_FORCE_PAIR", "1")
+    else:
+        monkeypatch.delenv("FOCT_FORCE_PAIR", raising=False)
+    return request.param
+
+
 def case_to_batch(case):
     from fitoct_b200 import _abi as abi
 

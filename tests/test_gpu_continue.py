@@ -25,7 +25,7 @@ def batch_of(n, Nn=10, first_id=0):
 
 
 @pytest.mark.parametrize("Nn", [10, 15])   # two chains per warp / one chain per warp
-def test_split_run_is_bit_identical_to_the_unsplit_run(L, Nn):
+def test_split_run_is_bit_identical_to_the_unsplit_run(L, Nn, sampling_kernel):
     _, b = batch_of(3, Nn)
     spec = abi.default_spec()
     full = L.sample(0, b, 3, spec, abi.default_cfg(n_warmup=40, n_iter=90, seed=7))
@@ -46,7 +46,7 @@ def test_split_run_is_bit_identical_to_the_unsplit_run(L, Nn):
     np.testing.assert_allclose(full["last_q"], last, rtol=1e-13, atol=1e-15)
 
 
-def test_continuation_builds_the_same_trees_as_the_oracle(L, O):
+def test_continuation_builds_the_same_trees_as_the_oracle(L, O, sampling_kernel):
     _, b = batch_of(2, 10, first_id=11)
     spec = abi.default_spec()
     cfg = abi.default_cfg(n_warmup=30, n_iter=40, seed=99)
@@ -62,7 +62,7 @@ def test_continuation_builds_the_same_trees_as_the_oracle(L, O):
 
 
 @pytest.mark.parametrize("Nn,n_warmup", [(10, 150), (10, 40), (15, 150)])
-def test_adaptation_windows_match_the_oracle(L, O, Nn, n_warmup):
+def test_adaptation_windows_match_the_oracle(L, O, Nn, n_warmup, sampling_kernel):
     """Deterministic comparison ACROSS the metric windows (tree identity stopped at transition 6, before
     any window closed).  Shallow trees (max_treedepth 3) and a cautious step size (adapt_delta 0.95) keep the floating-
     point chaos of the trajectories small — on the CPU restatement a 1e-15 perturbation of the data grows to 1e-11 over
@@ -93,7 +93,7 @@ def test_adaptation_windows_match_the_oracle(L, O, Nn, n_warmup):
     np.testing.assert_array_equal(sp[:, n_warmup:, :, 1], np.broadcast_to(out["stepsize"][:, None, :], sp[:, n_warmup:, :, 1].shape))
 
 
-def test_run_until_converged(L, O):
+def test_run_until_converged(L, O, sampling_kernel):
     n = 12
     _, b = batch_of(n, 10, first_id=40)
     spec = abi.default_spec()
@@ -172,3 +172,37 @@ def test_progress_callback_and_cancel(L):
         plan.sync()
     assert ei.value.code == -5
     plan.close()
+
+
+@pytest.mark.parametrize("ticks", [37, 500])
+def test_time_sliced_work_items_are_bit_identical(L, monkeypatch, ticks):
+    """nuts2_kernel's time slicing (more work items than resident CTAs): a fit that is suspended after `ticks` gradient
+    evaluations — in the middle of a tree, a step-size trial or an adaptation window — stored, queued and resumed by
+    whichever CTA is free gives exactly the draws, sampler parameters, adapted state and counts of the uninterrupted fit."""
+    n = 24
+    _, b = batch_of(n, 10, first_id=300)   # one depth grid for the batch: the shared-basis kernel
+    spec = abi.default_spec()
+    cfg = abi.default_cfg(n_warmup=60, n_iter=100, seed=21, save_warmup=1)
+    monkeypatch.setenv("FOCT_FORCE_PAIR", "1")   # (a batch this small would otherwise run one chain per warp, unsliced)
+    monkeypatch.setenv("FOCT_MAX_GRID", "5")     # 24 items on 5 CTAs: every slice ends with other items waiting
+    monkeypatch.setenv("FOCT_SLICE_TICKS", "0")
+    plain = L.sample(0, b, n, spec, cfg)
+    monkeypatch.setenv("FOCT_SLICE_TICKS", str(ticks))
+    sliced = L.sample(0, b, n, spec, cfg)
+    for k in ("draws", "sampler_params", "summary", "stepsize", "inv_metric", "last_q", "n_leapfrog", "n_divergent"):
+        np.testing.assert_array_equal(sliced[k], plain[k], err_msg=k)
+    assert plain["n_leapfrog"].sum() > 20 * ticks * n   # the fits were long enough to be suspended many times
+    # the other two variants of the kernel: basis read through L1 (the fallback when the shared-memory copy does not
+    # fit), and the whole blob staged per item (ragged depth grids: no shared basis).  All three sum in the same order.
+    for env in ({"FOCT_BASIS_MODE": "1"}, {"FOCT_NO_SHARED_BASIS": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        monkeypatch.setenv("FOCT_SLICE_TICKS", "0")
+        plain2 = L.sample(0, b, n, spec, cfg)
+        monkeypatch.setenv("FOCT_SLICE_TICKS", str(ticks))
+        sliced2 = L.sample(0, b, n, spec, cfg)
+        for k in ("draws", "sampler_params", "stepsize", "inv_metric", "n_leapfrog"):
+            np.testing.assert_array_equal(sliced2[k], plain2[k], err_msg=k)
+            np.testing.assert_array_equal(plain2[k], plain[k], err_msg=k)
+        for k in env:
+            monkeypatch.delenv(k)

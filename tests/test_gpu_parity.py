@@ -152,7 +152,7 @@ def test_ragged_batch_and_empty_errors(L, O):
 
 
 @pytest.mark.parametrize("Nn,chains", [(10, 4), (5, 1), (15, 8), (20, 3)])
-def test_sampler_builds_the_same_trees_as_the_oracle(L, O, Nn, chains):
+def test_sampler_builds_the_same_trees_as_the_oracle(L, O, Nn, chains, sampling_kernel):
     # same Philox draw sites => identical tree depth / leapfrog count / divergence flags and (to rounding) the
     # same draws, until floating-point chaos separates the trajectories.  Checked over the first transitions,
     # which include the init_stepsize heuristic and the first dual-averaging updates.
@@ -171,7 +171,7 @@ def test_sampler_builds_the_same_trees_as_the_oracle(L, O, Nn, chains):
     assert np.all(out["n_leapfrog"].sum(axis=2) == out["sampler_params"][..., 3].sum(axis=1))
 
 
-def test_monoexp_sampler_and_prior_pd(L, O):
+def test_monoexp_sampler_and_prior_pd(L, O, sampling_kernel):
     S = synth.make_profiles(5)
     b = abi.make_problems_dense(S["x"], S["Y"][:1], S["UY"][:1], S["theta0"][:1], S["Sigma0"][:1], Nn=0)
     spec = abi.default_spec(abi.FOCT_MONOEXP)
@@ -233,7 +233,7 @@ def test_map_and_predict_vs_oracle(L, O):
         np.testing.assert_allclose(m, mo, rtol=1e-8)
 
 
-def test_shard_invariance_and_determinism(L):
+def test_shard_invariance_and_determinism(L, sampling_kernel):
     # a profile's chains depend only on (seed, profile id, chain): not on batch composition, order or device shard
     S = synth.make_profiles(6, modulated_only=True)
     b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=10, ids=S["ids"])
@@ -333,7 +333,7 @@ def test_expgp_map_vs_oracle(L, O):
     assert fit["fit"]["hessian"].shape == (15, 15)                                                # server.R:164-173
 
 
-def test_size_edges(L, O):
+def test_size_edges(L, O, sampling_kernel):
     rng = np.random.default_rng(11)
     # long profile (N = 1500 > 32 * 46), few control points; tiny profile at the N >= Nn + 4 limit; widest model Nn = 25
     x = np.linspace(5.0, 900.0, 1500)
@@ -364,7 +364,7 @@ def test_size_edges(L, O):
         L.logp_grad(0, abi.make_problems([few]), 1, abi.default_spec(), np.zeros((1, 1, 10)))
 
 
-def test_sampler_cfg_edges(L, O):
+def test_sampler_cfg_edges(L, O, sampling_kernel):
     S = synth.make_profiles(1, modulated_only=True)
     b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=10)
     spec = abi.default_spec()

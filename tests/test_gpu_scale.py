@@ -53,9 +53,10 @@ def test_batch_recovers_synthData_truth(batch_run):
     assert 0.88 < cover <= 1.0
 
 
-def test_plan_path_equals_one_shot_path(L, batch_run):
+def test_plan_path_equals_one_shot_path(L, batch_run, monkeypatch):
     S, b, cfg, out = batch_run
     n = 64
+    monkeypatch.setenv("FOCT_FORCE_PAIR", "1")   # the kernel the 1000-profile batch ran on (foct_inst.cu picks by batch size)
     sub = abi.make_problems_dense(S["x"], S["Y"][:n], S["UY"][:n], S["theta0"][:n], S["Sigma0"][:n], Nn=10, ids=S["ids"][:n])
     plan = L.Plan(abi.FOCT_EXPGP, sub, n, abi.default_spec(), cfg, want_draws=False, want_summary=True)
     plan.run(cfg.seed)
@@ -70,10 +71,11 @@ def test_plan_path_equals_one_shot_path(L, batch_run):
     np.testing.assert_array_equal(res["stepsize"], out["stepsize"][:n])
 
 
-def test_leapfrog_accounting(L, batch_run):
+def test_leapfrog_accounting(L, batch_run, monkeypatch):
     # the roofline numerator: leapfrogs counted on device equal the n_leapfrog__ column of the draws
     S, b, cfg, out = batch_run
     n = 8
+    monkeypatch.setenv("FOCT_FORCE_PAIR", "1")   # the kernel the 1000-profile batch ran on
     sub = abi.make_problems_dense(S["x"], S["Y"][:n], S["UY"][:n], S["theta0"][:n], S["Sigma0"][:n], Nn=10, ids=S["ids"][:n])
     cfg2 = abi.default_cfg(n_warmup=500, n_iter=1500, seed=1234, save_warmup=1)
     o = L.sample(abi.FOCT_EXPGP, sub, n, abi.default_spec(), cfg2, draws=True, summary=True)
