@@ -415,7 +415,8 @@ def main():
                          "algorithmic_bytes_per_launch": n * ((3 + args.nn) * 512 * 8 + chains * n_post * (args.nn + 7) * 8),
                          "peak_source": "DFMA-chain microbenchmark measured in this run (foct_fp64_peak); "
                                         "MEASURED_PEAKS.json has no fp64 figure",
-                         "kernel": "foct::nuts2_kernel" if args.nn <= 11 else "foct::nuts_kernel",
+                         "kernel": ("foct::nuts2w_kernel (two chains per warp, warps claim (profile, chain pair) units, time-sliced)"
+                                    if tm["block"] == 64 and args.nn <= 11 else "foct::nuts_kernel (one chain per warp)"),
                          "algorithmic_flop_per_grad": f_grad(481, args.nn),
                          "leapfrogs_per_step": leap_all / world / args.steps,
                          "hbm_writeback_gbs": (n * chains * n_post * (args.nn + 7) * 8 * args.steps / Ts_max) / 1e9,

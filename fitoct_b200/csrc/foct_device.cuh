@@ -287,10 +287,10 @@ struct Dims {
 // Raw sums go to acc[] (theta2 / theta3 factors are applied once, after the reduction).
 // W = 32: point u of the iteration sits one pass block further (pp + u * block); W = 16 (half-warp lane groups, pp
 // carries the lane index inside the group): the points are the two 16-point halves of consecutive 32-point blocks.
-// GB != 0: the basis rows are not in the staged block (which then holds cx | y | w only) because every profile of the batch
-// shares them (same depth grid => same basis).  GB = 1: read through L1 from `pg`, a whole blob in global
-// memory (rows cx | y | w | B_0.. per block).  GB = 2: `pg` is a copy of the basis rows alone (NN rows per block) in shared
-// memory that the sub-CTAs of one CTA share (nuts2_kernel).
+// GB: the basis rows are not in the staged block (which then holds cx | y | w only) but read through L1 from `pg`, a
+// blob in global memory that every profile of the batch shares (same depth grid => same basis).  (A copy
+// of the basis rows in shared memory, shared by three two-warp sub-CTAs of a 192-thread CTA, was measured 11 % slower at
+// the same twelve warps per SM: profiles/r2_kernel_experiments.txt.)
 #ifndef FOCT_PAIR_LDS128
 #define FOCT_PAIR_LDS128 1
 #endif
@@ -303,7 +303,6 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
   const double* __restrict__ pp = pp0;
 #define FOCT_PT(u) (W == 32 ? (u) * SROWS * 32 : ((u) >> 1) * SROWS * 32 + ((u) & 1) * 16)
 #define FOCT_PTG(u) (W == 32 ? (u) * (3 + NN) * 32 : ((u) >> 1) * (3 + NN) * 32 + ((u) & 1) * 16)
-  static_assert(GB != 2 || (W == 16 && FOCT_PAIR_LDS128), "the shared-memory basis copy is read by the half-warp point-pair path only");
   double b[U][NN > 0 ? NN : 1];
   double dl0[U], dl1[U], s[U], cx[U], y[U], ws[U], r[U], t[U];
 #pragma unroll
@@ -317,9 +316,8 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
     for (int k = 0; k < NN; ++k) {
 #pragma unroll
       for (int v = 0; v < U / 2; ++v) {
-        const double2 bb = GB == 1 ? __ldg(reinterpret_cast<const double2*>(pg + v * (3 + NN) * 32 + (3 + k) * 32))
-                           : GB == 2 ? *reinterpret_cast<const double2*>(pg + v * NN * 32 + k * 32)
-                                     : *reinterpret_cast<const double2*>(pp + v * SROWS * 32 + (3 + k) * 32);
+        const double2 bb = GB ? __ldg(reinterpret_cast<const double2*>(pg + v * (3 + NN) * 32 + (3 + k) * 32))
+                              : *reinterpret_cast<const double2*>(pp + v * SROWS * 32 + (3 + k) * 32);
         b[2 * v][k] = bb.x; b[2 * v + 1][k] = bb.y;
         if (k & 1) { dl1[2 * v] = fma(bb.x, yg[k], dl1[2 * v]); dl1[2 * v + 1] = fma(bb.y, yg[k], dl1[2 * v + 1]); }
         else { dl0[2 * v] = fma(bb.x, yg[k], dl0[2 * v]); dl0[2 * v + 1] = fma(bb.y, yg[k], dl0[2 * v + 1]); }
@@ -553,13 +551,18 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
   if (!P.prior_PD) {
     const double r3 = frcp(th3);  // (a full division drags its exponent-range slow path into every leaf)
     constexpr int ROWS = GB ? 3 : 3 + NN;     // rows of a staged block
-    constexpr int GROWS = GB == 2 ? NN : 3 + NN;  // rows of a block of the shared basis (whole blob in global / basis rows in smem)
+    constexpr int GROWS = 3 + NN;             // rows of a block of the shared (global) blob
     // (half-warp groups with 128-bit loads: lane l owns the neighbouring points 2l, 2l+1 of each block)
     const int lane_off = (W == 16 && FOCT_PAIR_LDS128) ? 2 * lane : lane;
     const double* pp = blob + lane_off;
     const double* pg = GB ? gbasis + lane_off : nullptr;
     FOCT_T(t_l0);
     FOCT_TADD(3, t_g0, t_l0);
+    // (A profile of 481 points is 15 blocks and ONE point, so the 16th iteration runs 1/32 full.  Evaluating such tail
+    // points by the lane group as a whole — control point k in lane 3 + k, the scalar chain repeated by every lane — was
+    // measured 2.5 % SLOWER than the padded iteration: it is one more serial dependency chain of the same length, and
+    // the kernel is bound by latency, not by issue slots.  profiles/r2_kernel_experiments.txt)
+    const int npass = P.npass;
     int pass = 0;
     if constexpr (W == 16) {
       // 32-point blocks: the two 16-point halves of a block are two points in flight per lane; FOCT_UNROLL16 = 4 takes
@@ -574,20 +577,20 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
       constexpr int U16 = NN <= 11 ? (GB ? FOCT_UNROLL16_GB : FOCT_UNROLL16) : 2;
       if (U16 > 2) {
 #pragma unroll 1
-        for (; pass + U16 / 2 <= P.npass; pass += U16 / 2, pp += (U16 / 2) * ROWS * 32, pg += (U16 / 2) * GROWS * 32)
+        for (; pass + U16 / 2 <= npass; pass += U16 / 2, pp += (U16 / 2) * ROWS * 32, pg += (U16 / 2) * GROWS * 32)
           sweep_points<NN, MOD, KP, ZI, U16, W, GB>(pp, th1, th2, th3, r3, yg, acc, pg);
       }
 #pragma unroll 1
-      for (; pass < P.npass; ++pass, pp += ROWS * 32, pg += GROWS * 32)
+      for (; pass < npass; ++pass, pp += ROWS * 32, pg += GROWS * 32)
         sweep_points<NN, MOD, KP, ZI, 2, W, GB>(pp, th1, th2, th3, r3, yg, acc, pg);
     } else {
       if (UNROLL >= 2) {
 #pragma unroll 1
-        for (; pass + UNROLL <= P.npass; pass += UNROLL, pp += UNROLL * ROWS * 32, pg += UNROLL * GROWS * 32)
+        for (; pass + UNROLL <= npass; pass += UNROLL, pp += UNROLL * ROWS * 32, pg += UNROLL * GROWS * 32)
           sweep_points<NN, MOD, KP, ZI, UNROLL, W, GB>(pp, th1, th2, th3, r3, yg, acc, pg);
       }
 #pragma unroll 1
-      for (; pass < P.npass; ++pass, pp += ROWS * 32, pg += GROWS * 32)
+      for (; pass < npass; ++pass, pp += ROWS * 32, pg += GROWS * 32)
         sweep_points<NN, MOD, KP, ZI, 1, W, GB>(pp, th1, th2, th3, r3, yg, acc, pg);
     }
     FOCT_T(t_l1);
@@ -630,6 +633,8 @@ __device__ __forceinline__ void stage_blob_tma(double* smem_dst, const double* g
   const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
   if (leader) {
     const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    // (the block may have been read through the generic proxy by the previous work item)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(bytes) : "memory");
     // chunks of <= 64 KB keep every copy well inside any per-instruction limit
     uint32_t off = 0;
@@ -664,6 +669,7 @@ __device__ __forceinline__ void stage_rows_tma(double* smem_dst, const double* g
   if (leader) {
     const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(smem_dst);
     const uint32_t blk = (uint32_t)rows * 32u * (uint32_t)sizeof(double);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(blk * (uint32_t)nblocks) : "memory");
     for (int j = 0; j < nblocks; ++j)
       asm volatile(

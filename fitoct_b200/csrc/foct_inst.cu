@@ -398,11 +398,13 @@ static cudaError_t launch_nuts_mod(int grid, int block, size_t smem, cudaStream_
   cudaError_t e;
   if constexpr (Dims<NN>::D <= 16) {
     if (K.pair_kernel) {
-      if (K.shared_basis == 2) {
-        e = cudaFuncSetAttribute(nuts2_kernel<NN, MOD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        nuts2_kernel<NN, MOD, 2><<<grid, block, smem, st>>>(K);
-      } else if (K.shared_basis == 1) {
+      if (K.shared_basis && K.warp_units) {
+        if constexpr (NN > 0) {
+          e = cudaFuncSetAttribute(nuts2w_kernel<NN, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return e;
+          nuts2w_kernel<NN, MOD><<<grid, block, smem, st>>>(K);
+        }
+      } else if (K.shared_basis) {
         e = cudaFuncSetAttribute(nuts2_kernel<NN, MOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         nuts2_kernel<NN, MOD, 1><<<grid, block, smem, st>>>(K);
@@ -459,9 +461,9 @@ static cudaError_t occupancy_of(KernelT kernel, int block, size_t smem, int* blo
 template <int NN>
 static cudaError_t nuts_occupancy(int mod, int chains, long long n_items, int n_sm, size_t smem_full, size_t smem_rows,
                                   int* shared_basis, size_t* smem, int* block, int* blocks_per_sm, int* cta_chains, int* regs,
-                                  size_t* slice_bytes, int* pair_kernel, int* subs) {
+                                  size_t* slice_bytes, int* pair_kernel, int* warp_units) {
   *smem = smem_full;
-  *subs = 1;  // independent two-warp sub-CTAs per CTA, each working through items (nuts2_kernel, basis mode 2)
+  *warp_units = 0;
   *slice_bytes = 0;  // per work item: saved state of a CTA's warps (time slicing); 0 = this kernel runs items to completion
   *pair_kernel = 0;
   *cta_chains = FOCT_CTA_CHAINS;
@@ -486,26 +488,24 @@ static cudaError_t nuts_occupancy(int mod, int chains, long long n_items, int n_
       *block = nuts_block<NN>(chains, true);
       *cta_chains = FOCT_PAIR_CTA_CHAINS;
       *slice_bytes = (size_t)(FOCT_PAIR_CTA_CHAINS / 2) * FOCT_PAIR_STATE_DOUBLES * 32 * sizeof(double);
-      // One depth grid for the batch = one GP basis for every profile: only cx | y | w are staged per item, and twelve
-      // warps fit an SM instead of eight.  Mode 2: the basis rows sit once per CTA in shared memory, shared by
-      // FOCT_PAIR_SUBS sub-CTAs; mode 1 (the fallback when that copy does not fit, FOCT_BASIS_MODE=1 for A/B runs): read
-      // through L1 from blob 0.  Measured in profiles/r2_kernel_experiments.txt.
+      // One depth grid for the batch = one GP basis for every profile: only cx | y | w are staged per item (12 KB), the
+      // basis rows come through L1 from blob 0, and twelve warps fit an SM instead of eight.  With 64-bit loads that bought
+      // nothing (2.58e8 vs 2.61e8 gradients/s at full waves: twice the L1 requests of the staged variant's LDS); with one
+      // 128-bit load per row and point pair it is 3.0e8 (profiles/r2_kernel_experiments.txt).  FOCT_NO_SHARED_BASIS=1: A/B.
       const bool use_gb = std::getenv("FOCT_NO_SHARED_BASIS") == nullptr;  // (read per plan: tests flip it)
       if (*shared_basis && NN > 0 && use_gb) {
-        const char* bm = std::getenv("FOCT_BASIS_MODE");
-        if (!bm || std::atoi(bm) == 2) {
-          const size_t smem2 = smem_rows / 3 * NN + (size_t)FOCT_PAIR_SUBS * smem_rows;
-          int b2 = 0, r2 = 0;
-          const int block2 = *block * FOCT_PAIR_SUBS;
-          cudaError_t e2 = mod == 0 ? occupancy_of(nuts2_kernel<NN, 0, 2>, block2, smem2, &b2, &r2)
-                                    : occupancy_of(nuts2_kernel<NN, 1, 2>, block2, smem2, &b2, &r2);
-          if (e2 == cudaSuccess && b2 >= 1) {
-            *shared_basis = 2; *smem = smem2; *block = block2; *blocks_per_sm = b2; *regs = r2; *subs = FOCT_PAIR_SUBS;
-            return cudaSuccess;
-          }
-          cudaGetLastError();
-        }
         *shared_basis = 1;
+        if constexpr (NN > 0) {
+          if (!std::getenv("FOCT_CTA_ITEMS")) {  // (A/B: the CTA-level items of nuts2_kernel<.., 1>)
+            // warps as the scheduling unit: two warps per CTA whatever the chain count, each with its own staged rows
+            *warp_units = 1;
+            *block = 64;
+            *smem = 2 * smem_rows;
+            *slice_bytes = (size_t)FOCT_PAIR_STATE_DOUBLES * 32 * sizeof(double);  // per unit = per warp
+            return mod == 0 ? occupancy_of(nuts2w_kernel<NN, 0>, *block, *smem, blocks_per_sm, regs)
+                            : occupancy_of(nuts2w_kernel<NN, 1>, *block, *smem, blocks_per_sm, regs);
+          }
+        }
         *smem = smem_rows;
         return mod == 0 ? occupancy_of(nuts2_kernel<NN, 0, 1>, *block, *smem, blocks_per_sm, regs)
                         : occupancy_of(nuts2_kernel<NN, 1, 1>, *block, *smem, blocks_per_sm, regs);

@@ -62,7 +62,7 @@ struct InstEntry {
   // launch geometry for a batch of n_items profiles on a device with n_sm SMs; n_items = 0: the one-chain-per-warp kernel
   cudaError_t (*nuts_occupancy)(int mod, int chains, long long n_items, int n_sm, size_t smem_full, size_t smem_rows,
                                 int* shared_basis, size_t* smem, int* block, int* blocks_per_sm, int* cta_chains, int* regs,
-                                size_t* slice_bytes, int* pair_kernel, int* subs);
+                                size_t* slice_bytes, int* pair_kernel, int* warp_units);
   cudaError_t (*launch_map)(int mod, int grid, size_t smem, cudaStream_t st, const MapParams& K);
   cudaError_t (*launch_vb)(int mod, int grid, size_t smem, cudaStream_t st, const VbParams& K);
 };

@@ -500,7 +500,10 @@ struct foct_plan {
   int* d_counter = nullptr;
   int* d_order = nullptr;  // work-item order: longest expected fits first (see plan_order)
   const InstEntry* inst = nullptr;
-  int grid = 0, block = 0, blocks_per_sm = 0, regs = 0, groups = 1, n_sm = 0;
+  int grid = 0, block = 0, blocks_per_sm = 0, regs = 0, n_sm = 0;
+  int groups = 1;  // work units per profile: groups of <= 4 chains (CTA-level items) or chain pairs (nuts2w_kernel)
+  int wpc = 1;     // work units a CTA has in flight (2: the warps of nuts2w_kernel claim units on their own)
+  int warp_units = 0, alt_groups = 1;
   size_t smem = 0;
   bool ran = false;
   // continuation inputs (cfg.inv_metric_init / stepsize_init) and the state a continuation starts from
@@ -531,7 +534,6 @@ struct foct_plan {
   // geometry of the one-chain-per-warp kernel for continuation rounds of few profiles
   int pair_kernel = 0;
   int alt_block = 0, alt_blocks_per_sm = 0;
-  int subs = 1;  // two-warp sub-CTAs per CTA (nuts2_kernel with the basis copy in shared memory): items a CTA works on at once
   size_t alt_smem = 0;
 };
 
@@ -889,7 +891,7 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
   CUP(pool_malloc(&p->d_invm, pc * p->D * sizeof(double)));
   CUP(pool_malloc(&p->d_nleap, pc * 2 * sizeof(double)));
   CUP(pool_malloc(&p->d_ndiv, pc * sizeof(double)));
-  CUP(pool_malloc(&p->d_counter, 4 * sizeof(int)));  // work counter; with time slicing: tickets | pushes | finished
+  CUP(pool_malloc(&p->d_counter, (4 + 64) * sizeof(int)));  // work counter; with time slicing: tickets | pushes | finished | - | waiting units by progress bin
   if (cfg->init_mode == 2) {
     CUP(pool_malloc(&p->d_init, pc * p->D * sizeof(double)));
     CUP(cudaMemcpy(p->d_init, init_slice, pc * p->D * sizeof(double), cudaMemcpyHostToDevice));
@@ -917,24 +919,26 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
   int n_sm = 0;  // (cudaGetDeviceProperties costs milliseconds; one attribute does not)
   CUP(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
   CUP(p->inst->nuts_occupancy(spec->modulation, cfg->chains, n, n_sm, p->blob_stride * sizeof(double), (size_t)3 * p->npad * sizeof(double),
-                              &shared_basis, &p->smem, &p->block, &p->blocks_per_sm, &cta_chains, &p->regs, &slice_bytes, &p->pair_kernel, &p->subs));
+                              &shared_basis, &p->smem, &p->block, &p->blocks_per_sm, &cta_chains, &p->regs, &slice_bytes, &p->pair_kernel, &p->warp_units));
   p->shared_basis = shared_basis;
+  if (const char* env = std::getenv("FOCT_SMEM_PAD")) p->smem += (size_t)std::atoi(env);  // experiments: shrink L1 by unused shared memory
   if (p->blocks_per_sm < 1) { plan_free(p); return fail(FOCT_EINVAL, "sampling kernel does not fit an SM (smem %zu B)", p->smem); }
   if (p->pair_kernel) {
     // (n_items = 0: the geometry of the one-chain-per-warp kernel, if the blob fits an SM at all)
-    int sb = 0, cc = 0, rg = 0, pk = 0, su = 0;
+    int sb = 0, cc = 0, rg = 0, pk = 0, wu = 0;
     size_t sl = 0;
     if (p->inst->nuts_occupancy(spec->modulation, cfg->chains, 0, n_sm, p->blob_stride * sizeof(double), (size_t)3 * p->npad * sizeof(double),
-                                &sb, &p->alt_smem, &p->alt_block, &p->alt_blocks_per_sm, &cc, &rg, &sl, &pk, &su) != cudaSuccess || pk) {
+                                &sb, &p->alt_smem, &p->alt_block, &p->alt_blocks_per_sm, &cc, &rg, &sl, &pk, &wu) != cudaSuccess || pk) {
       cudaGetLastError();
       p->alt_blocks_per_sm = 0;
     }
   }
-  const int groups = (cfg->chains + cta_chains - 1) / cta_chains;
-  p->groups = groups; p->n_sm = n_sm;
-  p->grid = (int)std::min<long long>(((long long)n * groups + p->subs - 1) / p->subs, (long long)n_sm * p->blocks_per_sm);
+  p->alt_groups = (cfg->chains + FOCT_CTA_CHAINS - 1) / FOCT_CTA_CHAINS;
+  const int groups = p->warp_units ? (cfg->chains + 1) / 2 : (cfg->chains + cta_chains - 1) / cta_chains;
+  p->groups = groups; p->n_sm = n_sm; p->wpc = p->warp_units ? 2 : 1;
+  p->grid = (int)std::min<long long>(((long long)n * groups + p->wpc - 1) / p->wpc, (long long)n_sm * p->blocks_per_sm);
   if (const char* env = std::getenv("FOCT_MAX_GRID")) p->grid = std::max(1, std::min(p->grid, std::atoi(env)));  // tests: few CTAs
-  const long long resident = (long long)p->grid * p->subs;  // work items in flight at once
+  const long long resident = (long long)p->grid * p->wpc;  // work units in flight at once
   // More work items than resident CTAs: the CTAs share them in time slices (nuts2_kernel) instead of running each to
   // completion, so that the last fits of the batch do not run alone.  FOCT_SLICE_TICKS=0 turns it off (A/B runs).
   if (slice_bytes > 0 && (long long)n * groups > resident) {
@@ -944,7 +948,7 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
       const size_t items = (size_t)n * groups;
       CUP(pool_malloc(&p->d_slice_state, items * slice_bytes));
       CUP(pool_malloc(&p->d_slice_queue, items * sizeof(unsigned long long)));
-      CUP(pool_malloc(&p->d_slice_done, items * (size_t)(cta_chains / 2) * sizeof(int)));
+      CUP(pool_malloc(&p->d_slice_done, items * 2 * sizeof(int)));
       p->slice_ticks = ticks;
     }
   }
@@ -1010,7 +1014,11 @@ static void plan_params(const foct_plan* p, unsigned long long seed, SamplerPara
   K.progress = p->d_progress; K.cancel = p->d_cancel; K.shared_basis = p->shared_basis;
   K.slice_state = p->d_slice_state; K.slice_queue = p->d_slice_queue; K.slice_done = p->d_slice_done;
   K.slice_ctl = reinterpret_cast<unsigned*>(p->d_counter); K.slice_ticks = p->slice_ticks;
-  K.pair_kernel = p->pair_kernel;
+  K.pair_kernel = p->pair_kernel; K.warp_units = p->warp_units;
+  // progress-aware yielding (foct_nuts2.cuh); FOCT_SLICE_PRIO=0: plain round robin (A/B runs)
+  const char* prio_env = std::getenv("FOCT_SLICE_PRIO");
+  const bool prio = !(prio_env && std::atoi(prio_env) == 0);
+  K.slice_hist = (p->warp_units && p->d_slice_state && prio) ? p->d_counter + 4 : nullptr;
 }
 
 extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
@@ -1019,7 +1027,7 @@ extern "C" int foct_plan_run(foct_plan* p, unsigned long long seed) {
   SamplerParams K;
   plan_params(p, seed, K);
   const foct_sampler_cfg& c = p->cfg;
-  CU(cudaMemsetAsync(p->d_counter, 0, 4 * sizeof(int), p->stream));
+  CU(cudaMemsetAsync(p->d_counter, 0, (4 + 64) * sizeof(int), p->stream));
   if (p->d_slice_queue) CU(cudaMemsetAsync(p->d_slice_queue, 0xff, (size_t)p->n * p->groups * sizeof(unsigned long long), p->stream));
   CU(cudaMemsetAsync(p->d_progress, 0, sizeof(unsigned long long), p->stream));
   CU(cudaMemsetAsync(p->d_cancel, 0, sizeof(int), p->stream));
@@ -1116,17 +1124,17 @@ static int plan_extend(foct_plan* p) {
     K.it_offset = c.iter_offset + c.n_iter + (e - 1) * ext;
     K.draws = p->d_xdraws; K.sparams = p->d_xsparams; K.slot_of = p->d_slot_of;
     K.save_stride = p->x_cap; K.save_offset = n_post + (e - 1) * ext; K.accumulate = 1;
-    CU(cudaMemsetAsync(p->d_counter, 0, 4 * sizeof(int), p->stream));
-    if ((long long)m * p->groups <= (long long)p->n_sm * p->blocks_per_sm * p->subs) K.slice_state = nullptr;  // every item has a CTA
+    CU(cudaMemsetAsync(p->d_counter, 0, (4 + 64) * sizeof(int), p->stream));
+    if ((long long)m * p->groups <= (long long)p->n_sm * p->blocks_per_sm * p->wpc) K.slice_state = nullptr;  // every unit has its CTA / warp
     else if (p->d_slice_queue) CU(cudaMemsetAsync(p->d_slice_queue, 0xff, (size_t)m * p->groups * sizeof(unsigned long long), p->stream));
     cudaEvent_t a0, a1, a2;
     CU(cudaEventCreate(&a0)); CU(cudaEventCreate(&a1)); CU(cudaEventCreate(&a2));
     CU(cudaEventRecord(a0, p->stream));
     // few profiles left: a warp per chain (a chain advances ~1.5x faster than with half a warp, and the GPU is not full)
-    const bool one_chain = p->pair_kernel && p->alt_blocks_per_sm > 0 && (long long)m * p->groups <= (long long)p->n_sm * p->alt_blocks_per_sm;
-    if (one_chain) { K.pair_kernel = 0; K.shared_basis = 0; K.slice_state = nullptr; }
-    const int bpsm = one_chain ? p->alt_blocks_per_sm : p->blocks_per_sm, subs = one_chain ? 1 : p->subs;
-    const int grid = (int)std::min<long long>(((long long)m * p->groups + subs - 1) / subs, (long long)p->n_sm * bpsm);
+    const bool one_chain = p->pair_kernel && p->alt_blocks_per_sm > 0 && (long long)m * p->alt_groups <= (long long)p->n_sm * p->alt_blocks_per_sm;
+    if (one_chain) { K.pair_kernel = 0; K.warp_units = 0; K.shared_basis = 0; K.slice_state = nullptr; }
+    const int bpsm = one_chain ? p->alt_blocks_per_sm : p->blocks_per_sm, wpc = one_chain ? 1 : p->wpc;
+    const int grid = (int)std::min<long long>(((long long)m * (one_chain ? p->alt_groups : p->groups) + wpc - 1) / wpc, (long long)p->n_sm * bpsm);
     CU(p->inst->launch_nuts(p->spec.modulation, grid, one_chain ? p->alt_block : p->block, one_chain ? p->alt_smem : p->smem, p->stream, K));
     CU(cudaEventRecord(a1, p->stream));
     CU(launch_summary(p->d_xdraws, m, p->x_cap, 0, n_post + e * ext, C, P_out, p->d_summary, p->stream, p->d_sel_slots, p->d_sel));

@@ -54,8 +54,10 @@ struct SamplerParams {
   int* slice_done;                  // [n_items][warps per CTA] != 0: the chains of this warp have finished
   unsigned long long* slice_queue;  // [n_items] ring of suspended items, (ticket << 32 | item)
   unsigned* slice_ctl;              // tickets handed out | pushes | items finished
+  int* slice_hist;                  // [FOCT_PROGRESS_BINS] waiting units by iterations done (nuts2w_kernel), or nullptr
   int slice_ticks;                  // gradient evaluations per slice
   int pair_kernel;                  // host: 1 = nuts2_kernel (two chains per warp), 0 = nuts_kernel
+  int warp_units;                   // host: 1 = nuts2w_kernel (warps claim (profile, chain pair) units on their own)
 };
 
 #define FOCT_PROGRESS_EVERY 8

@@ -53,12 +53,18 @@ __device__ __forceinline__ bool merge_persists_w(double invM, double i_rho, doub
 // lane32 = lane in the warp; this half's chain is `chain` (>= K.chains: the half has no chain and only keeps the other
 // half company in the gradient evaluations).
 // Time slicing: `sv` (nullptr: off) is this warp's block of FOCT_PAIR_STATE_DOUBLES x 32 doubles in global memory.  With
-// `resume` the state is loaded from it instead of being initialised; after K.slice_ticks gradient evaluations, if other
-// work items are waiting for a CTA, the state is stored there and the function returns false (true: both chains finished).
+// `resume` the state is loaded from it instead of being initialised; after K.slice_ticks gradient evaluations the warp
+// may give its place up: the state is stored there and the function returns the unit's progress bin (iterations done,
+// in FOCT_PROGRESS_BINS-ths of the run); -1: both chains finished.  Who yields:
+//   K.slice_hist == nullptr (CTA-level items): whoever finds another item waiting (round robin);
+//   else: only a unit that is AHEAD, in iterations done, of some unit that waits.  Fits differ in cost by up to 40 %;
+//   keeping them level in iterations instead of in gradient evaluations lets them all finish together, so the expensive
+//   fits are not left to run alone at the end (an online approximation of longest-remaining-time-first).
+#define FOCT_PROGRESS_BINS 64
 template <int NN, int MOD, int GB>
-__device__ bool run_pair(const SamplerParams& K, const DevProblem& P, const double* __restrict__ blob, int prob,
+__device__ int run_pair(const SamplerParams& K, const DevProblem& P, const double* __restrict__ blob, int prob,
                          int chain, int lane32, double* __restrict__ sv, bool resume, int n_items,
-                         const double* __restrict__ gbasis) {  // GB = 1: blob 0 (global); GB = 2: the CTA's copy of the basis rows
+                         const double* __restrict__ gbasis) {  // GB: blob 0, whose basis rows every profile of the batch shares
   using DM = Dims<NN>;
   constexpr int D = DM::D;
   constexpr int P_OUT = DM::P_OUT;
@@ -185,10 +191,28 @@ __device__ bool run_pair(const SamplerParams& K, const DevProblem& P, const doub
     __syncwarp();
 #ifndef FOCT_TEST_NO_SUSPEND
     if (sv && ticks >= K.slice_ticks) {
-      // end of the slice: give the CTA up only if a work item is waiting for one
+      // end of the slice
       const unsigned head = *reinterpret_cast<const volatile unsigned*>(K.slice_ctl);
       const unsigned pushed = *reinterpret_cast<const volatile unsigned*>(K.slice_ctl + 1);
-      if (head < (unsigned)n_items + pushed) {
+      bool yield = head < (unsigned)n_items + pushed;  // somebody waits
+      int bin = 0;
+      if (K.slice_hist) {
+        int f = mode == PM_DONE ? 0x7fffffff : it;
+        f = min(f, __shfl_xor_sync(FOCT_FULL, f, 16));
+        bin = min((int)(((long long)f * FOCT_PROGRESS_BINS) / max(K.n_iter, 1)), FOCT_PROGRESS_BINS - 1);
+        if (yield) {
+          // the least advanced waiting unit: one that has not started yet (bin 0), else the lowest occupied bin
+          int qmin = 0;
+          if (head >= (unsigned)n_items) {
+            const int h0 = *reinterpret_cast<const volatile int*>(K.slice_hist + lane32);
+            const int h1 = *reinterpret_cast<const volatile int*>(K.slice_hist + 32 + lane32);
+            const unsigned b0 = __ballot_sync(FOCT_FULL, h0 > 0), b1 = __ballot_sync(FOCT_FULL, h1 > 0);
+            qmin = b0 ? __ffs((int)b0) - 1 : (b1 ? 32 + __ffs((int)b1) - 1 : FOCT_PROGRESS_BINS);
+          }
+          yield = bin > qmin;
+        }
+      }
+      if (yield) {
         double* s = sv + lane32;
 #define X(v) __stcg(s, (double)v); s += 32;
         FOCT_PAIR_DOUBLES(X)
@@ -204,7 +228,8 @@ __device__ bool run_pair(const SamplerParams& K, const DevProblem& P, const doub
           __stcg(s + 128, st_gp[k]); __stcg(s + 160, st_lsw[k]); __stcg(s + 192, st_V[k]); __stcg(s + 224, st_c2[k]);
           __stcg(s + 256, st_H[k]);
         }
-        return false;
+        __threadfence();
+        return bin;
       }
       ticks = 0;
     }
@@ -252,7 +277,7 @@ __device__ bool run_pair(const SamplerParams& K, const DevProblem& P, const doub
       mode = PM_EPS_EVAL;
     }
     __syncwarp();
-    if (__all_sync(FOCT_FULL, mode == PM_DONE)) return true;
+    if (__all_sync(FOCT_FULL, mode == PM_DONE)) return -1;
 
     // ================================================================ one leapfrog step, both chains together
     {
@@ -464,71 +489,21 @@ __device__ bool run_pair(const SamplerParams& K, const DevProblem& P, const doub
 #ifndef FOCT_PAIR_MINB_GB
 #define FOCT_PAIR_MINB_GB 6
 #endif
-// GB = 2: a CTA is FOCT_PAIR_SUBS independent sub-CTAs of two warps.  Each works through items exactly like a CTA of
-// the other variants (own staged cx | y | w rows, own mbarrier, named barrier 1 + sub); what they share is ONE copy of the
-// basis rows in shared memory, loaded once per CTA, so that the sweep's basis loads are LDS instead of LDG through L1
-// (the L1 path was the co-bottleneck of the GB = 1 kernel: doubling its loads cost 18 %, profiles/r2_kernel_experiments.txt)
-// while twelve warps still share an SM: 2 CTAs x (NN x Npad x 8 + 3 x 12 KB) = 152 KB at Nn = 10, N = 481.
-#ifndef FOCT_PAIR_SUBS
-#define FOCT_PAIR_SUBS 3
-#endif
-#ifndef FOCT_PAIR_MINB_GS
-#define FOCT_PAIR_MINB_GS 2
-#endif
-
-__device__ __forceinline__ void sub_sync(int sub, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(sub + 1), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ int sub_sync_and(int sub, int nthreads, int pred) {
-  int r;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.s32 p, %1, 0;\n\t"
-      "bar.red.and.pred q, %2, %3, p;\n\t"
-      "selp.s32 %0, 1, 0, q;\n\t}"
-      : "=r"(r)
-      : "r"(pred), "r"(sub + 1), "r"(nthreads)
-      : "memory");
-  return r;
-}
-
 template <int NN, int MOD, int GB>
-__global__ void __launch_bounds__(16 * FOCT_PAIR_CTA_CHAINS * (GB == 2 ? FOCT_PAIR_SUBS : 1),
-                                  GB == 2 ? FOCT_PAIR_MINB_GS : (GB == 1 ? FOCT_PAIR_MINB_GB : FOCT_PAIR_MINB))
+__global__ void __launch_bounds__(16 * FOCT_PAIR_CTA_CHAINS, GB ? FOCT_PAIR_MINB_GB : FOCT_PAIR_MINB)
 nuts2_kernel(const SamplerParams K) {
-  constexpr int SUBS = GB == 2 ? FOCT_PAIR_SUBS : 1;
-  const int SUB_THREADS = (int)blockDim.x / SUBS;  // 64, or 32 when a profile has at most two chains
-  extern __shared__ __align__(128) double smem_all[];
-  __shared__ uint64_t mbar[SUBS + 1];
-  __shared__ int s_next[SUBS], s_resume[SUBS];
-  __shared__ DevProblem s_prob[SUBS];
-  const int sub = GB == 2 ? (int)threadIdx.x / SUB_THREADS : 0;
-  const int tid = (int)threadIdx.x - sub * SUB_THREADS;
-  const int lane = tid & 31, warp = tid >> 5;
-  const bool leader = tid == 0;
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t mbar;
+  __shared__ int s_next, s_resume;
+  __shared__ DevProblem s_prob;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool leader = threadIdx.x == 0;
   const int groups = (K.chains + FOCT_PAIR_CTA_CHAINS - 1) / FOCT_PAIR_CTA_CHAINS;
   const int n_items = K.n_problems * groups;
   const bool sliced = K.slice_state != nullptr;
   constexpr int CTA_WARPS = FOCT_PAIR_CTA_CHAINS / 2;
-  // shared memory: [basis rows, NN x npad (GB = 2 only)] [sub 0: staged rows / blob] [sub 1] ...
-  const double* gbasis = GB == 1 ? K.blobs : nullptr;
-  double* smem = smem_all;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i <= SUBS; ++i) {
-      const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(&mbar[i]);
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (GB == 2) {
-    // the basis rows of blob 0 (rows 3 .. 3 + NN of every 32-point block), once per CTA
-    uint32_t ph = 0;
-    stage_rows_tma(smem_all, K.blobs + 3 * 32, K.npad / 32, 3 + NN, NN, &mbar[SUBS], ph, threadIdx.x == 0);
-    gbasis = smem_all;
-    smem = smem_all + (size_t)NN * K.npad + (size_t)sub * 3 * K.npad;
-    __syncthreads();
-  }
+  const double* gbasis = GB ? K.blobs : nullptr;  // blob 0: the basis every profile of the batch shares
+  mbar_init(&mbar);
   uint32_t phase = 0;
   for (;;) {
     if (leader) {
@@ -552,37 +527,116 @@ nuts2_kernel(const SamplerParams K) {
           __threadfence();
         }
       }
-      s_next[sub] = w; s_resume[sub] = res;
+      s_next = w; s_resume = res;
     }
-    sub_sync(sub, SUB_THREADS);
-    const int w = s_next[sub];
-    const bool resume = s_resume[sub] != 0;
+    __syncthreads();
+    const int w = s_next;
+    const bool resume = s_resume != 0;
     if (w < 0) break;
     const int j = K.order ? K.order[w / groups] : w / groups;
     const int chain = (w % groups) * FOCT_PAIR_CTA_CHAINS + 2 * warp + (lane >> 4);
-    if (leader) s_prob[sub] = K.probs[j];
-    if (GB) stage_rows_tma(smem, K.blobs + (size_t)j * K.blob_stride, K.npad / 32, 3 + NN, 3, &mbar[sub], phase, leader);
-    else stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar[sub], phase, leader);
-    sub_sync(sub, SUB_THREADS);
+    if (leader) s_prob = K.probs[j];
+    if (GB) stage_rows_tma(smem, K.blobs + (size_t)j * K.blob_stride, K.npad / 32, 3 + NN, 3, &mbar, phase, leader);
+    else stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase, leader);
+    __syncthreads();
     // a warp runs if at least its first half has a chain
     bool fin = true;
     if ((w % groups) * FOCT_PAIR_CTA_CHAINS + 2 * warp < K.chains) {
       double* sv = sliced ? K.slice_state + ((size_t)w * CTA_WARPS + warp) * (FOCT_PAIR_STATE_DOUBLES * 32) : nullptr;
       int* wdone = sliced ? K.slice_done + (size_t)w * CTA_WARPS + warp : nullptr;
       if (!(resume && __ldcg(wdone) != 0)) {
-        fin = run_pair<NN, MOD, GB>(K, s_prob[sub], smem, j, chain, lane, sv, resume, n_items, gbasis);
+        fin = run_pair<NN, MOD, GB>(K, s_prob, smem, j, chain, lane, sv, resume, n_items, gbasis) < 0;
         if (sliced && lane == 0) __stcg(wdone, fin ? 1 : 0);
       }
     }
-    const int all_fin = sub_sync_and(sub, SUB_THREADS, fin ? 1 : 0);
+    const int all_fin = __syncthreads_and(fin ? 1 : 0);
     if (sliced && leader) {
       if (all_fin) {
         atomicAdd(K.slice_ctl + 2, 1u);
       } else {
-        __threadfence();  // the state stored by this sub-CTA's warps before the barrier is visible before the queue entry is
+        __threadfence();  // the state stored by this CTA's warps before the barrier is visible before the queue entry is
         const unsigned p = atomicAdd(K.slice_ctl + 1, 1u);
         *reinterpret_cast<volatile unsigned long long*>(K.slice_queue + p % (unsigned)n_items) =
             ((unsigned long long)((unsigned)n_items + p) << 32) | (unsigned)w;
+      }
+    }
+  }
+}
+
+// The shared-basis kernel with WARPS as the scheduling unit.  A work unit is (profile, pair of chains); each warp claims
+// units on its own, stages the cx | y | w rows of its profile into its own 12 KB of shared memory (own mbarrier, TMA
+// issued by lane 0), and runs, suspends and resumes them exactly like a CTA of nuts2_kernel does with an item — but
+// without any CTA-wide barrier: the two warps of a CTA share nothing but the SM.  Against CTA-level items this removes
+// the wait of a profile's faster pair for its slower one (the four chains of a profile differ by ~5 % in gradient
+// evaluations) and lets the time slicing act per pair.
+//   ctl[0] tickets | ctl[1] pushes | ctl[2] units finished      (as in nuts2_kernel, with units for items)
+template <int NN, int MOD>
+__global__ void __launch_bounds__(64, FOCT_PAIR_MINB_GB) nuts2w_kernel(const SamplerParams K) {
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t mbar[2];
+  __shared__ DevProblem s_prob[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool leader = lane == 0;
+  const int upp = (K.chains + 1) / 2;  // units (chain pairs) per profile
+  const int n_units = K.n_problems * upp;
+  const bool sliced = K.slice_state != nullptr;
+  double* rows = smem + (size_t)warp * 3 * K.npad;
+  if (leader) {
+    const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(&mbar[warp]);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t phase = 0;
+  for (;;) {
+    int u = -1, res = 0;
+    if (leader) {
+      if (!sliced) {
+        u = atomicAdd(K.work_counter, 1);
+        if (u >= n_units) u = -1;
+      } else {
+        const unsigned t = atomicAdd(K.slice_ctl, 1u);
+        if (t < (unsigned)n_units) {
+          u = (int)t;
+        } else {
+          // wait for the push this ticket stands for, or for the last unit to finish
+          const volatile unsigned long long* slot = K.slice_queue + (t - (unsigned)n_units) % (unsigned)n_units;
+          for (;;) {
+            const unsigned long long v = *slot;
+            if ((unsigned)(v >> 32) == t) {
+              u = (int)((v & 0xffffffffu) >> 6); res = 1;
+              if (K.slice_hist) atomicSub(K.slice_hist + (int)(v & 63u), 1);  // no longer waiting
+              break;
+            }
+            if (*reinterpret_cast<const volatile unsigned*>(K.slice_ctl + 2) >= (unsigned)n_units) break;
+            __nanosleep(2000);
+          }
+          __threadfence();
+        }
+      }
+    }
+    u = __shfl_sync(FOCT_FULL, u, 0);
+    res = __shfl_sync(FOCT_FULL, res, 0);
+    if (u < 0) break;
+    const int r = u / upp, pair = u - r * upp;
+    const int j = K.order ? K.order[r] : r;
+    const int chain = 2 * pair + (lane >> 4);
+    if (leader) s_prob[warp] = K.probs[j];
+    stage_rows_tma(rows, K.blobs + (size_t)j * K.blob_stride, K.npad / 32, 3 + NN, 3, &mbar[warp], phase, leader);
+    __syncwarp();
+    double* sv = sliced ? K.slice_state + (size_t)u * (FOCT_PAIR_STATE_DOUBLES * 32) : nullptr;
+    const int bin = run_pair<NN, MOD, 1>(K, s_prob[warp], rows, j, chain, lane, sv, res != 0, n_units, K.blobs);
+    __syncwarp();
+    if (sliced && leader) {
+      if (bin < 0) {
+        atomicAdd(K.slice_ctl + 2, 1u);
+      } else {
+        __threadfence();  // the state stored by this warp's lanes (before the __syncwarp) is visible before the queue entry is
+        if (K.slice_hist) atomicAdd(K.slice_hist + bin, 1);
+        const unsigned p = atomicAdd(K.slice_ctl + 1, 1u);
+        // (unit << 6 | progress bin: whoever takes the unit removes it from the histogram of the waiting ones)
+        *reinterpret_cast<volatile unsigned long long*>(K.slice_queue + p % (unsigned)n_units) =
+            ((unsigned long long)((unsigned)n_units + p) << 32) | ((unsigned)u << 6) | (unsigned)bin;
       }
     }
   }

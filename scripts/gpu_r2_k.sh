@@ -1,0 +1,23 @@
+#!/bin/bash
+# round-2 GPU check K: tail points by the lane group, SBC on both kernels, run-to-run spread of the sliced 1000-profile step
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out; rm -f gpurun_out/parity_metrics.jsonl
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/k_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/k_smoke.log
+timeout 900 python -m pytest tests -m gpu -q --timeout 240 --timeout-method thread > gpurun_out/k_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/k_pytest.log
+tail -8 gpurun_out/k_pytest.log
+timeout 400 python tests/perf/sbc_probe.py 77 78 79 > gpurun_out/k_sbc.txt 2>&1; echo "sbc rc=$?"; cat gpurun_out/k_sbc.txt
+run() { name=$1; shift; env "$@" timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --rhat-target 0 $BARGS > gpurun_out/k_bench_$name.json 2> gpurun_out/k_bench_$name.err; }
+BARGS="--profiles 1776" run tail_1776 FOCT_SLICE_TICKS=0
+BARGS="--profiles 1776" run tail_1776_sliced A=1
+BARGS="" run tail_1000_a A=1
+BARGS="--seed 99" run tail_1000_b A=1
+BARGS="--profiles 444" run one_444 A=1
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/k_bench_*.json")):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split("k_bench_")[1], "ms", round(d["ms_per_step"],1), "grad/s %.3e"%d["grad_per_s"], "frac %.3f"%d["roofline"]["frac"], "ess/s %.0f"%d["value"], d["roofline"]["launch"], "rhat_max %.3f"%d["quality"]["rhat_max"])
+    except Exception as e:
+        print(f, "failed", e, open(f.replace(".json",".err")).read()[-300:])
+PY

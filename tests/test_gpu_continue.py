@@ -192,9 +192,21 @@ def test_time_sliced_work_items_are_bit_identical(L, monkeypatch, ticks):
     for k in ("draws", "sampler_params", "summary", "stepsize", "inv_metric", "last_q", "n_leapfrog", "n_divergent"):
         np.testing.assert_array_equal(sliced[k], plain[k], err_msg=k)
     assert plain["n_leapfrog"].sum() > 20 * ticks * n   # the fits were long enough to be suspended many times
-    # the other two variants of the kernel: basis read through L1 (the fallback when the shared-memory copy does not
-    # fit), and the whole blob staged per item (ragged depth grids: no shared basis).  All three sum in the same order.
-    for env in ({"FOCT_BASIS_MODE": "1"}, {"FOCT_NO_SHARED_BASIS": "1"}):
+    # plain round robin instead of the progress-aware rule (who yields does not change what a fit computes)
+    monkeypatch.setenv("FOCT_SLICE_PRIO", "0")
+    rr = L.sample(0, b, n, spec, cfg)
+    monkeypatch.delenv("FOCT_SLICE_PRIO")
+    for k in ("draws", "sampler_params", "stepsize", "n_leapfrog"):
+        np.testing.assert_array_equal(rr[k], plain[k], err_msg=k)
+    # CTA-level work items (the scheduling of the staged-blob variant) on the shared-basis kernel
+    monkeypatch.setenv("FOCT_CTA_ITEMS", "1")
+    ci = L.sample(0, b, n, spec, cfg)
+    monkeypatch.delenv("FOCT_CTA_ITEMS")
+    for k in ("draws", "sampler_params", "stepsize", "n_leapfrog"):
+        np.testing.assert_array_equal(ci[k], plain[k], err_msg=k)
+    # the other variant of the kernel: the whole blob staged per item (ragged depth grids: no shared basis); it sums in
+    # the same order
+    for env in ({"FOCT_NO_SHARED_BASIS": "1"},):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         monkeypatch.setenv("FOCT_SLICE_TICKS", "0")
