@@ -47,8 +47,8 @@ __device__ __forceinline__ bool merge_persists_w(double invM, double i_rho, doub
   X(e_site) X(n_leap) X(n) X(n_leaves) X(mode)
 #define FOCT_PAIR_N_DOUBLES 41
 #define FOCT_PAIR_N_INTS 15
-// doubles per lane of a saved warp: the scalars above, the ints packed two to a double, nine stack arrays
-#define FOCT_PAIR_STATE_DOUBLES (FOCT_PAIR_N_DOUBLES + (FOCT_PAIR_N_INTS + 1) / 2 + 9 * FOCT_STACK_LEVELS)
+// doubles per lane of a saved warp: the scalars above, the ints packed two to a double, six stack arrays
+#define FOCT_PAIR_STATE_DOUBLES (FOCT_PAIR_N_DOUBLES + (FOCT_PAIR_N_INTS + 1) / 2 + 6 * FOCT_STACK_LEVELS)
 
 // lane32 = lane in the warp; this half's chain is `chain` (>= K.chains: the half has no chain and only keeps the other
 // half company in the gradient evaluations).
@@ -125,7 +125,10 @@ __device__ int run_pair(const SamplerParams& K, const DevProblem& P, const doubl
   // pending "init" subtrees, one slot per level (local memory; touched only at merges)
   double st_rho[FOCT_STACK_LEVELS], st_pbeg[FOCT_STACK_LEVELS], st_pend[FOCT_STACK_LEVELS];
   double st_qp[FOCT_STACK_LEVELS], st_gp[FOCT_STACK_LEVELS];
-  double st_lsw[FOCT_STACK_LEVELS], st_V[FOCT_STACK_LEVELS], st_c2[FOCT_STACK_LEVELS], st_H[FOCT_STACK_LEVELS];
+  // the four scalars of a pending subtree (log weight, potential, chi2, H of its proposal: uniform over the half) share ONE
+  // per-lane slot — lane 0 keeps lsw, lane 1 V, lane 2 c2, lane 3 H — instead of four replicated ones: a third less
+  // local-memory traffic per leaf (the subtree stack is what misses L1: profiles/r2_ncu_nuts2w_summary.txt)
+  double st_sc[FOCT_STACK_LEVELS];
 
 #ifndef FOCT_TEST_NO_RESUME
   if (resume) {
@@ -140,10 +143,9 @@ __device__ int run_pair(const SamplerParams& K, const DevProblem& P, const doubl
 #undef X
     s = sv + (FOCT_PAIR_N_DOUBLES + (FOCT_PAIR_N_INTS + 1) / 2) * 32 + lane32;
 #pragma unroll 1
-    for (int k = 0; k < FOCT_STACK_LEVELS; ++k, s += 9 * 32) {
+    for (int k = 0; k < FOCT_STACK_LEVELS; ++k, s += 6 * 32) {
       st_rho[k] = __ldcg(s); st_pbeg[k] = __ldcg(s + 32); st_pend[k] = __ldcg(s + 64); st_qp[k] = __ldcg(s + 96);
-      st_gp[k] = __ldcg(s + 128); st_lsw[k] = __ldcg(s + 160); st_V[k] = __ldcg(s + 192); st_c2[k] = __ldcg(s + 224);
-      st_H[k] = __ldcg(s + 256);
+      st_gp[k] = __ldcg(s + 128); st_sc[k] = __ldcg(s + 160);
     }
   } else
 #endif
@@ -223,10 +225,9 @@ __device__ int run_pair(const SamplerParams& K, const DevProblem& P, const doubl
 #undef X
         s = sv + (FOCT_PAIR_N_DOUBLES + (FOCT_PAIR_N_INTS + 1) / 2) * 32 + lane32;
 #pragma unroll 1
-        for (int k = 0; k < FOCT_STACK_LEVELS; ++k, s += 9 * 32) {
+        for (int k = 0; k < FOCT_STACK_LEVELS; ++k, s += 6 * 32) {
           __stcg(s, st_rho[k]); __stcg(s + 32, st_pbeg[k]); __stcg(s + 64, st_pend[k]); __stcg(s + 96, st_qp[k]);
-          __stcg(s + 128, st_gp[k]); __stcg(s + 160, st_lsw[k]); __stcg(s + 192, st_V[k]); __stcg(s + 224, st_c2[k]);
-          __stcg(s + 256, st_H[k]);
+          __stcg(s + 128, st_gp[k]); __stcg(s + 160, st_sc[k]);
         }
         __threadfence();
         return bin;
@@ -305,7 +306,8 @@ __device__ int run_pair(const SamplerParams& K, const DevProblem& P, const doubl
         int mb_group = -1;
         for (; (n >> k) & 1u; ++k) {
           double prob_final;
-          const double lsw_sub = lse_prob(st_lsw[k], c_lsw, prob_final);
+          const double i_sc = st_sc[k];
+          const double lsw_sub = lse_prob(bcast<W>(i_sc, 0, hm), c_lsw, prob_final);
           // one Philox block serves the merges of four consecutive levels at this leaf (32-bit uniforms)
           if ((k >> 2) != mb_group) {
             mb_group = k >> 2;
@@ -315,14 +317,17 @@ __device__ int run_pair(const SamplerParams& K, const DevProblem& P, const doubl
           const bool take_final = ((double)w + 0.5) * 0x1.0p-32 < prob_final;
           const double i_rho = st_rho[k], i_pbeg = st_pbeg[k], i_pend = st_pend[k];
           const bool persist = merge_persists_w<W>(invM, i_rho, i_pbeg, i_pend, c_rho, c_pbeg, c_pend, lane, hm);
-          if (!take_final) { c_qp = st_qp[k]; c_gp = st_gp[k]; c_V = st_V[k]; c_c2 = st_c2[k]; c_H = st_H[k]; }
+          if (!take_final) {
+            c_qp = st_qp[k]; c_gp = st_gp[k];
+            c_V = bcast<W>(i_sc, 1, hm); c_c2 = bcast<W>(i_sc, 2, hm); c_H = bcast<W>(i_sc, 3, hm);
+          }
           c_lsw = lsw_sub; c_rho = i_rho + c_rho; c_pbeg = i_pbeg;
           if (!persist) { valid = false; break; }
         }
       }
       if (valid && n + 1 < n_leaves) {
         st_rho[k] = c_rho; st_pbeg[k] = c_pbeg; st_pend[k] = c_pend; st_qp[k] = c_qp; st_gp[k] = c_gp;
-        st_lsw[k] = c_lsw; st_V[k] = c_V; st_c2[k] = c_c2; st_H[k] = c_H;
+        st_sc[k] = lane == 0 ? c_lsw : (lane == 1 ? c_V : (lane == 2 ? c_c2 : c_H));
         ++n;
       } else {
         // ---- end of this doubling

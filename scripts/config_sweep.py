@@ -1,6 +1,6 @@
 """BASELINE.json configs[0..3] on one B200: MonoExp sampled, single ExpGP profile, Nn sweep 5..20 (fitted-form uy)."""
 import json, sys, time
-sys.path.insert(0, "/root/repo")
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from fitoct_b200 import _abi as abi, _lib as L, synth
 res = {}
