@@ -24,7 +24,7 @@ EXPORTS = (
     "foct_plan_sync", "foct_plan_timing", "foct_plan_fetch", "foct_plan_destroy", "foct_fp64_peak",
     "foct_estimate_noise", "foct_birge_ci", "foct_print_br", "foct_estimate_exp_prior", "foct_pipeline_cfg_default",
     "foct_pipeline", "foct_vb_cfg_default", "foct_vb", "foct_release_cache",
-    "foct_sample_cb", "foct_plan_query", "foct_plan_cancel", "foct_expgp_logp_grad", "foct_plan_launches",
+    "foct_sample_cb", "foct_plan_query", "foct_plan_cancel", "foct_expgp_logp_grad", "foct_plan_launches", "foct_summary",
 )
 
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_double, C.c_char_p, C.c_void_p)
@@ -70,6 +70,7 @@ def lib():
         L.foct_monoexp_map.argtypes = [PP, C.c_int, MS, dp, dp, dp, dp, ip]
         L.foct_expgp_map.argtypes = [PP, C.c_int, MS, dp, dp, dp, ip]
         L.foct_predict.argtypes = [C.c_int, PP, MS, dp, C.c_int, dp, dp, dp]
+        L.foct_summary.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, dp]
         L.foct_plan_create.argtypes = [C.c_int, PP, C.c_int, MS, SC, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.foct_plan_run.argtypes = [C.c_void_p, C.c_ulonglong]
         L.foct_plan_sync.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -279,6 +280,18 @@ def predict(kind, batch, j, spec, draws):
     check(lib().foct_predict(kind, C.byref(batch.array[j]), C.byref(spec), abi.as_ptr(draws), n, abi.as_ptr(m),
                              abi.as_ptr(r), abi.as_ptr(dl)))
     return m, r, dl
+
+
+def summary(draws):
+    """rstan's summary(fit)$summary for draws[n_draws, chains, n_cols] (or [n_sets, n_draws, chains, n_cols]) on the device."""
+    d = np.ascontiguousarray(draws, dtype=np.float64)
+    single = d.ndim == 3
+    if single:
+        d = d[None]
+    n_sets, n, c, p = d.shape
+    out = np.empty((n_sets, p, abi.FOCT_N_SUMMARY_COLS))
+    check(lib().foct_summary(abi.as_ptr(d), n_sets, n, c, p, abi.as_ptr(out)))
+    return out[0] if single else out
 
 
 def fp64_peak(device: int = 0):

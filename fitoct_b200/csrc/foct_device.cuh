@@ -280,6 +280,29 @@ struct Dims {
   static constexpr int KP = D <= 8 ? 8 : (D <= 16 ? 16 : 32);
 };
 
+// FOCT_EXPTAB_SMEM: the sweeps read the 2^(j/32) table of exp() from a per-CTA copy in shared memory (every kernel that
+// evaluates the model calls fill_exptab() first) instead of through L1 from global memory: two integer instructions less
+// per point, a shorter and steadier latency on the critical path of the point, and the L1 request path — the co-bottleneck
+// of the sampling kernels — is left to the basis rows.  Measured on nuts2w_kernel: +3.1 % gradients/s at full waves, 1000
+// profiles 4.21 s -> 4.08 s, bit-identical draws (profiles/r2_kernel_experiments.txt).
+#ifndef FOCT_EXPTAB_SMEM
+#define FOCT_EXPTAB_SMEM 1
+#endif
+__shared__ double s_exptab[32];
+__device__ __forceinline__ void fill_exptab() {
+#if FOCT_EXPTAB_SMEM
+  if (threadIdx.x < 32) s_exptab[threadIdx.x] = FEXP_TAB[threadIdx.x];
+  __syncthreads();  // (blocks are a whole number of warps; one-warp blocks included)
+#endif
+}
+__device__ __forceinline__ double exptab(int n) {
+#if FOCT_EXPTAB_SMEM
+  return s_exptab[n & 31];
+#else
+  return __ldg(&FEXP_TAB[n & 31]);
+#endif
+}
+
 // U data points of the sweep processed in LOCKSTEP, statement by statement (ptxas keeps source order inside a
 // basic block, so writing the U independent dependency chains interleaved is what actually puts U chains in
 // flight; two inlined copies of a one-point body were scheduled back to back — profiles/r1_ncu_nuts_v2).
@@ -385,7 +408,7 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
 #pragma unroll
   for (int u = 0; u < U; ++u) tt[u] = fma(-t[u], FEXPT_L2E32, FEXP_MAGIC);
 #pragma unroll
-  for (int u = 0; u < U; ++u) { nd[u] = tt[u] - FEXP_MAGIC; n[u] = __double2loint(tt[u]); tj[u] = __ldg(&FEXP_TAB[n[u] & 31]); }
+  for (int u = 0; u < U; ++u) { nd[u] = tt[u] - FEXP_MAGIC; n[u] = __double2loint(tt[u]); tj[u] = exptab(n[u]); }
 #pragma unroll
   for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXPT_NHI, -t[u]);
 #pragma unroll
@@ -459,6 +482,104 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
 
 #undef FOCT_PT
 #undef FOCT_PTG
+
+// Software-pipelined form of the half-warp / shared-basis sweep (W = 16, GB = 1, two points per lane, length modulation):
+// the basis rows of a block arrive in `bb` (loaded one iteration AHEAD), and each row of the NEXT block is requested right
+// after its last use in the transposed accumulation, so the L1 latency of the ten 128-bit basis loads is covered by the
+// tail of this iteration instead of being exposed at the head of the next one (ncu: "long scoreboard" was the second
+// largest stall of nuts2w_kernel, 1.0-1.7 cycles per issued instruction).  Same arithmetic in the same order as
+// sweep_points<..., U = 2, W = 16, GB = 1>: bit-identical results.
+#ifndef FOCT_PREFETCH
+#define FOCT_PREFETCH 1
+#endif
+template <int NN, int KP, int ZI>
+__device__ __forceinline__ void sweep_points_pf(const double* __restrict__ pp, const double* __restrict__ pgn, double th1,
+                                                double th2, double th3, const double (&yg)[NN], double (&acc)[KP],
+                                                double2 (&bb)[NN]) {
+  constexpr int U = 2;
+  double dl0[U], dl1[U], cx[U], y[U], ws[U], r[U], t[U], a[U], x0[U], e0[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) { dl0[u] = 1.0; dl1[u] = 0.0; }  // s = 1 + dL: the 1 rides in the first partial sum
+#pragma unroll
+  for (int k = 0; k < NN; ++k) {
+    if (k & 1) { dl1[0] = fma(bb[k].x, yg[k], dl1[0]); dl1[1] = fma(bb[k].y, yg[k], dl1[1]); }
+    else { dl0[0] = fma(bb[k].x, yg[k], dl0[0]); dl0[1] = fma(bb[k].y, yg[k], dl0[1]); }
+  }
+  {
+    const double2 c2 = *reinterpret_cast<const double2*>(pp);
+    const double2 y2 = *reinterpret_cast<const double2*>(pp + 32);
+    const double2 w2 = *reinterpret_cast<const double2*>(pp + 64);
+    cx[0] = c2.x; cx[1] = c2.y; y[0] = y2.x; y[1] = y2.y; ws[0] = w2.x; ws[1] = w2.y;
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    a[u] = th3 * (dl0[u] + dl1[u]);
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0[u]) : "d"(a[u]));
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) e0[u] = fma(-a[u], x0[u], 1.0);
+#pragma unroll
+  for (int u = 0; u < U; ++u) e0[u] = fma(e0[u], e0[u], e0[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) r[u] = fma(x0[u], e0[u], x0[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) t[u] = cx[u] * r[u];
+  double tt[U], nd[U], rr[U], pe[U], tj[U], e[U];
+  int n[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) tt[u] = fma(-t[u], FEXPT_L2E32, FEXP_MAGIC);
+#pragma unroll
+  for (int u = 0; u < U; ++u) { nd[u] = tt[u] - FEXP_MAGIC; n[u] = __double2loint(tt[u]); tj[u] = exptab(n[u]); }
+#pragma unroll
+  for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXPT_NHI, -t[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) rr[u] = fma(nd[u], FEXP_K[0], rr[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) pe[u] = fma(rr[u], FEXPT_C6, FEXPT_C5);
+#pragma unroll
+  for (int u = 0; u < U; ++u) pe[u] = fma(pe[u], rr[u], FEXP_K[2]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) pe[u] = fma(pe[u], rr[u], FEXP_K[1]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) pe[u] = fma(pe[u], rr[u], 0.5);
+#pragma unroll
+  for (int u = 0; u < U; ++u) pe[u] = fma(pe[u], rr[u], 1.0);
+#pragma unroll
+  for (int u = 0; u < U; ++u) pe[u] = fma(pe[u], rr[u], 1.0);
+#pragma unroll
+  for (int u = 0; u < U; ++u) e[u] = fexp_scale(pe[u] * tj[u], n[u], __double2hiint(t[u]) ^ 0x80000000);
+  double m[U], z[U], gi[U], ge[U], gt[U], qq[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) m[u] = fma(th2, e[u], th1);
+#pragma unroll
+  for (int u = 0; u < U; ++u) z[u] = (y[u] - m[u]) * ws[u];
+#pragma unroll
+  for (int u = 0; u < U; ++u) gi[u] = z[u] * ws[u];
+#pragma unroll
+  for (int u = 0; u < U; ++u) ge[u] = gi[u] * e[u];
+#pragma unroll
+  for (int u = 0; u < U; ++u) gt[u] = ge[u] * t[u];
+#pragma unroll
+  for (int u = 0; u < U; ++u) qq[u] = gt[u] * r[u];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    acc[ZI] = fma(z[u], z[u], acc[ZI]);
+    acc[0] += gi[u];
+    acc[1] += ge[u];
+    acc[2] += gt[u];
+  }
+  // transposed accumulation, two rows at a time so that the two dependent updates of an accumulator are not adjacent;
+  // a row's registers are refilled for the next block as soon as both of its points are consumed
+#pragma unroll
+  for (int k = 0; k < NN; k += 2) {
+    acc[3 + k] = fma(qq[0], bb[k].x, acc[3 + k]);
+    if (k + 1 < NN) acc[4 + k] = fma(qq[0], bb[k + 1].x, acc[4 + k]);
+    acc[3 + k] = fma(qq[1], bb[k].y, acc[3 + k]);
+    if (k + 1 < NN) acc[4 + k] = fma(qq[1], bb[k + 1].y, acc[4 + k]);
+    bb[k] = __ldg(reinterpret_cast<const double2*>(pgn + (3 + k) * 32));
+    if (k + 1 < NN) bb[k + 1] = __ldg(reinterpret_cast<const double2*>(pgn + (4 + k) * 32));
+  }
+}
 
 // Fused sweep over the staged profile.  qd = this lane's component of q.  Everything a lane needs from
 // the other lanes is fetched with shuffles up front; the per-point loop touches only shared memory and
@@ -575,14 +696,25 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
 #define FOCT_UNROLL16_GB 2
 #endif
       constexpr int U16 = NN <= 11 ? (GB ? FOCT_UNROLL16_GB : FOCT_UNROLL16) : 2;
-      if (U16 > 2) {
+      if constexpr (FOCT_PREFETCH && GB && MOD == 0 && NN > 0 && NN <= 11 && U16 == 2 && FOCT_PAIR_LDS128) {
+        double2 bb[NN];
+#pragma unroll
+        for (int k = 0; k < NN; ++k) bb[k] = __ldg(reinterpret_cast<const double2*>(pg + (3 + k) * 32));
 #pragma unroll 1
-        for (; pass + U16 / 2 <= npass; pass += U16 / 2, pp += (U16 / 2) * ROWS * 32, pg += (U16 / 2) * GROWS * 32)
-          sweep_points<NN, MOD, KP, ZI, U16, W, GB>(pp, th1, th2, th3, r3, yg, acc, pg);
+        for (; pass < npass; ++pass, pp += ROWS * 32) {
+          if (pass + 1 < npass) pg += GROWS * 32;  // the last iteration re-requests its own block: harmless, stays in bounds
+          sweep_points_pf<NN, KP, ZI>(pp, pg, th1, th2, th3, yg, acc, bb);
+        }
+      } else {
+        if (U16 > 2) {
+#pragma unroll 1
+          for (; pass + U16 / 2 <= npass; pass += U16 / 2, pp += (U16 / 2) * ROWS * 32, pg += (U16 / 2) * GROWS * 32)
+            sweep_points<NN, MOD, KP, ZI, U16, W, GB>(pp, th1, th2, th3, r3, yg, acc, pg);
+        }
+#pragma unroll 1
+        for (; pass < npass; ++pass, pp += ROWS * 32, pg += GROWS * 32)
+          sweep_points<NN, MOD, KP, ZI, 2, W, GB>(pp, th1, th2, th3, r3, yg, acc, pg);
       }
-#pragma unroll 1
-      for (; pass < npass; ++pass, pp += ROWS * 32, pg += GROWS * 32)
-        sweep_points<NN, MOD, KP, ZI, 2, W, GB>(pp, th1, th2, th3, r3, yg, acc, pg);
     } else {
       if (UNROLL >= 2) {
 #pragma unroll 1

@@ -13,6 +13,7 @@ namespace foct {
 template <int NN, int MOD>
 __global__ void __launch_bounds__(128) logp_kernel(const LogpParams K) {
   extern __shared__ __align__(128) double smem[];
+  fill_exptab();
   __shared__ uint64_t mbar;
   __shared__ DevProblem s_prob;
   constexpr int D = Dims<NN>::D;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(128) logp_kernel(const LogpParams K) {
 template <int NN, int MOD>
 __global__ void __launch_bounds__(32) map_bfgs_kernel(const MapParams K) {
   extern __shared__ __align__(128) double smem[];
+  fill_exptab();
   __shared__ uint64_t mbar;
   __shared__ DevProblem s_prob;
   using DM = Dims<NN>;
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(32) map_bfgs_kernel(const MapParams K) {
 template <int NN, int MOD>
 __global__ void __launch_bounds__(32) vb_kernel(const VbParams K) {
   extern __shared__ __align__(128) double smem[];
+  fill_exptab();
   __shared__ uint64_t mbar;
   __shared__ DevProblem s_prob;
   using DM = Dims<NN>;
@@ -498,10 +501,10 @@ static cudaError_t nuts_occupancy(int mod, int chains, long long n_items, int n_
         if constexpr (NN > 0) {
           if (!std::getenv("FOCT_CTA_ITEMS")) {  // (A/B: the CTA-level items of nuts2_kernel<.., 1>)
             // warps as the scheduling unit: two warps per CTA whatever the chain count, each with its own staged rows
-            *warp_units = 1;
+            *slice_bytes = (size_t)FOCT_PAIR_STATE_DOUBLES * 32 * sizeof(double);  // per unit = per warp
+            *warp_units = 2;
             *block = 64;
             *smem = 2 * smem_rows;
-            *slice_bytes = (size_t)FOCT_PAIR_STATE_DOUBLES * 32 * sizeof(double);  // per unit = per warp
             return mod == 0 ? occupancy_of(nuts2w_kernel<NN, 0>, *block, *smem, blocks_per_sm, regs)
                             : occupancy_of(nuts2w_kernel<NN, 1>, *block, *smem, blocks_per_sm, regs);
           }

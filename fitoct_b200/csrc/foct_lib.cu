@@ -795,6 +795,28 @@ extern "C" int foct_logp_grad(int kind, const foct_problem* P, int n, const foct
   return rc;
 }
 
+extern "C" int foct_summary(const double* draws, int n_sets, int n_draws, int chains, int n_cols, double* summary) {
+  if (int rc = check_device()) return rc;
+  if (!draws || !summary) return fail(FOCT_EINVAL, "NULL draws / summary");
+  if (n_sets < 1 || n_cols < 1 || n_draws < 4 || chains < 1 || chains > FOCT_MAX_CHAINS)
+    return fail(FOCT_EINVAL, "need n_sets, n_cols >= 1, n_draws >= 4, 1 <= chains <= %d", FOCT_MAX_CHAINS);
+  const size_t nd = (size_t)n_sets * n_draws * chains * n_cols, ns = (size_t)n_sets * n_cols * FOCT_N_SUMMARY_COLS;
+  double *d_dr = nullptr, *d_su = nullptr;
+  int rc = 0;
+  do {
+#define CUB(call) if ((call) != cudaSuccess) { rc = fail(FOCT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); break; }
+    CUB(pool_malloc(&d_dr, nd * sizeof(double)));
+    CUB(pool_malloc(&d_su, ns * sizeof(double)));
+    CUB(cudaMemcpy(d_dr, draws, nd * sizeof(double), cudaMemcpyHostToDevice));
+    CUB(launch_summary(d_dr, n_sets, n_draws, 0, n_draws, chains, n_cols, d_su, nullptr));
+    CUB(cudaDeviceSynchronize());
+    CUB(cudaMemcpy(summary, d_su, ns * sizeof(double), cudaMemcpyDeviceToHost));
+#undef CUB
+  } while (0);
+  pool_free(d_dr); pool_free(d_su);
+  return rc;
+}
+
 extern "C" int foct_predict(int kind, const foct_problem* P, const foct_model_spec* spec, const double* draws,
                             int n_draws, double* m, double* resid, double* dL) {
   if (int rc = check_device()) return rc;
@@ -935,7 +957,7 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
   }
   p->alt_groups = (cfg->chains + FOCT_CTA_CHAINS - 1) / FOCT_CTA_CHAINS;
   const int groups = p->warp_units ? (cfg->chains + 1) / 2 : (cfg->chains + cta_chains - 1) / cta_chains;
-  p->groups = groups; p->n_sm = n_sm; p->wpc = p->warp_units ? 2 : 1;
+  p->groups = groups; p->n_sm = n_sm; p->wpc = p->warp_units ? p->warp_units : 1;  // (warp_units = warps per CTA of nuts2w_kernel)
   p->grid = (int)std::min<long long>(((long long)n * groups + p->wpc - 1) / p->wpc, (long long)n_sm * p->blocks_per_sm);
   if (const char* env = std::getenv("FOCT_MAX_GRID")) p->grid = std::max(1, std::min(p->grid, std::atoi(env)));  // tests: few CTAs
   const long long resident = (long long)p->grid * p->wpc;  // work units in flight at once

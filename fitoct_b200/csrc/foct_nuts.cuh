@@ -57,7 +57,7 @@ struct SamplerParams {
   int* slice_hist;                  // [FOCT_PROGRESS_BINS] waiting units by iterations done (nuts2w_kernel), or nullptr
   int slice_ticks;                  // gradient evaluations per slice
   int pair_kernel;                  // host: 1 = nuts2_kernel (two chains per warp), 0 = nuts_kernel
-  int warp_units;                   // host: 1 = nuts2w_kernel (warps claim (profile, chain pair) units on their own)
+  int warp_units;                   // host: > 0 = nuts2w_kernel (warps claim (profile, chain pair) units on their own), the warps of a CTA
 };
 
 #define FOCT_PROGRESS_EVERY 8
@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(32 * FOCT_CTA_CHAINS, NutsBounds<NN>::MINB) nu
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int groups = (K.chains + FOCT_CTA_CHAINS - 1) / FOCT_CTA_CHAINS;
   const int n_items = K.n_problems * groups;
+  fill_exptab();
   mbar_init(&mbar);
   uint32_t phase = 0;
   for (;;) {

@@ -508,6 +508,7 @@ nuts2_kernel(const SamplerParams K) {
   const bool sliced = K.slice_state != nullptr;
   constexpr int CTA_WARPS = FOCT_PAIR_CTA_CHAINS / 2;
   const double* gbasis = GB ? K.blobs : nullptr;  // blob 0: the basis every profile of the batch shares
+  fill_exptab();
   mbar_init(&mbar);
   uint32_t phase = 0;
   for (;;) {
@@ -586,6 +587,7 @@ __global__ void __launch_bounds__(64, FOCT_PAIR_MINB_GB) nuts2w_kernel(const Sam
   const int n_units = K.n_problems * upp;
   const bool sliced = K.slice_state != nullptr;
   double* rows = smem + (size_t)warp * 3 * K.npad;
+  fill_exptab();
   if (leader) {
     const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(&mbar[warp]);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");

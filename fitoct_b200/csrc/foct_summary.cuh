@@ -126,12 +126,11 @@ __device__ double ess_block(double* x, int len, int CC, double* scratch) {
   // Stan's monotone pass stops one pair short of max_s: a stored final pair keeps its raw value
   if (last_stored) sum_pairs += last_raw - last_adj;
   const double extra = rho_even > 0.0 ? rho_even : 0.0;
-  const double tau = -1.0 + 2.0 * sum_pairs + extra;
   const double nt = (double)S;
-  double ess = nt / tau;
-  const double cap = nt * log10(nt);
-  if (ess > cap) ess = cap;
-  return ess;
+  // rstan's ess_rfun: tau_hat = max(tau_hat, 1 / log10(S)) — caps the ESS at S log10(S) and keeps a strongly antithetic
+  // column (tau <= 0) finite and positive
+  const double tau = fmax(-1.0 + 2.0 * sum_pairs + extra, 1.0 / log10(nt));
+  return nt / tau;
 }
 
 // Dynamic shared memory layout: A[S] doubles | W[Spad] doubles | I[Spad] ints.

@@ -193,6 +193,13 @@ int foct_expgp_map(const foct_problem* P, int n_problems, const foct_model_spec*
 int foct_predict(int kind, const foct_problem* P, const foct_model_spec* spec, const double* draws,
                  int n_draws, double* m, double* resid, double* dL);
 
+/* rstan's summary(fit)$summary / monitor() for caller-supplied draws (plotExpGP.R:9-11, server.R:88-104 read it):
+ * mean, se_mean, sd, 2.5/25/50/75/97.5 % quantiles, n_eff (Stan's Geyer estimator with rstan's tau clamp), split R-hat,
+ * rank-normalised Bulk_ESS — the same kernel that summarises a fit inside foct_sample.
+ * draws: [n_sets][n_draws][chains][n_cols] (the layout of foct_result.draws); summary: [n_sets][n_cols][FOCT_N_SUMMARY_COLS].
+ * n_draws >= 4, 1 <= chains <= FOCT_MAX_CHAINS. */
+int foct_summary(const double* draws, int n_sets, int n_draws, int chains, int n_cols, double* summary);
+
 /* Plan API: the same path with device-resident inputs, for repeated runs and for timing the
  * sampling step without host<->device copies (bench.py `value`; `e2e` uses foct_sample). */
 typedef struct foct_plan foct_plan;

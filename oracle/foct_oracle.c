@@ -929,9 +929,10 @@ static double ess_stan(const double* x, int n, int C) {
     for (s = 0; s <= max_s; ++s) sum += rho[s];
     double tau = -1.0 + 2.0 * sum + rho[max_s + 1];
     double nt = (double)n * C;
+    /* rstan's ess_rfun: tau_hat = max(tau_hat, 1 / log10(S)) - caps the ESS at S log10(S) and keeps a strongly
+       antithetic column (tau <= 0) finite and positive */
+    tau = fmax(tau, 1.0 / log10(nt));
     ess = nt / tau;
-    double cap = nt * log10(nt);
-    if (ess > cap) ess = cap;
     free(rho);
 #undef MEAN_ACOV
   }

@@ -1,4 +1,5 @@
-"""BASELINE.json configs[0..3] on one B200: MonoExp sampled, single ExpGP profile, Nn sweep 5..20 (fitted-form uy)."""
+"""BASELINE.json configs[0..3] on one B200: MonoExp sampled, single ExpGP profile, Nn sweep 5..20 with uy from
+foct_estimate_noise (the smoothing-spline residual law of the reference's estimateNoise, FitOCT.R:90-93), not a closed form."""
 import json, sys, time
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -25,8 +26,12 @@ res["c1_expgp_single"] = dict(wall_s=dt, leapfrogs=float(o["n_leapfrog"].sum()),
 # configs[3]: Nn sweep with the estimateNoise-form uy
 for Nn in (5, 10, 15, 20):
     n = 888 if Nn <= 15 else 592
-    Sx = synth.make_profiles(n, modulated_only=True, fitted_uy=True)
-    b = abi.make_problems_dense(Sx["x"], Sx["Y"], Sx["UY"], Sx["theta0"], Sx["Sigma0"], Nn=Nn, ids=Sx["ids"])
+    Sx = synth.make_profiles(n, modulated_only=True)
+    b0 = abi.make_problems_dense(Sx["x"], Sx["Y"], Sx["UY"], Sx["theta0"], Sx["Sigma0"], Nn=Nn, ids=Sx["ids"])
+    t = time.perf_counter(); en = L.estimate_noise(b0, n); t_noise = time.perf_counter() - t
+    assert np.all(en["status"] <= 1)
+    UY = np.stack(en["uy"])
+    b = abi.make_problems_dense(Sx["x"], Sx["Y"], UY, Sx["theta0"], Sx["Sigma0"], Nn=Nn, ids=Sx["ids"])
     plan = L.Plan(0, b, n, abi.default_spec(), cfg, want_draws=False, want_summary=True)
     plan.run(1); plan.sync(); plan.run(2); plan.sync()
     tm = plan.timing(); o = plan.fetch(); plan.close()
@@ -35,5 +40,7 @@ for Nn in (5, 10, 15, 20):
     res[f"c3_Nn{Nn}"] = dict(profiles=n, step_s=T, grad_per_s=leap / T, tflops=leap * 481 * (4 * Nn + 23) / T / 1e12,
                              draws_per_s=n * 4000 / T, min_ess_per_s=float(np.nansum(np.nanmin(o["summary"][:, :Nn + 5, 10], axis=1))) / T,
                              rhat_q99=float(np.nanquantile(np.nanmax(o["summary"][:, :Nn + 5, 9], axis=1), 0.99)),
-                             launch={k: tm[k] for k in ("grid", "blocks_per_sm", "regs", "smem_bytes")})
+                             launch={k: tm[k] for k in ("grid", "blocks_per_sm", "regs", "smem_bytes")},
+                             uy="foct_estimate_noise", estimate_noise_s=t_noise,
+                             uy_over_true_sd_median=float(np.median(UY / Sx["UY"])), sigma_mean=float(np.nanmean(o["summary"][:, Nn + 4, 0])))
 print(json.dumps(res))

@@ -208,6 +208,25 @@ def test_summary_kernel_vs_oracle(L, O):
     np.testing.assert_allclose(out["summary"][0], O.summary(out["draws"][0, 60:]), rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("phi,n,chains", [(0.0, 400, 4), (0.95, 777, 4), (0.9, 40, 4), (-0.9, 300, 4), (-0.97, 60, 2), (-0.99, 25, 1)])
+def test_foct_summary_vs_oracle_on_ar1_columns(L, O, phi, n, chains):
+    """foct_summary on caller-supplied draws: short chains (the Geyer loop ends by length) and strongly antithetic
+    columns (tau <= 0 before rstan's clamp) against the oracle, which tests/test_oracle_sampler.py pins to numpy."""
+    rng = np.random.default_rng(int(1000 * abs(phi)) + n)
+    x = np.zeros((n, chains, 3))
+    e = rng.standard_normal((n, chains, 3))
+    for t in range(1, n):
+        x[t] = phi * x[t - 1] + e[t]
+    x[..., 1] = 5.0 + 2.0 * x[..., 1] + np.arange(chains)[None, :] * 0.3
+    x[..., 2] = 1e6 + 1e-3 * x[..., 2]
+    s = L.summary(x)
+    so = O.summary(x)
+    np.testing.assert_allclose(s, so, rtol=1e-9, atol=1e-12)
+    assert np.all(np.isfinite(s[:, 8])) and np.all(s[:, 8] > 0) and np.all(np.isfinite(s[:, 1]))
+    both = L.summary(np.stack([x, x[::-1]]))
+    np.testing.assert_array_equal(both[0], s)
+
+
 def test_map_and_predict_vs_oracle(L, O):
     S = synth.make_profiles(10)
     b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=0)

@@ -94,10 +94,10 @@ def numpy_ess(x):
             rho[s + 1] = (rho[s - 1] + rho[s]) / 2
             rho[s + 2] = rho[s + 1]
     tau = -1 + 2 * rho[: max_s + 1].sum() + rho[max_s + 1]
-    return min(C * n / tau, C * n * np.log10(C * n))
+    return C * n / max(tau, 1.0 / np.log10(C * n))      # rstan's ess_rfun: tau_hat = max(tau_hat, 1 / log10(S))
 
 
-@pytest.mark.parametrize("phi,n", [(0.0, 400), (0.7, 1000), (0.95, 777), (-0.5, 500)])
+@pytest.mark.parametrize("phi,n", [(0.0, 400), (0.7, 1000), (0.95, 777), (-0.5, 500), (0.9, 40), (-0.9, 300), (-0.97, 60)])
 def test_summary_against_numpy(O, phi, n):
     rng = np.random.default_rng(int(1000 * abs(phi)) + n)
     C = 4
@@ -125,6 +125,8 @@ def test_summary_against_numpy(O, phi, n):
         z = norm.ppf((rankdata(order.reshape(-1), method="ordinal") - 0.375) / (order.size + 0.25)).reshape(order.shape)
         assert np.isclose(S[p, 10], numpy_ess(z), rtol=1e-8)
         assert np.isclose(S[p, 1], S[p, 2] / np.sqrt(S[p, 8]), rtol=1e-12)
+        # a strongly antithetic column (tau <= 0 before the clamp) still has a finite, positive n_eff and se_mean
+        assert np.isfinite(S[p, 8]) and 0 < S[p, 8] <= C * n * np.log10(C * n) * (1 + 1e-12) and np.isfinite(S[p, 1])
     if abs(phi) < 0.9:
         assert S[1, 9] > S[0, 9]
 
