@@ -322,7 +322,8 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
                                              const double (&yg)[NN > 0 ? NN : 1], double (&acc)[KP],
                                              const double* __restrict__ pg = nullptr) {
   static_assert(W == 32 || (W == 16 && U % 2 == 0), "half-warp groups take the two halves of a block together");
-  constexpr int SROWS = GB ? 3 : 3 + NN;   // rows of a staged block
+  constexpr int SROWS = GB == 2 ? 2 : (GB ? 3 : 3 + NN);   // rows of a staged block (GB = 2: y | w only, c x comes from the shared blob too)
+  constexpr int YR = GB == 2 ? 0 : 1;                      // row of y inside a staged block
   const double* __restrict__ pp = pp0;
 #define FOCT_PT(u) (W == 32 ? (u) * SROWS * 32 : ((u) >> 1) * SROWS * 32 + ((u) & 1) * 16)
 #define FOCT_PTG(u) (W == 32 ? (u) * (3 + NN) * 32 : ((u) >> 1) * (3 + NN) * 32 + ((u) & 1) * 16)
@@ -348,9 +349,10 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
     }
 #pragma unroll
     for (int v = 0; v < U / 2; ++v) {
-      const double2 c2 = *reinterpret_cast<const double2*>(pp + v * SROWS * 32);
-      const double2 y2 = *reinterpret_cast<const double2*>(pp + v * SROWS * 32 + 32);
-      const double2 w2 = *reinterpret_cast<const double2*>(pp + v * SROWS * 32 + 64);
+      const double2 c2 = GB == 2 ? __ldg(reinterpret_cast<const double2*>(pg + v * (3 + NN) * 32))
+                                 : *reinterpret_cast<const double2*>(pp + v * SROWS * 32);
+      const double2 y2 = *reinterpret_cast<const double2*>(pp + v * SROWS * 32 + YR * 32);
+      const double2 w2 = *reinterpret_cast<const double2*>(pp + v * SROWS * 32 + (YR + 1) * 32);
       cx[2 * v] = c2.x; cx[2 * v + 1] = c2.y; y[2 * v] = y2.x; y[2 * v + 1] = y2.y; ws[2 * v] = w2.x; ws[2 * v + 1] = w2.y;
     }
 #pragma unroll
@@ -369,9 +371,9 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       s[u] = dl0[u] + dl1[u];
-      cx[u] = pp[FOCT_PT(u)];
-      y[u] = pp[FOCT_PT(u) + 32];
-      ws[u] = pp[FOCT_PT(u) + 64];  // 1/uy; the 1/sigma^2 common to every sum is applied once after the reduction
+      cx[u] = GB == 2 ? __ldg(pg + FOCT_PTG(u)) : pp[FOCT_PT(u)];
+      y[u] = pp[FOCT_PT(u) + YR * 32];
+      ws[u] = pp[FOCT_PT(u) + (YR + 1) * 32];  // 1/uy; the 1/sigma^2 common to every sum is applied once after the reduction
     }
   }
   // reciprocal of the local decay length (length modulation with a GP); otherwise r3 is hoisted
@@ -492,11 +494,15 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
 #ifndef FOCT_PREFETCH
 #define FOCT_PREFETCH 1
 #endif
-template <int NN, int KP, int ZI>
-__device__ __forceinline__ void sweep_points_pf(const double* __restrict__ pp, const double* __restrict__ pgn, double th1,
-                                                double th2, double th3, const double (&yg)[NN], double (&acc)[KP],
-                                                double2 (&bb)[NN]) {
+template <int NN, int KP, int ZI, bool CXG>
+__device__ __forceinline__ void sweep_points_pf(const double* __restrict__ pp, const double* __restrict__ pgc,
+                                                const double* __restrict__ pgn, double th1, double th2, double th3,
+                                                const double (&yg)[NN], double (&acc)[KP], double2 (&bb)[NN]) {
   constexpr int U = 2;
+  // CXG: the depth row c x is the same for every profile of the batch, so it is read from the shared blob (current block
+  // `pgc`) like the basis rows, and only y | w are staged per warp: 8 KB instead of 12 KB of shared memory per warp
+  double2 c2g;
+  if constexpr (CXG) c2g = __ldg(reinterpret_cast<const double2*>(pgc));
   double dl0[U], dl1[U], cx[U], y[U], ws[U], r[U], t[U], a[U], x0[U], e0[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) { dl0[u] = 1.0; dl1[u] = 0.0; }  // s = 1 + dL: the 1 rides in the first partial sum
@@ -506,9 +512,11 @@ __device__ __forceinline__ void sweep_points_pf(const double* __restrict__ pp, c
     else { dl0[0] = fma(bb[k].x, yg[k], dl0[0]); dl0[1] = fma(bb[k].y, yg[k], dl0[1]); }
   }
   {
-    const double2 c2 = *reinterpret_cast<const double2*>(pp);
-    const double2 y2 = *reinterpret_cast<const double2*>(pp + 32);
-    const double2 w2 = *reinterpret_cast<const double2*>(pp + 64);
+    constexpr int YR = CXG ? 0 : 1;
+    double2 c2;
+    if constexpr (CXG) c2 = c2g; else c2 = *reinterpret_cast<const double2*>(pp);
+    const double2 y2 = *reinterpret_cast<const double2*>(pp + YR * 32);
+    const double2 w2 = *reinterpret_cast<const double2*>(pp + (YR + 1) * 32);
     cx[0] = c2.x; cx[1] = c2.y; y[0] = y2.x; y[1] = y2.y; ws[0] = w2.x; ws[1] = w2.y;
   }
 #pragma unroll
@@ -581,16 +589,32 @@ __device__ __forceinline__ void sweep_points_pf(const double* __restrict__ pp, c
   }
 }
 
+// Two warps per chain (TEAM = 2, the latency kernel of small batches: nuts_lat_kernel).  Both warps of a team execute the
+// whole chain redundantly — same state, same Philox sites, same decisions — but each sweeps only its half of the profile's
+// blocks; the reduce-scattered partial sums are exchanged through shared memory and added in a fixed order (member 0's +
+// member 1's), so both members continue with bit-identical values and never diverge.  One named barrier per gradient
+// (the exchange buffer is double-buffered by parity, which makes the write-after-read of the next gradient safe).
+struct TeamCtx {
+  int member;    // 0 / 1; member 0 is the one that writes results
+  int bar_id;    // named barrier of the team (1 + chain slot of the CTA), 64 threads
+  int parity;
+  double* xch;   // shared memory: [2 parities][2 members][32]
+  int* flag;     // shared memory: the team's cancel decision
+};
+__device__ __forceinline__ void team_sync(const TeamCtx* tc) { asm volatile("bar.sync %0, 64;" ::"r"(tc->bar_id) : "memory"); }
+
 // Fused sweep over the staged profile.  qd = this lane's component of q.  Everything a lane needs from
 // the other lanes is fetched with shuffles up front; the per-point loop touches only shared memory and
 // processes two passes (64 points per warp) per iteration so that two independent dependency chains are
 // in flight per warp (the fp64 pipe was latency-, not throughput-bound with one: profiles/r1_*v1*).
 // W = 32: one chain per warp.  W = 16: one chain per half-warp — `lane` is then the index inside the half, both halves
 // must call together (full-mask shuffles of width 16) and walk the same profile, so every LDS is a 16-word broadcast.
-template <int NN, int MOD, int W = 32, int GB = 0>
+template <int NN, int MOD, int W = 32, int GB = 0, int TEAM = 1>
 __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, const DevProblem& P, const DevSpec& S,
-                                               double qd, int lane, const double* __restrict__ gbasis = nullptr) {
+                                               double qd, int lane, const double* __restrict__ gbasis = nullptr,
+                                               TeamCtx* tc = nullptr) {
   static_assert(W == 32 || Dims<NN>::D <= 16, "a half-warp holds at most 16 components");
+  static_assert(TEAM == 1 || (TEAM == 2 && W == 32 && GB == 0), "teams of two whole warps on a staged blob");
   FOCT_T(t_g0);
   using DM = Dims<NN>;
   constexpr int D = DM::D;
@@ -601,7 +625,13 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
 #ifndef FOCT_UNROLL_MAXNN
 #define FOCT_UNROLL_MAXNN 12
 #endif
-  constexpr int UNROLL = NN <= FOCT_UNROLL_MAXNN ? FOCT_UNROLL : 1;  // above 12 control points the second basis row spills (measured: Nn=15 is 9 % faster with 1)
+#ifndef FOCT_UNROLL_LAT
+#define FOCT_UNROLL_LAT 4
+#endif
+  // above 12 control points the second basis row spills (measured: Nn=15 is 9 % faster with 1); the latency kernel has
+  // 255 registers per thread and one warp per scheduler: four points in flight, two above 12 control points
+  constexpr int UNROLL = TEAM == 2 ? (NN <= FOCT_UNROLL_MAXNN ? FOCT_UNROLL_LAT : (NN <= 20 ? 2 : 1))
+                                   : (NN <= FOCT_UNROLL_MAXNN ? FOCT_UNROLL : 1);
   const double th1 = bcast<W>(qd, 0), th2 = bcast<W>(qd, 1), th3 = bcast<W>(qd, 2);
   double yg[NN > 0 ? NN : 1];
 #pragma unroll
@@ -671,7 +701,7 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
   double zz = 0.0;
   if (!P.prior_PD) {
     const double r3 = frcp(th3);  // (a full division drags its exponent-range slow path into every leaf)
-    constexpr int ROWS = GB ? 3 : 3 + NN;     // rows of a staged block
+    constexpr int ROWS = GB == 2 ? 2 : (GB ? 3 : 3 + NN);     // rows of a staged block
     constexpr int GROWS = 3 + NN;             // rows of a block of the shared (global) blob
     // (half-warp groups with 128-bit loads: lane l owns the neighbouring points 2l, 2l+1 of each block)
     const int lane_off = (W == 16 && FOCT_PAIR_LDS128) ? 2 * lane : lane;
@@ -683,8 +713,12 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
     // points by the lane group as a whole — control point k in lane 3 + k, the scalar chain repeated by every lane — was
     // measured 2.5 % SLOWER than the padded iteration: it is one more serial dependency chain of the same length, and
     // the kernel is bound by latency, not by issue slots.  profiles/r2_kernel_experiments.txt)
-    const int npass = P.npass;
+    int npass = P.npass;
     int pass = 0;
+    if constexpr (TEAM == 2) {  // this member's half of the blocks
+      const int half = (npass + 1) >> 1;
+      if (tc->member) { pass = half; pp += (size_t)half * ROWS * 32; } else { npass = half; }
+    }
     if constexpr (W == 16) {
       // 32-point blocks: the two 16-point halves of a block are two points in flight per lane; FOCT_UNROLL16 = 4 takes
       // two blocks per iteration (two warps per scheduler is all the staged profiles leave room for: the instruction-
@@ -702,8 +736,9 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
         for (int k = 0; k < NN; ++k) bb[k] = __ldg(reinterpret_cast<const double2*>(pg + (3 + k) * 32));
 #pragma unroll 1
         for (; pass < npass; ++pass, pp += ROWS * 32) {
+          const double* pgc = pg;
           if (pass + 1 < npass) pg += GROWS * 32;  // the last iteration re-requests its own block: harmless, stays in bounds
-          sweep_points_pf<NN, KP, ZI>(pp, pg, th1, th2, th3, yg, acc, bb);
+          sweep_points_pf<NN, KP, ZI, GB == 2>(pp, pgc, pg, th1, th2, th3, yg, acc, bb);
         }
       } else {
         if (U16 > 2) {
@@ -727,7 +762,15 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
     }
     FOCT_T(t_l1);
     FOCT_TADD(1, t_l0, t_l1);
-    const double red = warp_reduce_scatter<KP, W>(acc, lane) * isig2;  // every sum carries the factor 1/sigma^2
+    double red = warp_reduce_scatter<KP, W>(acc, lane);
+    if constexpr (TEAM == 2) {
+      double* buf = tc->xch + tc->parity * 64;
+      buf[tc->member * 32 + lane] = red;
+      team_sync(tc);
+      red = buf[lane] + buf[32 + lane];
+      tc->parity ^= 1;
+    }
+    red *= isig2;  // every sum carries the factor 1/sigma^2
     zz = bcast<W>(red, ZI);
     FOCT_T(t_l2);
     FOCT_TADD(2, t_l1, t_l2);

@@ -419,6 +419,16 @@ static cudaError_t launch_nuts_mod(int grid, int block, size_t smem, cudaStream_
       return cudaGetLastError();
     }
   }
+  // At most one work item per SM: the latency kernel (two warps per chain, one CTA per SM).  FOCT_NO_LAT=1: A/B runs and
+  // the tests that pin the one-chain-per-warp kernel.
+  if (grid <= sm_count() && !std::getenv("FOCT_NO_LAT")) {
+    e = cudaFuncSetAttribute(nuts_lat_kernel<NN, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      nuts_lat_kernel<NN, MOD><<<grid, 2 * block, smem, st>>>(K);
+      return cudaGetLastError();
+    }
+    cudaGetLastError();  // (a blob that leaves no room for the team buffers: the one-chain-per-warp kernel below)
+  }
   e = cudaFuncSetAttribute(nuts_kernel<NN, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   nuts_kernel<NN, MOD><<<grid, block, smem, st>>>(K);
@@ -504,7 +514,8 @@ static cudaError_t nuts_occupancy(int mod, int chains, long long n_items, int n_
             *slice_bytes = (size_t)FOCT_PAIR_STATE_DOUBLES * 32 * sizeof(double);  // per unit = per warp
             *warp_units = 2;
             *block = 64;
-            *smem = 2 * smem_rows;
+            *smem = 2 * (FOCT_CX_SHARED ? smem_rows / 3 * 2 : smem_rows);  // per warp: y | w (c x is shared too), or c x | y | w
+            if (FOCT_CX_SHARED) *smem += (size_t)FOCT_STACK_SMEM * 64 * 7 * sizeof(double);  // the busiest levels of the subtree stacks
             return mod == 0 ? occupancy_of(nuts2w_kernel<NN, 0>, *block, *smem, blocks_per_sm, regs)
                             : occupancy_of(nuts2w_kernel<NN, 1>, *block, *smem, blocks_per_sm, regs);
           }

@@ -934,7 +934,7 @@ static int plan_create_on(int device, int kind, const foct_problem* P, int n, co
   // GP basis: the sampling kernel then stages only cx | y | w per profile and reads the basis of blob 0 through L1.
   int shared_basis = kind == FOCT_EXPGP && n > 1;
   for (int j = 1; j < n && shared_basis; ++j)
-    shared_basis = P[j].N == P[0].N && P[j].gridType == P[0].gridType && P[j].rho == P[0].rho &&
+    shared_basis = P[j].N == P[0].N && P[j].gridType == P[0].gridType && P[j].rho == P[0].rho && P[j].dataType == P[0].dataType &&
                    std::memcmp(P[j].x, P[0].x, (size_t)P[0].N * sizeof(double)) == 0;
   int cta_chains = FOCT_CTA_CHAINS;
   size_t slice_bytes = 0;

@@ -110,20 +110,22 @@ __device__ __forceinline__ bool merge_persists(double invM, double i_rho, double
 #ifndef FOCT_LEAPFROG_INLINE
 #define FOCT_LEAPFROG_INLINE __forceinline__
 #endif
-template <int NN, int MOD>
+template <int NN, int MOD, int TEAM = 1>
 __device__ FOCT_LEAPFROG_INLINE void leapfrog(const double* __restrict__ blob, const DevProblem* P, const DevSpec* S,
                                       double eps, double invM, double* zq, double* zp, double* zg, double* zV,
-                                      double* zc2, int lane) {
+                                      double* zc2, int lane, TeamCtx* tc = nullptr) {
   double p = fma(0.5 * eps, *zg, *zp);
   double q = fma(eps * invM, p, *zq);
-  const Eval ev = warp_logp_grad<NN, MOD>(blob, *P, *S, q, lane);
+  const Eval ev = warp_logp_grad<NN, MOD, 32, 0, TEAM>(blob, *P, *S, q, lane, nullptr, tc);
   p = fma(0.5 * eps, ev.g, p);
   *zq = q; *zp = p; *zg = ev.g; *zV = -ev.lp; *zc2 = ev.chi2;
 }
 
-template <int NN, int MOD>
+// TEAM = 2: the chain is run by two warps (see TeamCtx in foct_device.cuh); `writer` is the member that stores results.
+template <int NN, int MOD, int TEAM = 1>
 __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const double* __restrict__ blob, int prob,
-                          int chain, int lane) {
+                          int chain, int lane, TeamCtx* tc = nullptr) {
+  const bool writer = TEAM == 1 || tc->member == 0;
   using DM = Dims<NN>;
   constexpr int D = DM::D;
   constexpr int P_OUT = DM::P_OUT;
@@ -147,7 +149,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       else q = 0.0;
     }
   }
-  Eval ev = warp_logp_grad<NN, MOD>(blob, P, K.spec, q, lane);
+  Eval ev = warp_logp_grad<NN, MOD, 32, 0, TEAM>(blob, P, K.spec, q, lane, nullptr, tc);
   double g = ev.g, V = -ev.lp, c2 = ev.chi2;
   double invM = 1.0;
   double eps = K.stepsize0 > 0.0 ? K.stepsize0 : 1.0;
@@ -195,7 +197,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       }
       ++attempt;
       const double H0 = zV + 0.5 * warp_sum(invM * zp * zp);
-      leapfrog<NN, MOD>(blob, &P, &K.spec, eps, invM, &zq, &zp, &zg, &zV, &zc2, lane);
+      leapfrog<NN, MOD, TEAM>(blob, &P, &K.spec, eps, invM, &zq, &zp, &zg, &zV, &zc2, lane, tc);
       double h = zV + 0.5 * warp_sum(invM * zp * zp);
       if (isnan(h)) h = CUDART_INF;
       const double dH = H0 - h;
@@ -216,7 +218,17 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
 
   int it_done = 0;
   for (int it = 0; it < K.n_iter; ++it) {
-    if (cancel_requested(K)) break;
+    if constexpr (TEAM == 2) {
+      // the members must take the same decision: member 0 reads the flag, the team barrier publishes it (the next write
+      // is ordered behind this read by the gradient barriers of the iteration in between)
+      if (K.cancel) {
+        if (tc->member == 0 && lane == 0) *tc->flag = cancel_requested(K) ? 1 : 0;
+        team_sync(tc);
+        if (*reinterpret_cast<volatile int*>(tc->flag)) break;
+      }
+    } else {
+      if (cancel_requested(K)) break;
+    }
     // ================================================================ one NUTS transition
     double p = 0.0;
     if (act) {
@@ -247,7 +259,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       const uint32_t n_leaves = 1u << depth;
       for (uint32_t n = 0; n < n_leaves; ++n) {
         FOCT_T(t_f0);
-        leapfrog<NN, MOD>(blob, &P, &K.spec, eps_s, invM, &zq, &zp, &zg, &zV, &zc2, lane);
+        leapfrog<NN, MOD, TEAM>(blob, &P, &K.spec, eps_s, invM, &zq, &zp, &zg, &zV, &zc2, lane, tc);
         ++n_leap;
         double h = zV + 0.5 * warp_sum(invM * zp * zp);
         if (isnan(h)) h = CUDART_INF;
@@ -312,7 +324,7 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
     const bool warm = it < K.n_warmup;
     if (warm) nlf_warm += n_leap; else { nlf_samp += n_leap; ndiv += divergent ? 1.0 : 0.0; }
     const int save_idx = K.save_warmup ? it : it - K.n_warmup;
-    if (save_idx >= 0) {
+    if (save_idx >= 0 && writer) {
       const size_t row = save_row(K, prob, n_saved, save_idx, chain);
       if (K.draws) {
         double v;
@@ -376,10 +388,11 @@ __device__ void run_chain(const SamplerParams& K, const DevProblem& P, const dou
       if (it == K.n_warmup - 1) eps = exp(da_xbar);
     }
     it_done = it + 1;
-    report_progress(K, it_done, false, lane == 0);
+    report_progress(K, it_done, false, lane == 0 && writer);
   }
-  report_progress(K, it_done, true, lane == 0);
+  report_progress(K, it_done, true, lane == 0 && writer);
   const size_t pc = (size_t)prob * K.chains + chain;
+  if (!writer) return;
   if (lane == 0) {
     if (K.stepsize) K.stepsize[pc] = eps;
     if (K.n_leapfrog) {
@@ -427,6 +440,40 @@ __global__ void __launch_bounds__(32 * FOCT_CTA_CHAINS, NutsBounds<NN>::MINB) nu
     stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase, threadIdx.x == 0);
     __syncthreads();
     if (chain < K.chains) run_chain<NN, MOD>(K, s_prob, smem, j, chain, lane);
+    __syncthreads();
+  }
+}
+
+// The latency kernel: batches of at most one work item per SM (a single profile — what FitOCT.R's loop submits per call —
+// or the continuation rounds of a few unconverged profiles).  Such a batch cannot fill the GPU; what counts is how fast
+// ONE chain advances.  Each chain gets a team of two warps (TeamCtx), the CTA an SM of its own, every thread 255
+// registers, and the sweep keeps four points in flight per lane (FOCT_UNROLL_LAT): 8 warps x 1 CTA per SM.
+template <int NN, int MOD>
+__global__ void __launch_bounds__(64 * FOCT_CTA_CHAINS, 1) nuts_lat_kernel(const SamplerParams K) {
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t mbar;
+  __shared__ int s_next;
+  __shared__ DevProblem s_prob;
+  __shared__ double s_xch[FOCT_CTA_CHAINS][2 * 64];
+  __shared__ int s_flag[FOCT_CTA_CHAINS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, slot = warp >> 1;
+  const int groups = (K.chains + FOCT_CTA_CHAINS - 1) / FOCT_CTA_CHAINS;
+  const int n_items = K.n_problems * groups;
+  fill_exptab();
+  mbar_init(&mbar);
+  uint32_t phase = 0;
+  TeamCtx tc;
+  tc.member = warp & 1; tc.bar_id = 1 + slot; tc.parity = 0; tc.xch = &s_xch[slot][0]; tc.flag = &s_flag[slot];
+  for (;;) {
+    if (threadIdx.x == 0) s_next = atomicAdd(K.work_counter, 1);
+    __syncthreads();
+    const int w = s_next;
+    if (w >= n_items) break;
+    const int j = K.order ? K.order[w / groups] : w / groups, chain = (w % groups) * FOCT_CTA_CHAINS + slot;
+    if (threadIdx.x == 0) s_prob = K.probs[j];
+    stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase, threadIdx.x == 0);
+    __syncthreads();
+    if (chain < K.chains) run_chain<NN, MOD, 2>(K, s_prob, smem, j, chain, lane, &tc);
     __syncthreads();
   }
 }

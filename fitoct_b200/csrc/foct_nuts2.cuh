@@ -48,6 +48,13 @@ __device__ __forceinline__ bool merge_persists_w(double invM, double i_rho, doub
 #define FOCT_PAIR_N_DOUBLES 41
 #define FOCT_PAIR_N_INTS 15
 // doubles per lane of a saved warp: the scalars above, the ints packed two to a double, six stack arrays
+// Levels of the subtree stack that nuts2w_kernel keeps in shared memory (run_pair, GB = 2).  Measured with y | w staged
+// (8 KB per warp), 1776 profiles, gradients/s: 0 levels 3.27e8 (98 KB of shared memory per SM -> 132 KB carve-out..., L1 124 KB),
+// 1 level 3.32e8 (same carve-out), 2 levels 3.18e8 and 3 levels 2.97e8 (the next carve-outs leave 92 / 60 KB of L1 for the
+// 40 KB of basis rows and the remaining stack traffic): what the kernel needs most is L1 capacity.  profiles/r2_kernel_experiments.txt
+#ifndef FOCT_STACK_SMEM
+#define FOCT_STACK_SMEM 1
+#endif
 #define FOCT_PAIR_STATE_DOUBLES (FOCT_PAIR_N_DOUBLES + (FOCT_PAIR_N_INTS + 1) / 2 + 6 * FOCT_STACK_LEVELS)
 
 // lane32 = lane in the warp; this half's chain is `chain` (>= K.chains: the half has no chain and only keeps the other
@@ -64,7 +71,8 @@ __device__ __forceinline__ bool merge_persists_w(double invM, double i_rho, doub
 template <int NN, int MOD, int GB>
 __device__ int run_pair(const SamplerParams& K, const DevProblem& P, const double* __restrict__ blob, int prob,
                          int chain, int lane32, double* __restrict__ sv, bool resume, int n_items,
-                         const double* __restrict__ gbasis) {  // GB: blob 0, whose basis rows every profile of the batch shares
+                         const double* __restrict__ gbasis,    // GB: blob 0, whose basis rows every profile of the batch shares
+                         double* stack_smem = nullptr) {       // GB = 2: FOCT_STACK_SMEM levels x blockDim.x x 7 doubles
   using DM = Dims<NN>;
   constexpr int D = DM::D;
   constexpr int P_OUT = DM::P_OUT;
@@ -129,6 +137,14 @@ __device__ int run_pair(const SamplerParams& K, const DevProblem& P, const doubl
   // per-lane slot — lane 0 keeps lsw, lane 1 V, lane 2 c2, lane 3 H — instead of four replicated ones: a third less
   // local-memory traffic per leaf (the subtree stack is what misses L1: profiles/r2_ncu_nuts2w_summary.txt)
   double st_sc[FOCT_STACK_LEVELS];
+  // The lowest levels are the busy ones (level k is written and read once per 2^(k+1) leaves): nuts2w_kernel keeps the
+  // first FOCT_STACK_SMEM of them in shared memory (7 doubles per thread and level: 6 used, an odd word stride), the rest
+  // stays in local memory.  75 % of the stack traffic of a leaf then neither misses L1 nor evicts the basis rows from it.
+  constexpr int SL = GB == 2 ? FOCT_STACK_SMEM : 0;
+  double* const sst = SL > 0 ? stack_smem + threadIdx.x * 7 : nullptr;
+  const int SST = (int)blockDim.x * 7;
+#define ST_LD(arr, row, k) ((SL > 0 && (k) < SL) ? sst[(k) * SST + (row)] : arr[k])
+#define ST_ST(arr, row, k, v) do { if (SL > 0 && (k) < SL) sst[(k) * SST + (row)] = (v); else arr[k] = (v); } while (0)
 
 #ifndef FOCT_TEST_NO_RESUME
   if (resume) {
@@ -144,8 +160,8 @@ __device__ int run_pair(const SamplerParams& K, const DevProblem& P, const doubl
     s = sv + (FOCT_PAIR_N_DOUBLES + (FOCT_PAIR_N_INTS + 1) / 2) * 32 + lane32;
 #pragma unroll 1
     for (int k = 0; k < FOCT_STACK_LEVELS; ++k, s += 6 * 32) {
-      st_rho[k] = __ldcg(s); st_pbeg[k] = __ldcg(s + 32); st_pend[k] = __ldcg(s + 64); st_qp[k] = __ldcg(s + 96);
-      st_gp[k] = __ldcg(s + 128); st_sc[k] = __ldcg(s + 160);
+      ST_ST(st_rho, 0, k, __ldcg(s)); ST_ST(st_pbeg, 1, k, __ldcg(s + 32)); ST_ST(st_pend, 2, k, __ldcg(s + 64));
+      ST_ST(st_qp, 3, k, __ldcg(s + 96)); ST_ST(st_gp, 4, k, __ldcg(s + 128)); ST_ST(st_sc, 5, k, __ldcg(s + 160));
     }
   } else
 #endif
@@ -226,8 +242,8 @@ __device__ int run_pair(const SamplerParams& K, const DevProblem& P, const doubl
         s = sv + (FOCT_PAIR_N_DOUBLES + (FOCT_PAIR_N_INTS + 1) / 2) * 32 + lane32;
 #pragma unroll 1
         for (int k = 0; k < FOCT_STACK_LEVELS; ++k, s += 6 * 32) {
-          __stcg(s, st_rho[k]); __stcg(s + 32, st_pbeg[k]); __stcg(s + 64, st_pend[k]); __stcg(s + 96, st_qp[k]);
-          __stcg(s + 128, st_gp[k]); __stcg(s + 160, st_sc[k]);
+          __stcg(s, ST_LD(st_rho, 0, k)); __stcg(s + 32, ST_LD(st_pbeg, 1, k)); __stcg(s + 64, ST_LD(st_pend, 2, k));
+          __stcg(s + 96, ST_LD(st_qp, 3, k)); __stcg(s + 128, ST_LD(st_gp, 4, k)); __stcg(s + 160, ST_LD(st_sc, 5, k));
         }
         __threadfence();
         return bin;
@@ -306,7 +322,7 @@ __device__ int run_pair(const SamplerParams& K, const DevProblem& P, const doubl
         int mb_group = -1;
         for (; (n >> k) & 1u; ++k) {
           double prob_final;
-          const double i_sc = st_sc[k];
+          const double i_sc = ST_LD(st_sc, 5, k);
           const double lsw_sub = lse_prob(bcast<W>(i_sc, 0, hm), c_lsw, prob_final);
           // one Philox block serves the merges of four consecutive levels at this leaf (32-bit uniforms)
           if ((k >> 2) != mb_group) {
@@ -315,10 +331,10 @@ __device__ int run_pair(const SamplerParams& K, const DevProblem& P, const doubl
           }
           const uint32_t w = (k & 3) == 0 ? rb[0] : ((k & 3) == 1 ? rb[1] : ((k & 3) == 2 ? rb[2] : rb[3]));
           const bool take_final = ((double)w + 0.5) * 0x1.0p-32 < prob_final;
-          const double i_rho = st_rho[k], i_pbeg = st_pbeg[k], i_pend = st_pend[k];
+          const double i_rho = ST_LD(st_rho, 0, k), i_pbeg = ST_LD(st_pbeg, 1, k), i_pend = ST_LD(st_pend, 2, k);
           const bool persist = merge_persists_w<W>(invM, i_rho, i_pbeg, i_pend, c_rho, c_pbeg, c_pend, lane, hm);
           if (!take_final) {
-            c_qp = st_qp[k]; c_gp = st_gp[k];
+            c_qp = ST_LD(st_qp, 3, k); c_gp = ST_LD(st_gp, 4, k);
             c_V = bcast<W>(i_sc, 1, hm); c_c2 = bcast<W>(i_sc, 2, hm); c_H = bcast<W>(i_sc, 3, hm);
           }
           c_lsw = lsw_sub; c_rho = i_rho + c_rho; c_pbeg = i_pbeg;
@@ -326,8 +342,9 @@ __device__ int run_pair(const SamplerParams& K, const DevProblem& P, const doubl
         }
       }
       if (valid && n + 1 < n_leaves) {
-        st_rho[k] = c_rho; st_pbeg[k] = c_pbeg; st_pend[k] = c_pend; st_qp[k] = c_qp; st_gp[k] = c_gp;
-        st_sc[k] = lane == 0 ? c_lsw : (lane == 1 ? c_V : (lane == 2 ? c_c2 : c_H));
+        ST_ST(st_rho, 0, k, c_rho); ST_ST(st_pbeg, 1, k, c_pbeg); ST_ST(st_pend, 2, k, c_pend); ST_ST(st_qp, 3, k, c_qp);
+        ST_ST(st_gp, 4, k, c_gp);
+        ST_ST(st_sc, 5, k, lane == 0 ? c_lsw : (lane == 1 ? c_V : (lane == 2 ? c_c2 : c_H)));
         ++n;
       } else {
         // ---- end of this doubling
@@ -576,6 +593,12 @@ nuts2_kernel(const SamplerParams K) {
 // the wait of a profile's faster pair for its slower one (the four chains of a profile differ by ~5 % in gradient
 // evaluations) and lets the time slicing act per pair.
 //   ctl[0] tickets | ctl[1] pushes | ctl[2] units finished      (as in nuts2_kernel, with units for items)
+// FOCT_CX_SHARED: with one depth grid (and one dataType) for the batch the row c x is shared as well and comes through L1
+// from blob 0 next to the basis rows; a warp stages y | w only (8 KB).  Less shared memory = more L1 for the basis rows and
+// the subtree stacks in local memory (L1 hit rates at 12 KB per warp: global 94 %, local 35 %: profiles/r2_ncu_nuts2w_pf_summary.txt).
+#ifndef FOCT_CX_SHARED
+#define FOCT_CX_SHARED 1
+#endif
 template <int NN, int MOD>
 __global__ void __launch_bounds__(64, FOCT_PAIR_MINB_GB) nuts2w_kernel(const SamplerParams K) {
   extern __shared__ __align__(128) double smem[];
@@ -586,7 +609,9 @@ __global__ void __launch_bounds__(64, FOCT_PAIR_MINB_GB) nuts2w_kernel(const Sam
   const int upp = (K.chains + 1) / 2;  // units (chain pairs) per profile
   const int n_units = K.n_problems * upp;
   const bool sliced = K.slice_state != nullptr;
-  double* rows = smem + (size_t)warp * 3 * K.npad;
+  constexpr int GBW = FOCT_CX_SHARED ? 2 : 1, SR = FOCT_CX_SHARED ? 2 : 3;  // staged rows per block: y | w, or c x | y | w
+  double* rows = smem + (size_t)warp * SR * K.npad;
+  double* stack_smem = smem + (size_t)2 * SR * K.npad;  // [FOCT_STACK_SMEM levels][64 threads][7]
   fill_exptab();
   if (leader) {
     const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(&mbar[warp]);
@@ -629,10 +654,10 @@ __global__ void __launch_bounds__(64, FOCT_PAIR_MINB_GB) nuts2w_kernel(const Sam
     const int j = K.order ? K.order[r] : r;
     const int chain = 2 * pair + (lane >> 4);
     if (leader) s_prob[warp] = K.probs[j];
-    stage_rows_tma(rows, K.blobs + (size_t)j * K.blob_stride, K.npad / 32, 3 + NN, 3, &mbar[warp], phase, leader);
+    stage_rows_tma(rows, K.blobs + (size_t)j * K.blob_stride + (3 - SR) * 32, K.npad / 32, 3 + NN, SR, &mbar[warp], phase, leader);
     __syncwarp();
     double* sv = sliced ? K.slice_state + (size_t)u * (FOCT_PAIR_STATE_DOUBLES * 32) : nullptr;
-    const int bin = run_pair<NN, MOD, 1>(K, s_prob[warp], rows, j, chain, lane, sv, res != 0, n_units, K.blobs);
+    const int bin = run_pair<NN, MOD, GBW>(K, s_prob[warp], rows, j, chain, lane, sv, res != 0, n_units, K.blobs, stack_smem);
     __syncwarp();
     if (sliced && leader) {
       if (bin < 0) {

@@ -39,15 +39,18 @@ def L():
     return _lib
 
 
-@pytest.fixture(params=["auto", "pair"])
+@pytest.fixture(params=["auto", "pair", "one"])
 def sampling_kernel(request, monkeypatch):
-    """The library picks the sampling kernel by batch size (foct_inst.cu: one chain per warp while the batch fits the GPU
-    in one go, two chains per warp above that).  The parity tests use small batches, so they run twice: as shipped, and
-    with the two-chains-per-warp kernel forced — the one the BASELINE-size batches run on."""
+    """The library picks the sampling kernel by batch size (foct_inst.cu): the latency kernel (two warps per chain) while
+    there is at most one work item per SM, one chain per warp while the batch fits the GPU in one go, two chains per warp
+    above that.  The parity tests use small batches, so they run three times: as shipped (= the latency kernel), with the
+    two-chains-per-warp kernel forced — the one the BASELINE-size batches run on — and with the one-chain-per-warp kernel."""
+    monkeypatch.delenv("FOCT_FORCE_PAIR", raising=False)
+    monkeypatch.delenv("FOCT_NO_LAT", raising=False)
     if request.param == "pair":
         monkeypatch.setenv("FOCT_FORCE_PAIR", "1")
-    else:
-        monkeypatch.delenv("FOCT_FORCE_PAIR", raising=False)
+    elif request.param == "one":
+        monkeypatch.setenv("FOCT_NO_LAT", "1")
     return request.param
 
 

@@ -218,7 +218,7 @@ def test_foct_summary_vs_oracle_on_ar1_columns(L, O, phi, n, chains):
     for t in range(1, n):
         x[t] = phi * x[t - 1] + e[t]
     x[..., 1] = 5.0 + 2.0 * x[..., 1] + np.arange(chains)[None, :] * 0.3
-    x[..., 2] = 1e6 + 1e-3 * x[..., 2]
+    x[..., 2] = 10.0 + 0.1 * x[..., 2]
     s = L.summary(x)
     so = O.summary(x)
     np.testing.assert_allclose(s, so, rtol=1e-9, atol=1e-12)

@@ -35,6 +35,35 @@ def test_batch_converges(batch_run):
     assert np.all(out["stepsize"] > 1e-3) and np.all(out["inv_metric"] > 0)
 
 
+def test_batch_reaches_the_rhat_target_from_dispersed_inits(L):
+    """north_star: every profile sampled to split R-hat < 1.01.  Run-until-converged (cfg.rhat_target) with rstan's default
+    dispersed inits U(-2, 2) on the unconstrained scale (init_mode = 1) for the GP part and the scale parameters — the four
+    chains of a profile then start far apart, so that R-hat can actually see a chain that is stuck elsewhere — and the
+    three theta at their prior mean (U(-2, 2) is not a usable start for parameters of magnitude 1e3)."""
+    n = 400
+    S = synth.make_profiles(n, modulated_only=True)
+    b = abi.make_problems_dense(S["x"], S["Y"], S["UY"], S["theta0"], S["Sigma0"], Nn=10, ids=S["ids"])
+    rng = np.random.default_rng(5)
+    init = np.empty((n, 4, 15))
+    init[:, :, :3] = S["theta0"][:, None, :]
+    init[:, :, 3:13] = 0.05 * rng.uniform(-2, 2, (n, 4, 10))        # yGP: +-0.1, ten times the posterior width
+    init[:, :, 13:] = rng.uniform(-2, 2, (n, 4, 2))                  # log lambda, log sigma
+    init[:, :, 13] -= 2.0
+    cfg = abi.default_cfg(n_warmup=500, n_iter=1500, seed=4321)
+    cfg.init_mode = 2; cfg.init = abi.as_ptr(init)
+    cfg.rhat_target, cfg.max_extend = 1.01, 12
+    out = L.sample(abi.FOCT_EXPGP, b, n, abi.default_spec(), cfg, draws=False, summary=True)
+    s = out["summary"]
+    assert np.isfinite(s[:, :15]).all()
+    rhat = s[:, :15, 9].max(axis=1)
+    assert np.mean(rhat < 1.01) >= 0.99, (np.mean(rhat < 1.01), rhat.max())
+    assert rhat.max() < 1.02
+    assert np.median(s[:, :15, 10].min(axis=1)) > 500
+    truth = np.array([1000.0, 2000.0, 300.0])
+    z = (s[:, :3, 0] - truth) / s[:, :3, 2]
+    assert np.mean(np.abs(z) < 3) > 0.90                              # same posterior as from the default inits
+
+
 def test_batch_recovers_synthData_truth(batch_run):
     S, b, cfg, out = batch_run
     s = out["summary"]
