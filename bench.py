@@ -320,7 +320,7 @@ def main():
                 "grad_per_s": float(smf[3]) / float(mxf[0]), "gpu_launches": int(F["launches"])}
 
     # ---------------- e2e: host buffers through foct_sample (H2D + D2H inside the timed region)
-    e2e = e2e_draws = None
+    e2e = e2e_draws = single = None
     if not args.no_e2e:
         D, P_out = abi.dims(abi.FOCT_EXPGP, args.nn)
         h2d = n * (3 * 481 * 8 + 200)
@@ -347,6 +347,16 @@ def main():
         # the reference contract returns the draws (plotExpGP.R:44-47): the same call shipping them and the sampler
         # parameters to the host as well
         Td, d_all = timed_e2e(1, True)
+        # BASELINE configs[1]: ONE profile x 4 chains through the same call with host buffers - what FitOCT.R's loop
+        # submits per Courbe.csv (FitOCT.R:110-124); runs on the latency kernel (two warps per chain)
+        if rank == 0:
+            one = abi.make_problems_dense(S["x"], S["Y"][:1], S["UY"][:1], S["theta0"][:1], S["Sigma0"][:1], Nn=args.nn, ids=S["ids"][:1])
+            L.sample(abi.FOCT_EXPGP, one, 1, spec, cfg, draws=True, summary=True)
+            t0 = time.perf_counter()
+            o1 = L.sample(abi.FOCT_EXPGP, one, 1, spec, cfg, draws=True, summary=True)
+            t1 = time.perf_counter() - t0
+            single = {"wall_s": t1, "leapfrogs": float(o1["n_leapfrog"].sum()), "min_bulk_ess": float(np.nanmin(o1["summary"][0, : args.nn + 5, 10])),
+                      "rhat_max": float(np.nanmax(o1["summary"][0, : args.nn + 5, 9])), "kernel": "nuts_lat_kernel (two warps per chain)"}
         e2e_draws = {"value": d_all / Td, "unit": UNIT, "ms_per_step": 1e3 * Td, "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": d2h + n * chains * n_post * (P_out + 6) * 8}
 
@@ -431,7 +441,7 @@ def main():
                         "profiles_continued_per_step": ext_all / (world * args.steps),
                         "mean_min_bulk_ess_per_profile": ess_all / (world * n * args.steps)},
             "until_converged": conv,
-            "clocks": clk, "e2e": e2e, "e2e_with_draws": e2e_draws, "gpu_launches": int(R["launches"]),
+            "clocks": clk, "e2e": e2e, "e2e_with_draws": e2e_draws, "single_profile": single, "gpu_launches": int(R["launches"]),
             "wall_s_timed_region": t_wall,
         }
         if inlib is not None:

@@ -494,15 +494,23 @@ __device__ __forceinline__ void sweep_points(const double* __restrict__ pp0, dou
 #ifndef FOCT_PREFETCH
 #define FOCT_PREFETCH 1
 #endif
+#ifndef FOCT_CX_AHEAD_MAXNN
+#define FOCT_CX_AHEAD_MAXNN 9
+#endif
 template <int NN, int KP, int ZI, bool CXG>
 __device__ __forceinline__ void sweep_points_pf(const double* __restrict__ pp, const double* __restrict__ pgc,
                                                 const double* __restrict__ pgn, double th1, double th2, double th3,
-                                                const double (&yg)[NN], double (&acc)[KP], double2 (&bb)[NN]) {
+                                                const double (&yg)[NN], double (&acc)[KP], double2 (&bb)[NN], double2& cxn) {
   constexpr int U = 2;
-  // CXG: the depth row c x is the same for every profile of the batch, so it is read from the shared blob (current block
-  // `pgc`) like the basis rows, and only y | w are staged per warp: 8 KB instead of 12 KB of shared memory per warp
+  // CXG: the depth row c x is the same for every profile of the batch, so it is read from the shared blob like the basis
+  // rows, and only y | w are staged per warp: 8 KB instead of 12 KB of shared memory per warp.  With few control points the
+  // iteration is too short to cover the load between its head and the use of c x (Nn = 5 lost 13 %): there the pair is
+  // requested one iteration ahead like the basis rows (`cxn`, 4 more registers live across the iteration); from
+  // FOCT_CX_AHEAD_MAXNN + 1 control points on the dot products of the A phase cover it and the registers are not there.
+  constexpr bool AHEAD = CXG && NN <= FOCT_CX_AHEAD_MAXNN;
   double2 c2g;
-  if constexpr (CXG) c2g = __ldg(reinterpret_cast<const double2*>(pgc));
+  if constexpr (AHEAD) c2g = cxn;
+  else if constexpr (CXG) c2g = __ldg(reinterpret_cast<const double2*>(pgc));
   double dl0[U], dl1[U], cx[U], y[U], ws[U], r[U], t[U], a[U], x0[U], e0[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) { dl0[u] = 1.0; dl1[u] = 0.0; }  // s = 1 + dL: the 1 rides in the first partial sum
@@ -587,6 +595,7 @@ __device__ __forceinline__ void sweep_points_pf(const double* __restrict__ pp, c
     bb[k] = __ldg(reinterpret_cast<const double2*>(pgn + (3 + k) * 32));
     if (k + 1 < NN) bb[k + 1] = __ldg(reinterpret_cast<const double2*>(pgn + (4 + k) * 32));
   }
+  if constexpr (AHEAD) cxn = __ldg(reinterpret_cast<const double2*>(pgn));
 }
 
 // Two warps per chain (TEAM = 2, the latency kernel of small batches: nuts_lat_kernel).  Both warps of a team execute the
@@ -734,11 +743,13 @@ __device__ __forceinline__ Eval warp_logp_grad(const double* __restrict__ blob, 
         double2 bb[NN];
 #pragma unroll
         for (int k = 0; k < NN; ++k) bb[k] = __ldg(reinterpret_cast<const double2*>(pg + (3 + k) * 32));
+        double2 cxn = make_double2(0.0, 0.0);
+        if constexpr (GB == 2 && NN <= FOCT_CX_AHEAD_MAXNN) cxn = __ldg(reinterpret_cast<const double2*>(pg));
 #pragma unroll 1
         for (; pass < npass; ++pass, pp += ROWS * 32) {
           const double* pgc = pg;
           if (pass + 1 < npass) pg += GROWS * 32;  // the last iteration re-requests its own block: harmless, stays in bounds
-          sweep_points_pf<NN, KP, ZI, GB == 2>(pp, pgc, pg, th1, th2, th3, yg, acc, bb);
+          sweep_points_pf<NN, KP, ZI, GB == 2>(pp, pgc, pg, th1, th2, th3, yg, acc, bb, cxn);
         }
       } else {
         if (U16 > 2) {

@@ -422,9 +422,10 @@ static cudaError_t launch_nuts_mod(int grid, int block, size_t smem, cudaStream_
   // At most one work item per SM: the latency kernel (two warps per chain, one CTA per SM).  FOCT_NO_LAT=1: A/B runs and
   // the tests that pin the one-chain-per-warp kernel.
   if (grid <= sm_count() && !std::getenv("FOCT_NO_LAT")) {
-    e = cudaFuncSetAttribute(nuts_lat_kernel<NN, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem_blob = K.blob_stride * sizeof(double);  // (the latency kernel stages whole blobs whatever `smem` says)
+    e = cudaFuncSetAttribute(nuts_lat_kernel<NN, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blob);
     if (e == cudaSuccess) {
-      nuts_lat_kernel<NN, MOD><<<grid, 2 * block, smem, st>>>(K);
+      nuts_lat_kernel<NN, MOD><<<grid, 2 * block, smem_blob, st>>>(K);
       return cudaGetLastError();
     }
     cudaGetLastError();  // (a blob that leaves no room for the team buffers: the one-chain-per-warp kernel below)
@@ -483,6 +484,9 @@ static cudaError_t nuts_occupancy(int mod, int chains, long long n_items, int n_
   // geometry of the one-chain-per-warp kernel: what a batch must exceed to be worth two chains per warp
   *block = nuts_block<NN>(chains, false);
   int one_bpsm = 0, one_regs = 0;
+  // (Staging c x | y | w only and reading the basis rows through L1, as the two-chains-per-warp kernels do, was measured
+  // on this kernel too: Nn = 15 1.94e8 against 1.98e8 gradients/s, Nn = 20 1.41e8 against 1.53e8, Nn = 10 2.26e8 against
+  // 2.32e8 - a warp that owns its chain reads 32 distinct points per row, and LDS serves that better than L1.  Removed.)
   cudaError_t e = mod == 0 ? occupancy_of(nuts_kernel<NN, 0>, *block, *smem, &one_bpsm, &one_regs)
                            : occupancy_of(nuts_kernel<NN, 1>, *block, *smem, &one_bpsm, &one_regs);
   if (e != cudaSuccess) {
@@ -515,7 +519,7 @@ static cudaError_t nuts_occupancy(int mod, int chains, long long n_items, int n_
             *warp_units = 2;
             *block = 64;
             *smem = 2 * (FOCT_CX_SHARED ? smem_rows / 3 * 2 : smem_rows);  // per warp: y | w (c x is shared too), or c x | y | w
-            if (FOCT_CX_SHARED) *smem += (size_t)FOCT_STACK_SMEM * 64 * 7 * sizeof(double);  // the busiest levels of the subtree stacks
+            if (FOCT_CX_SHARED) *smem += (size_t)FOCT_STACK_SMEM_LEVELS(NN) * 64 * 7 * sizeof(double);  // the busiest levels of the subtree stacks
             return mod == 0 ? occupancy_of(nuts2w_kernel<NN, 0>, *block, *smem, blocks_per_sm, regs)
                             : occupancy_of(nuts2w_kernel<NN, 1>, *block, *smem, blocks_per_sm, regs);
           }

@@ -55,6 +55,10 @@ __device__ __forceinline__ bool merge_persists_w(double invM, double i_rho, doub
 #ifndef FOCT_STACK_SMEM
 #define FOCT_STACK_SMEM 1
 #endif
+// Below seven control points ptxas answers the shared-memory stack with a schedule that runs the two points of a sweep
+// iteration one after the other instead of interleaved (scripts/sass_sched.py: rcp at [9, 44] instead of [16, 23]; Nn = 5
+// measured 13 % slower), so those instantiations keep the whole stack in local memory.
+#define FOCT_STACK_SMEM_LEVELS(NN) ((NN) >= 7 ? FOCT_STACK_SMEM : 0)
 #define FOCT_PAIR_STATE_DOUBLES (FOCT_PAIR_N_DOUBLES + (FOCT_PAIR_N_INTS + 1) / 2 + 6 * FOCT_STACK_LEVELS)
 
 // lane32 = lane in the warp; this half's chain is `chain` (>= K.chains: the half has no chain and only keeps the other
@@ -140,7 +144,7 @@ __device__ int run_pair(const SamplerParams& K, const DevProblem& P, const doubl
   // The lowest levels are the busy ones (level k is written and read once per 2^(k+1) leaves): nuts2w_kernel keeps the
   // first FOCT_STACK_SMEM of them in shared memory (7 doubles per thread and level: 6 used, an odd word stride), the rest
   // stays in local memory.  75 % of the stack traffic of a leaf then neither misses L1 nor evicts the basis rows from it.
-  constexpr int SL = GB == 2 ? FOCT_STACK_SMEM : 0;
+  constexpr int SL = GB == 2 ? FOCT_STACK_SMEM_LEVELS(NN) : 0;
   double* const sst = SL > 0 ? stack_smem + threadIdx.x * 7 : nullptr;
   const int SST = (int)blockDim.x * 7;
 #define ST_LD(arr, row, k) ((SL > 0 && (k) < SL) ? sst[(k) * SST + (row)] : arr[k])

@@ -201,3 +201,13 @@ estimateExpPrior <- function(x, uy, dataType, priorType = "mono", out, ru_theta 
         as.integer(priorType == "abc"), as.numeric(out$best.theta), as.numeric(fit$hessian), as.numeric(ru_theta),
         PACKAGE = "FitOCTb200")
 }
+
+# rstan's summary(fit)$summary / monitor() for draws the caller holds (an [iterations, chains, parameters] array, the
+# shape of as.array(stanfit)): mean, se_mean, sd, quantiles, n_eff, Rhat, Bulk_ESS on the device (foct_summary).
+summaryDraws <- function(draws) {
+  stopifnot(length(dim(draws)) == 3, dim(draws)[1] >= 4)
+  d <- dim(draws)
+  s <- .Call("foct_R_summary", as.numeric(aperm(draws, c(3, 2, 1))), as.integer(d[1]), as.integer(d[2]), PACKAGE = "FitOCTb200")
+  dimnames(s) <- list(dimnames(draws)[[3]], c("mean", "se_mean", "sd", "2.5%", "25%", "50%", "75%", "97.5%", "n_eff", "Rhat", "Bulk_ESS"))
+  s
+}

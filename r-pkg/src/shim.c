@@ -197,6 +197,28 @@ SEXP foct_R_predict(SEXP kind_, SEXP x, SEXP y, SEXP uy, SEXP ctl, SEXP draws) {
   return out;
 }
 
+/* .Call("foct_R_summary", draws, n_draws, chains) -> [n_cols, 11] matrix: rstan's summary(fit)$summary / monitor() for
+ * caller-supplied draws (plotExpGP.R:9-11 and server.R:88-104 read that table), computed by the kernel that summarises
+ * a fit on the device.  draws: numeric of length n_draws * chains * n_cols in the order of foct_result.draws
+ * (column fastest, then chain, then draw). */
+SEXP foct_R_summary(SEXP draws, SEXP n_draws_, SEXP chains_) {
+  const int n = Rf_asInteger(n_draws_), c = Rf_asInteger(chains_);
+  if (n < 4 || c < 1 || XLENGTH(draws) < (R_xlen_t)n * c || XLENGTH(draws) % ((R_xlen_t)n * c))
+    Rf_error("fitoct_b200: draws must hold n_draws * chains * n_cols values, n_draws >= 4");
+  const int p = (int)(XLENGTH(draws) / ((R_xlen_t)n * c));
+  SEXP tmp = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)p * FOCT_N_SUMMARY_COLS));
+  const int rc = foct_summary(REAL(draws), 1, n, c, p, REAL(tmp));
+  if (rc) {
+    UNPROTECT(1);
+    Rf_error("fitoct_b200 error %d: %s", rc, foct_last_error());
+  }
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, p, FOCT_N_SUMMARY_COLS)); /* column-major for R */
+  for (int i = 0; i < p; ++i)
+    for (int k = 0; k < FOCT_N_SUMMARY_COLS; ++k) REAL(out)[(R_xlen_t)k * p + i] = REAL(tmp)[(R_xlen_t)i * FOCT_N_SUMMARY_COLS + k];
+  UNPROTECT(2);
+  return out;
+}
+
 /* .Call("foct_R_pipeline", xs, ys, ctl, devices) — the body of FitOCT.R's dataset loop (FitOCT.R:84-124) for ALL
  * datasets in one call: estimateNoise -> fitMonoExp -> printBr gate -> estimateExpPrior -> fitExpGP(method='sample') on
  * the profiles the gate lets through.  ctl carries ctrlParams.yaml's keys (smooth_df, priorType, ru_theta, Nn, gridType,
@@ -441,6 +463,7 @@ static const R_CallMethodDef call_methods[] = {
     {"foct_R_sample", (DL_FUNC)&foct_R_sample, 5},
     {"foct_R_sample_batch", (DL_FUNC)&foct_R_sample_batch, 6},
     {"foct_R_predict", (DL_FUNC)&foct_R_predict, 6},
+    {"foct_R_summary", (DL_FUNC)&foct_R_summary, 3},
     {"foct_R_pipeline", (DL_FUNC)&foct_R_pipeline, 4},
     {"foct_R_monoexp_map", (DL_FUNC)&foct_R_monoexp_map, 4},
     {"foct_R_expgp_map", (DL_FUNC)&foct_R_expgp_map, 4},

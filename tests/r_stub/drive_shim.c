@@ -12,6 +12,7 @@
 SEXP foct_R_sample_batch(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 SEXP foct_R_sample(SEXP, SEXP, SEXP, SEXP, SEXP);
 SEXP foct_R_predict(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+SEXP foct_R_summary(SEXP, SEXP, SEXP);
 SEXP foct_R_pipeline(SEXP, SEXP, SEXP, SEXP);
 
 static SEXP num(double v) { SEXP s = Rf_allocVector(REALSXP, 1); REAL(s)[0] = v; return s; }
@@ -107,6 +108,20 @@ int main(int argc, char** argv) {
     rmax = fmax(rmax, fabs(REAL(VECTOR_ELT(ys, 0))[i] - m - r));
   }
   printf("PREDICT n %ld max|y-m-resid| %.3g\n", (long)XLENGTH(get(gq, "m")), rmax);
+
+  /* ---- 3b. summary(fit)$summary of the draws just returned, through foct_R_summary: equals the summary of the fit */
+  const int n_post = nb_iter - nb_warmup;                      /* the fit's summary covers the post-warm-up draws */
+  SEXP post = Rf_allocVector(REALSXP, (R_xlen_t)n_post * chains * P_out);
+  memcpy(REAL(post), REAL(d1) + (size_t)nb_warmup * chains * P_out, (size_t)n_post * chains * P_out * sizeof(double));
+  SEXP sm = foct_R_summary(post, num(n_post), num(chains));
+  SEXP s1 = get(one, "summary");
+  double smax = 0.0;
+  for (int i = 0; i < P_out; ++i)
+    for (int k = 0; k < 11; ++k) {
+      const double a = REAL(sm)[(size_t)k * P_out + i], b = REAL(s1)[(size_t)i * 11 + k];
+      if (a == a || b == b) smax = fmax(smax, fabs(a - b) / (fabs(b) + 1e-300));
+    }
+  printf("SUMMARY rows %ld max_rel_diff %.3g\n", (long)(XLENGTH(sm) / 11), smax);
 
   /* ---- 4. the loop body of FitOCT.R:84-124 for all profiles in one call */
   const char* pn[] = {"dataType", "Nn", "smooth_df", "priorType", "ru_theta", "rho_scale", "lambda_rate", "nb_warmup", "nb_iter",

@@ -52,6 +52,8 @@ def test_shim_batch_progress_interrupt_pipeline(tmp_path, L):
     assert "SINGLE equals_batch_profile0 1" in out
     m = re.search(r"PREDICT n (\d+) max\|y-m-resid\| (\S+)", out)
     assert m and int(m.group(1)) == 2 * 481 and float(m.group(2)) < 1e-9
+    m = re.search(r"SUMMARY rows (\d+) max_rel_diff (\S+)", out)
+    assert m and int(m.group(1)) == 17 and float(m.group(2)) == 0.0   # foct_R_summary of the draws == the fit's own summary
     # 5. the FitOCT.R loop body in one call
     m = re.search(r"PIPELINE n_expgp (\d+) uy_len (\d+) mono_theta (\S+) (\S+) (\S+)", out)
     assert m and int(m.group(1)) == 3 and int(m.group(2)) == 3 * 481 and abs(float(m.group(5)) - 300) < 60
