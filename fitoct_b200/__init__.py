@@ -7,7 +7,7 @@ use; there is no CPU fallback.
 from ._abi import (FOCT_EXPGP, FOCT_MONOEXP, default_cfg, default_spec, make_problems, make_problems_dense,  # noqa: F401
                    param_names)
 
-__all__ = ["fitExpGP", "fitMonoExp", "fitExpGP_batch", "StanFit", "load_ctrl_params"]
+__all__ = ["fitExpGP", "fitMonoExp", "fitExpGP_batch", "StanFit", "load_ctrl_params", "monitor"]
 
 
 def __getattr__(name):

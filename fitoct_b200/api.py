@@ -107,6 +107,19 @@ class StanFit:
                           f"warmup={self.n_warmup}", head] + rows)
 
 
+def monitor(draws, par_names=None) -> dict:
+    """rstan::monitor(sims) / summary(fit)$summary for draws the caller holds: an [iterations, chains, parameters] array
+    (the shape of as.array(stanfit)), post-warm-up.  Computed on the device by the kernel that summarises a fit
+    (foct_summary); the table a merged or thinned stanfit needs again (server.R:88-104)."""
+    d = np.asarray(draws, dtype=np.float64)
+    if d.ndim != 3:
+        raise ValueError("draws must be [iterations, chains, parameters]")
+    names = list(par_names) if par_names is not None else [f"V{i + 1}" for i in range(d.shape[2])]
+    if len(names) != d.shape[2]:
+        raise ValueError("one name per parameter")
+    return {"rownames": names, "colnames": list(abi.SUMMARY_COL_NAMES), "summary": L.summary(d)}
+
+
 def _grid_code(gridType):
     if isinstance(gridType, str):
         if gridType not in ("internal", "extremal"):

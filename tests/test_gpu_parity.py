@@ -225,6 +225,10 @@ def test_foct_summary_vs_oracle_on_ar1_columns(L, O, phi, n, chains):
     assert np.all(np.isfinite(s[:, 8])) and np.all(s[:, 8] > 0) and np.all(np.isfinite(s[:, 1]))
     both = L.summary(np.stack([x, x[::-1]]))
     np.testing.assert_array_equal(both[0], s)
+    from fitoct_b200 import api
+    m = api.monitor(x, par_names=["a", "b", "c"])
+    np.testing.assert_array_equal(m["summary"], s)
+    assert m["rownames"] == ["a", "b", "c"] and m["colnames"][8:10] == ["n_eff", "Rhat"]
 
 
 def test_map_and_predict_vs_oracle(L, O):
