@@ -246,6 +246,35 @@ def test_prep_edge_cases(L, O):
         L.print_br(abi.FOCT_EXPGP, tiny, 1, abi.default_spec(abi.FOCT_EXPGP), np.array([1.0]))           # ... N - 3 - Nn < 1 is not
 
 
+def test_pipeline_survives_degenerate_profiles(L):
+    """One bad Courbe.csv must not abort the directory (FitOCT.R:74-84 loops over files independently): a constant signal
+    (no decay to fit: the MonoExp Hessian is singular) and a profile of pure noise ride in a batch of good ones.  The call
+    succeeds, every profile gets a status, the good ones are fitted exactly as they are without the bad ones."""
+    S = synth.make_profiles(6, modulated_only=True)
+    Y = S["Y"].copy()
+    Y[1] = 1234.5                                                    # constant
+    Y[4] = 1000.0 + np.random.default_rng(8).standard_normal(Y.shape[1])   # noise around a constant
+    dummy = np.ones_like(Y)
+    th = np.tile([0.0, 0.0, 1.0], (6, 1)); S0 = np.tile(np.eye(3), (6, 1, 1))
+    b = abi.make_problems_dense(S["x"], Y, dummy, th, S0, Nn=0, ids=S["ids"])
+    cfg = abi.default_cfg(chains=2, n_warmup=60, n_iter=120, seed=5)
+    out = L.pipeline(b, 6, L.pipeline_cfg(gate=1, Nn=6), cfg)
+    st = out["status"]
+    assert set(st.tolist()) <= {0, 1, 2, 3} and np.all(st[[0, 2, 3, 5]] == 0)      # the modulated profiles are sampled
+    assert st[1] in (1, 2, 3) and st[4] in (1, 2, 3)
+    k = out["n_expgp"]
+    assert k == int(np.sum((st == 0) | (st == 2))) and sorted(out["expgp_index"].tolist()) == sorted(np.flatnonzero((st == 0) | (st == 2)).tolist())
+    good = [i for i, j in enumerate(out["expgp_index"]) if st[j] == 0]
+    assert np.all(np.isfinite(out["expgp"]["summary"][good][:, :11, 0]))
+    # the good profiles alone: bit-identical fits (a profile's draws depend on its id, not on its neighbours)
+    keep = [0, 2, 3, 5]
+    b2 = abi.make_problems_dense(S["x"], Y[keep], dummy[keep], th[keep], S0[keep], Nn=0, ids=S["ids"][keep])
+    out2 = L.pipeline(b2, 4, L.pipeline_cfg(gate=1, Nn=6), cfg)
+    assert np.all(out2["status"] == 0)
+    sel = [list(out["expgp_index"]).index(j) for j in keep]
+    np.testing.assert_array_equal(out["expgp"]["summary"][sel], out2["expgp"]["summary"])
+
+
 def test_pripost_flow_prior_predictive_known_answers(L):
     """priPost.R:2-16: the same call with prior_PD = 1 samples the prior.  (a) the three-parameter model with the MVN prior
     switched on is a pure Gaussian target with known moments; (b) for fitExpGP the prior of (yGP, lambda) is a funnel that
