@@ -425,6 +425,20 @@ static cudaError_t launch_nuts_mod(int grid, int block, size_t smem, cudaStream_
     const size_t smem_blob = K.blob_stride * sizeof(double);  // (the latency kernel stages whole blobs whatever `smem` says)
     e = cudaFuncSetAttribute(nuts_lat_kernel<NN, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blob);
     if (e == cudaSuccess) {
+      // Few enough (profile, chain) pairs for a CTA - an SM - per chain: the four chains of a single profile run on four
+      // SMs, every warp with a scheduler to itself (measured: 0.78 s against 0.95 s with the four chains on one SM);
+      // else two chains per CTA (four warps = one per scheduler) while that still gives every CTA its own SM.
+      const long long chain_items = (long long)K.n_problems * K.chains, pair_items = (long long)K.n_problems * ((K.chains + 1) / 2);
+      if (chain_items <= sm_count() && K.chains > 1 &&
+          cudaFuncSetAttribute(nuts_lat_kernel<NN, MOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blob) == cudaSuccess) {
+        nuts_lat_kernel<NN, MOD, 1><<<(int)chain_items, 64, smem_blob, st>>>(K);
+        return cudaGetLastError();
+      }
+      if (pair_items <= sm_count() && K.chains > 2 &&
+          cudaFuncSetAttribute(nuts_lat_kernel<NN, MOD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blob) == cudaSuccess) {
+        nuts_lat_kernel<NN, MOD, 2><<<(int)pair_items, 128, smem_blob, st>>>(K);
+        return cudaGetLastError();
+      }
       nuts_lat_kernel<NN, MOD><<<grid, 2 * block, smem_blob, st>>>(K);
       return cudaGetLastError();
     }

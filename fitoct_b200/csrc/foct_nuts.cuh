@@ -448,16 +448,19 @@ __global__ void __launch_bounds__(32 * FOCT_CTA_CHAINS, NutsBounds<NN>::MINB) nu
 // or the continuation rounds of a few unconverged profiles).  Such a batch cannot fill the GPU; what counts is how fast
 // ONE chain advances.  Each chain gets a team of two warps (TeamCtx), the CTA an SM of its own, every thread 255
 // registers, and the sweep keeps four points in flight per lane (FOCT_UNROLL_LAT): 8 warps x 1 CTA per SM.
-template <int NN, int MOD>
-__global__ void __launch_bounds__(64 * FOCT_CTA_CHAINS, 1) nuts_lat_kernel(const SamplerParams K) {
+// CPC = chains per CTA: FOCT_CTA_CHAINS (an item is a profile's group of <= 4 chains, as in nuts_kernel), or 1 when even
+// (profile, chain) items number at most one per SM - the single profile of FitOCT.R's loop then spreads its four chains
+// over four SMs and every warp has a scheduler to itself.  The arithmetic of a chain is the same in both.
+template <int NN, int MOD, int CPC = FOCT_CTA_CHAINS>
+__global__ void __launch_bounds__(64 * CPC, 1) nuts_lat_kernel(const SamplerParams K) {
   extern __shared__ __align__(128) double smem[];
   __shared__ uint64_t mbar;
   __shared__ int s_next;
   __shared__ DevProblem s_prob;
-  __shared__ double s_xch[FOCT_CTA_CHAINS][2 * 64];
-  __shared__ int s_flag[FOCT_CTA_CHAINS];
+  __shared__ double s_xch[CPC][2 * 64];
+  __shared__ int s_flag[CPC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, slot = warp >> 1;
-  const int groups = (K.chains + FOCT_CTA_CHAINS - 1) / FOCT_CTA_CHAINS;
+  const int groups = (K.chains + CPC - 1) / CPC;
   const int n_items = K.n_problems * groups;
   fill_exptab();
   mbar_init(&mbar);
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__(64 * FOCT_CTA_CHAINS, 1) nuts_lat_kernel(const
     __syncthreads();
     const int w = s_next;
     if (w >= n_items) break;
-    const int j = K.order ? K.order[w / groups] : w / groups, chain = (w % groups) * FOCT_CTA_CHAINS + slot;
+    const int j = K.order ? K.order[w / groups] : w / groups, chain = (w % groups) * CPC + slot;
     if (threadIdx.x == 0) s_prob = K.probs[j];
     stage_blob_tma(smem, K.blobs + (size_t)j * K.blob_stride, (uint32_t)(K.blob_stride * sizeof(double)), &mbar, phase, threadIdx.x == 0);
     __syncthreads();
