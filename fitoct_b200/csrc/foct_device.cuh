@@ -1,8 +1,9 @@
 // foct_device.cuh — device-side building blocks: Philox, warp reductions, the fused fp64
 // log-density + analytic-gradient sweep (MODEL_SPEC §3-5, SURVEY a-4/a-5).
 //
-// Layout contract: one warp owns one chain; lane d (< D) owns component d of every
-// D-vector (q, p, grad, rho, ...); warp-uniform scalars are held redundantly by all lanes.  The profile
+// Layout contract: a lane group owns one chain - a warp (nuts_kernel), half a warp (nuts2*_kernel: two
+// chains per warp) or a team of two warps that both hold the whole state (nuts_lat_kernel); lane d (< D) of the group owns
+// component d of every D-vector (q, p, grad, rho, ...); group-uniform scalars are held redundantly by all lanes.  The profile
 // lives in shared memory as a "blob" of npass = Npad/32 pass blocks; block j holds, for points 32j..32j+31,
 // the rows cx | y | w | B_0 .. B_{NN-1}, 32 doubles each, so that one warp pass reads every operand at a
 // compile-time offset from a single per-lane pointer (conflict-free LDS.64, no address arithmetic).

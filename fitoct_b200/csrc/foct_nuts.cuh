@@ -46,7 +46,7 @@ struct SamplerParams {
   const int* slot_of;       // [..] draw block of profile j (nullptr: j)
   // ---- progress and cancellation (foct_plan_query / foct_plan_cancel / foct_sample_cb; SURVEY §8b: R polls and calls
   //      R_CheckUserInterrupt between polls, server.R:457-472 scrapes the progress)
-  int shared_basis;              // every profile has the same depth grid: 1 = basis rows read through L1 from blob 0, 2 = from the CTA's copy in shared memory
+  int shared_basis;              // every profile has the same depth grid (and dataType): the basis rows - in nuts2w_kernel c x too - are read through L1 from blob 0
   unsigned long long* progress;  // chain-iterations completed so far, or nullptr
   const int* cancel;             // != 0: every chain stops at its next iteration boundary, or nullptr
   // ---- time slicing of the work items (nuts2_kernel; all nullptr / 0: off)
