@@ -44,6 +44,35 @@ __global__ void __launch_bounds__(128) logp_kernel(const LogpParams K) {
         __syncthreads();
         continue;
       }
+      if constexpr (NN > 0) {
+        if (K.width == 17) {
+          // the evaluation of nuts2w_kernel, the kernel of BASELINE-size batches: half-warps, only y | w in the staged
+          // rows (copied behind the blob), c x and the basis rows through L1 from the profile's blob in global memory,
+          // software-pipelined sweep (sweep_points_pf) where the model has one (length modulation)
+          double* rows = smem + K.blob_stride;
+          for (int e = threadIdx.x; e < 2 * K.npad; e += blockDim.x) {
+            const int blk = e / 64, r = (e % 64) / 32, i = e % 32;
+            rows[e] = smem[(size_t)blk * (3 + NN) * 32 + (1 + r) * 32 + i];
+          }
+          __syncthreads();
+          const double* gb = K.blobs + (size_t)j * K.blob_stride;
+          const int l = lane & 15, half = lane >> 4;
+          for (int base = 0; base < K.n_q; base += 2 * nwarp) {
+            const int iq = base + 2 * warp + half;
+            const bool ok = iq < K.n_q;
+            const size_t r = (size_t)j * K.n_q + (ok ? iq : 0);
+            const double qd = ok && l < D ? K.q[r * D + l] : 0.0;
+            const Eval ev = warp_logp_grad<NN, MOD, 16, 2>(rows, s_prob, K.spec, qd, l, gb);
+            if (ok && l < D) K.grad[r * D + l] = ev.g;
+            if (ok && l == 0) {
+              K.lp[r] = ev.lp;
+              if (K.chi2) K.chi2[r] = ev.chi2;
+            }
+          }
+          __syncthreads();
+          continue;
+        }
+      }
     }
     for (int iq = warp; iq < K.n_q; iq += nwarp) {
       const size_t r = (size_t)j * K.n_q + iq;

@@ -23,7 +23,7 @@ struct LogpParams {
   double* lp;    // [n_problems][n_q]
   double* grad;  // [n_problems][n_q][D]
   double* chi2;  // [n_problems][n_q] or nullptr
-  int width;     // lanes per evaluation: 16 = the half-warp path of the two-chains-per-warp sampler (D <= 16), else 32
+  int width;     // evaluation layout: 16 = half-warps on a staged blob (D <= 16), 17 = half-warps in nuts2w_kernel's shared-basis layout, else full warps
 };
 
 struct MapParams {

@@ -779,12 +779,16 @@ extern "C" int foct_logp_grad(int kind, const foct_problem* P, int n, const foct
     LogpParams K;
     K.blobs = d_blobs; K.blob_stride = stride; K.npad = npad; K.probs = d_probs; K.n_problems = n;
     K.spec = dev_spec(*spec); K.q = d_q; K.n_q = n_q; K.lp = d_lp; K.grad = d_g; K.chi2 = d_c2;
-    {  // the parity hook exercises the evaluation the sampler uses: half-warps for D <= 16 (FOCT_LOGP_WIDTH=32: full warps)
+    {  // the parity hook exercises the evaluations the samplers use.  D <= 16: half-warps on a staged blob (default, the
+       // pair kernels on ragged grids), FOCT_LOGP_WIDTH=17: half-warps in the shared-basis layout of nuts2w_kernel (the kernel
+       // of BASELINE-size batches, software-pipelined sweep), FOCT_LOGP_WIDTH=32: full warps (one chain per warp / latency kernel)
       const char* wenv = std::getenv("FOCT_LOGP_WIDTH");
-      K.width = (wenv && std::atoi(wenv) == 32) ? 32 : 16;
+      const int w = wenv ? std::atoi(wenv) : 16;
+      K.width = (w == 32 || w == 17) ? w : 16;
     }
     const InstEntry* inst = inst_for(NN);
-    CUB(inst->launch_logp(spec->modulation, std::min(n, sm_count() * 4), 128, stride * sizeof(double), 0, K));
+    const size_t logp_smem = stride * sizeof(double) + (K.width == 17 ? (size_t)2 * npad * sizeof(double) : 0);
+    CUB(inst->launch_logp(spec->modulation, std::min(n, sm_count() * 4), 128, logp_smem, 0, K));
     CUB(cudaDeviceSynchronize());
     CUB(cudaMemcpy(lp, d_lp, nq * sizeof(double), cudaMemcpyDeviceToHost));
     CUB(cudaMemcpy(grad, d_g, nq * D * sizeof(double), cudaMemcpyDeviceToHost));

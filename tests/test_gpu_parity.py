@@ -27,7 +27,7 @@ def rand_q(rng, theta0, Nn, n_q, wide=False):
 
 
 @pytest.mark.parametrize("idx", range(7))
-def test_logp_grad_vs_golden(L, O, golden, idx):
+def test_logp_grad_vs_golden(L, O, golden, idx, logp_layout):
     """FROM RAW INPUTS (x, y, uy, q): the device builds its own grid and GP basis, and log density, gradient and chi2 must
     match the 50-digit restatement to 1e-12 (round 1 allowed 2e-8 here and reached 1e-12 only with the device basis
     substituted into the oracle; Kgg + jitter I has a condition number of ~40, not 1e9, so no allowance is needed)."""
@@ -64,9 +64,21 @@ def test_logp_grad_vs_golden(L, O, golden, idx):
                   worst_conditioned_err_grad=(np.abs(g[0] - g_ref) / (np.abs(g_ref) + at)).max())
 
 
+@pytest.fixture(params=["16", "17", "32"])
+def logp_layout(request, monkeypatch):
+    """foct_logp_grad evaluates through the layout a sampling kernel uses (FOCT_LOGP_WIDTH): half-warps on a staged blob
+    (16, the default: the pair kernels on ragged grids), half-warps in the shared-basis layout of nuts2w_kernel with its
+    software-pipelined sweep (17: the kernel BASELINE-size batches run on), full warps (32: one chain per warp and the
+    latency kernel).  D > 16 has the full-warp layout only."""
+    monkeypatch.setenv("FOCT_LOGP_WIDTH", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("Nn", [1, 5, 10, 11, 12, 15, 20, 25])
 @pytest.mark.parametrize("mod", [0, 1])
-def test_logp_grad_vs_oracle_random(L, O, Nn, mod):
+def test_logp_grad_vs_oracle_random(L, O, Nn, mod, logp_layout):
+    if Nn > 11 and logp_layout != "32":
+        pytest.skip("D > 16: full warps only")
     rng = np.random.default_rng(100 * Nn + mod)
     n = 3
     S = synth.make_profiles(n, first_id=Nn)
@@ -92,7 +104,7 @@ def test_logp_grad_vs_oracle_random(L, O, Nn, mod):
                       rel_err_lp=(np.abs(lp[j][ok] - lpo[ok]) / np.abs(lpo[ok])).max(), worst_plain_rel_err_grad=rel_plain.max())
 
 
-def test_logp_adversarial_points(L, O):
+def test_logp_adversarial_points(L, O, logp_layout):
     # SURVEY §8c ladder (1): tiny/huge sigma, dL -> -1 (theta3*s crosses zero => non-finite), x tail
     S = synth.make_profiles(1, first_id=1)
     Nn = 10
